@@ -1,0 +1,179 @@
+/* yoho_b200 — C ABI of the B200-native YOHO descriptor + registration hot path.
+ *
+ * The reference (HpWang-whu/YOHO) has NO FFI on this path: its boundary is a set of pure-Python plugin
+ * registries (name2network / name2extractor / name2matcher / name2estimator).  This header is
+ * the C boundary a maintainer binds underneath those Python classes (ctypes stub: INTEGRATION.md); every
+ * entry point names the reference function whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  Every data pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - return 0 on success, negative yoho_status otherwise; yoho_last_error() gives the message (thread-local).
+ *   - the context owns the packed weights, the group tables and a grow-only device workspace: steady-state
+ *     calls allocate nothing.  One context per (device, stream-of-use); calls on one context are not
+ *     re-entrant.
+ *   - tensor layouts at the boundary are the reference's own: group features [K,32,60] float32 with the
+ *     group axis innermost (tests/extractor.py:48,60), matches int64 [M,2], rotation index int64 [M],
+ *     keypoints float64 [K,3], transforms float64 [3,4] row-major.
+ *   - there is no CPU fallback anywhere: without a CUDA device every call returns YOHO_ERR_CUDA.
+ */
+#ifndef YOHO_B200_H
+#define YOHO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YOHO_ABI_VERSION 1
+#define YOHO_G 60      /* group order */
+#define YOHO_TAPS 13   /* group-convolution kernel support */
+#define YOHO_F 32      /* descriptor channels */
+
+typedef enum {
+    YOHO_OK = 0,
+    YOHO_ERR_CUDA = -1,        /* a CUDA runtime call failed / no device */
+    YOHO_ERR_ARG = -2,         /* bad argument */
+    YOHO_ERR_NOWEIGHTS = -3,   /* forward called before the matching *_load ("No model exists", tests/extractor.py:34,122) */
+    YOHO_ERR_ALLOC = -4
+} yoho_status;
+
+typedef struct yoho_ctx yoho_ctx;
+
+/* BatchNorm2d (eval mode) parameters, host float32[C] each; eps is the reference's 1e-5. */
+typedef struct {
+    const float* weight_host;
+    const float* bias_host;
+    const float* running_mean_host;
+    const float* running_var_host;
+} yoho_bn_host;
+
+/* Conv2d(C,O,(1,taps)) parameters in the reference's layout: weight [O,C,1,taps] float32, bias [O]. */
+typedef struct {
+    const float* weight_host;
+    const float* bias_host;
+} yoho_conv_host;
+
+/* PartI_test state-dict (utils/network.py:67-105; key names in SURVEY.md §8a). */
+typedef struct {
+    yoho_conv_host conv_in;       /* PartI_net.Conv_in.0                           32 -> 256 */
+    yoho_bn_host bn_a;            /* PartI_net.SO3_Conv_layers.0.comb_layer_in.0   256 */
+    yoho_conv_host conv_a;        /* ...comb_layer_in.2                            256 -> 512 */
+    yoho_bn_host bn_b;            /* ...comb_layer_out.0                           512 */
+    yoho_conv_host conv_b;        /* ...comb_layer_out.2                           512 -> 256 */
+    yoho_bn_host bn_out;          /* PartI_net.Conv_out.comb_layer.0               256 */
+    yoho_conv_host conv_out;      /* PartI_net.Conv_out.comb_layer.2               256 -> 32 */
+} yoho_part1_weights;
+
+/* PartII_test state-dict (utils/network.py:218-278). */
+typedef struct {
+    yoho_bn_host bn_init;         /* Conv_init.comb_layer.0                        128 */
+    yoho_conv_host conv_init;     /* Conv_init.comb_layer.2                        128 -> 256 */
+    yoho_bn_host bn_a;            /* PartII_SO3_Conv_layers.0.comb_layer_in.0      256 */
+    yoho_conv_host conv_a;        /* ...comb_layer_in.2                            256 -> 512 */
+    yoho_bn_host bn_b;            /* ...comb_layer_out.0                           512 */
+    yoho_conv_host conv_b;        /* ...comb_layer_out.2                           512 -> 256 */
+    yoho_conv_host fc1;           /* PartII_To_R_FC.0   [512,256,1,1] */
+    yoho_bn_host bn1;             /* PartII_To_R_FC.1   512 */
+    yoho_conv_host fc2;           /* PartII_To_R_FC.3   [128,512,1,1] */
+    yoho_bn_host bn2;             /* PartII_To_R_FC.4   128 */
+    yoho_conv_host fc3;           /* PartII_To_R_FC.6   [4,128,1,1] */
+} yoho_part2_weights;
+
+int yoho_abi_version(void);
+const char* yoho_last_error(void);
+
+/* A0 — group tables (utils/network.py:72-74,223-226; tests/extractor.py:67,110; tests/estimator.py:283-284).
+ * rotation_host float64[60*3*3], perm_host int32[60*60] (P[a][b]), nei_host int32[60*13] (N[g][k]). */
+int yoho_ctx_create(int device, const double* rotation_host, const int32_t* perm_host, const int32_t* nei_host,
+                    yoho_ctx** out);
+int yoho_ctx_destroy(yoho_ctx* ctx);
+
+/* Checkpoint packing: folds eval-mode BN into (scale, shift), reorders W[o,c,0,k] -> W_k[c][o], uploads.
+ * Replaces torch's load_state_dict for PartI_test / PartII_test (tests/extractor.py:26-34,113-122). */
+int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w);
+int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w);
+
+/* Implementation of the four group-convolution layers: 0 = FP32 SIMT (default), 1 = tcgen05 split-BF16. */
+int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
+
+/* A1-A6 — PartI_test.forward (utils/network.py:86-105,140-147) on B keypoints.
+ * x [B,32,60] -> eqv [B,32,60] (unit norm over channels per (b,g)), inv [B,32] (may be NULL),
+ * desc_mean [B,32] = mean_g eqv, the matcher's descriptor (tests/matcher.py:35-36; may be NULL). */
+int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* eqv, float* inv, float* desc_mean,
+                       void* stream);
+
+/* B1 — matcher descriptor from a stored eqv: np.mean(feats, axis=-1) in float32 (tests/matcher.py:35-36),
+ * same pairwise summation order as numpy.  eqv [K,32,60] -> desc [K,32]. */
+int yoho_group_mean(yoho_ctx* ctx, const float* eqv, int K, float* desc, void* stream);
+
+/* B2 — knn_module.KNN(1)(target, source) (utils/knn_search.py:17-24,26-66,138-154), dist_type 'L2':
+ * for every source row (m rows, F floats, F <= 32) the nearest target row: dist = sqrt(sum (s-t)^2 + 1e-7)
+ * in float32, ties -> lowest target index.  dist [m] float32, idx [m] int64. */
+int yoho_nn1(yoho_ctx* ctx, const float* source, int m, const float* target, int n, int F, float* dist,
+             int64_t* idx, void* stream);
+
+/* B1+B2 — matcher_dual.match (tests/matcher.py:37-48): both 1-NN searches in one pass over the Ka x Kb
+ * distance tiles, mutual filter, pairs written in ascending fragment-0 index.
+ * dA [Ka,32], dB [Kb,32]; pairs int64 [min(Ka,Kb),2] capacity; n_pairs device int32[1].
+ * nnA int32[Ka] / nnB int32[Kb] (argmin of each A row in B / each B row in A) may be NULL. */
+int yoho_mutual_nn(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, int64_t* pairs,
+                   int32_t* n_pairs, int32_t* nnA, int32_t* nnB, void* stream);
+
+/* C1 — extractor_dr_index.Batch_Des2R_torch (tests/extractor.py:74-78): for match m,
+ * cor[a] = sum_{f,g} des1[row1(m), f, P[a][g]] * des2[row2(m), f, g], idx[m] = argmax_a (ties -> lowest a).
+ * rows1/rows2: int64 row ids with element stride `row_stride` (pass the [M,2] match array with stride 2 and
+ * the column offset applied to the pointer), NULL = identity.  cor_out [M,60] may be NULL.
+ * The reference calls it with des1 = eqv of fragment 1, des2 = eqv of fragment 0 (tests/extractor.py:97-99). */
+int yoho_rot_argmax(yoho_ctx* ctx, const float* des1, const int64_t* rows1, const float* des2,
+                    const int64_t* rows2, int row_stride, int M, int64_t* idx, float* cor_out, void* stream);
+
+/* D1-D3 — extractor_PartII.batch_create + PartII_test.forward + the quaternion/transform post-loops
+ * (tests/extractor.py:125-138,185-201; utils/network.py:259-278; utils/r_eval.py:94-110).
+ * fcgf0/yoho0: fragment id0 ("A") tensors [K0,32,60]; fcgf1/yoho1: fragment id1 ("B").
+ * pairs int64 [M,2] (row in A, row in B); pre_idx int64 [M]; kps0/kps1 float64 [K,3] (NULL -> no trans).
+ * quat [M,4] float32 (w,x,y,z); trans [M,3,4] float64 = [R(q) Rgroup[idx] | k0 - R k1] (may be NULL).
+ * Evaluates only the receptive field of group element 0 (45/13/1 elements), which is exact. */
+int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float* fcgf1, const float* yoho0,
+                       const float* yoho1, const int64_t* pairs, const int64_t* pre_idx, int M,
+                       const double* kps0, const double* kps1, float* quat, double* trans, void* stream);
+
+/* Gather matched keypoints: out0[m] = kps0[pairs[m][0]], out1[m] = kps1[pairs[m][1]] (tests/estimator.py:98-99). */
+int yoho_gather_kps(yoho_ctx* ctx, const double* kps0, const double* kps1, const int64_t* pairs, int M,
+                    double* out0, double* out1, void* stream);
+
+/* E1 + draw — yohoc.DR_statictic (tests/estimator.py:34-51) and the hypothesis draws of the RANSAC loop
+ * (:119-126: categorical bin, then three members WITH replacement) generated on the device from a
+ * counter-based Philox4x32-10 stream.  Same distribution as the reference, not the same MT19937 stream;
+ * bit-parity runs pass a host-drawn list to yoho_c_ransac instead.
+ * status (device int32[1]): 0 ok, 1 = degenerate statistics (reference returns None -> identity, recalltime 50001). */
+int yoho_c_draw(yoho_ctx* ctx, const int64_t* dr_index, int M, int iters, uint64_t seed, int32_t* hyp,
+                int32_t* status, void* stream);
+
+/* E2-E4 — yohoc.ransac inner loop over a pre-drawn hypothesis list (tests/estimator.py:55-70,119-137).
+ * k0/k1 float64 [M,3] matched keypoints; hyp int32 [iters,3] match ids; signs int8[iters] or NULL
+ * (0 = sign rule of DESIGN.md, +1/-1 = forced determinant of the null-space completion).
+ * Outputs (device): T float64[12] ([I|0] if nothing scores), best_iter int32 (0-based, -1 if none),
+ * n_inl int32, mask uint8[M] (inliers of the winner), counts int32[iters] (may be NULL). */
+int yoho_c_ransac(yoho_ctx* ctx, const double* k0, const double* k1, int M, const int32_t* hyp,
+                  const int8_t* signs, int iters, double inlier_dist, double* T, int32_t* best_iter,
+                  int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream);
+
+/* Device-side random evaluation order for YOHO-O (np.random.shuffle(index), tests/estimator.py:321-323). */
+int yoho_o_order(yoho_ctx* ctx, int M, uint64_t seed, int32_t* order, void* stream);
+
+/* E5 — yohoo.ransac scoring (tests/estimator.py:321-336): trans float64 [Mt,3,4] hypotheses, order int32[H]
+ * (indices into trans, NULL = 0..H-1), first strictly-best kept.  best_iter is the position in `order`. */
+int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, int M, const double* trans,
+                 const int32_t* order, int H, double inlier_dist, double* T, int32_t* best_iter,
+                 int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream);
+
+/* Launch accounting for bench.py's "gpu_launches": kernels launched by this context since creation. */
+int64_t yoho_launch_count(const yoho_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOHO_B200_H */

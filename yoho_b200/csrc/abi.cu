@@ -1,0 +1,223 @@
+// Context, group tables, checkpoint packing and error plumbing of the yoho_b200 C ABI (include/yoho_b200.h).
+#include <stdarg.h>
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void yoho_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* yoho_last_error(void) { return g_err; }
+extern "C" int yoho_abi_version(void) { return YOHO_ABI_VERSION; }
+
+int yoho_ws_reserve(yoho_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return YOHO_OK;
+    size_t want = bytes + (bytes >> 3);
+    if (ctx->ws) {
+        YCHECK(cudaDeviceSynchronize());
+        YCHECK(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) {
+        yoho_set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return YOHO_ERR_ALLOC;
+    }
+    ctx->ws_bytes = want;
+    return YOHO_OK;
+}
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+    YCHECK(cudaMalloc((void**)dst, v.size() * sizeof(T)));
+    YCHECK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return YOHO_OK;
+}
+
+extern "C" int yoho_ctx_create(int device, const double* rotation_host, const int32_t* perm_host, const int32_t* nei_host,
+                               yoho_ctx** out) {
+    YARG(rotation_host && perm_host && nei_host && out);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        yoho_set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        return YOHO_ERR_CUDA;
+    }
+    YARG(device >= 0 && device < ndev);
+    YCHECK(cudaSetDevice(device));
+    yoho_ctx* c = new yoho_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    YCHECK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    for (int i = 0; i < YG * YG; ++i) YARG(perm_host[i] >= 0 && perm_host[i] < YG);
+    for (int i = 0; i < YG * YT; ++i) YARG(nei_host[i] >= 0 && nei_host[i] < YG);
+
+    std::vector<double> rot(rotation_host, rotation_host + YG * 9);
+    std::vector<float> rot32(YG * 9);
+    for (int i = 0; i < YG * 9; ++i) rot32[i] = (float)rot[i];
+    std::vector<uint8_t> perm(YG * YG), perm_t(YG * YG);
+    for (int a = 0; a < YG; ++a)
+        for (int g = 0; g < YG; ++g) {
+            perm[a * YG + g] = (uint8_t)perm_host[a * YG + g];
+            perm_t[g * YG + a] = (uint8_t)perm_host[a * YG + g];
+        }
+    std::vector<int> idx_full(nei_host, nei_host + YG * YT);
+    // receptive field of g = 0 (PartII): hop1 = N[0], hop2 = ordered union of N[e], e in hop1
+    std::vector<int> hop1(YT), hop2;
+    for (int k = 0; k < YT; ++k) hop1[k] = nei_host[k];
+    for (int e1 : hop1)
+        for (int k = 0; k < YT; ++k) {
+            int v = nei_host[e1 * YT + k];
+            bool seen = false;
+            for (int h : hop2) seen |= (h == v);
+            if (!seen) hop2.push_back(v);
+        }
+    YARG(hop2.size() == 45);
+    std::vector<int> pos(YG, -1);
+    for (size_t i = 0; i < hop2.size(); ++i) pos[hop2[i]] = (int)i;
+    std::vector<int> idx_init(45 * YT), idx_a(YT * YT), idx_b(YT), idx_one(1, 0);
+    for (int j = 0; j < 45; ++j)
+        for (int k = 0; k < YT; ++k) idx_init[j * YT + k] = nei_host[hop2[j] * YT + k];
+    for (int j = 0; j < YT; ++j)
+        for (int k = 0; k < YT; ++k) {
+            int v = pos[nei_host[hop1[j] * YT + k]];
+            YARG(v >= 0);
+            idx_a[j * YT + k] = v;
+        }
+    for (int k = 0; k < YT; ++k) idx_b[k] = k;   // N[0][k] = hop1[k]
+    c->hop2_zero_pos = pos[0];
+    YARG(c->hop2_zero_pos >= 0);
+
+    int rc = 0;
+    rc |= upload(&c->d_rot, rot);
+    rc |= upload(&c->d_rot32, rot32);
+    rc |= upload(&c->d_perm, perm);
+    rc |= upload(&c->d_perm_t, perm_t);
+    rc |= upload(&c->d_idx_full, idx_full);
+    rc |= upload(&c->d_idx_p2_init, idx_init);
+    rc |= upload(&c->d_idx_p2_a, idx_a);
+    rc |= upload(&c->d_idx_p2_b, idx_b);
+    rc |= upload(&c->d_idx_one, idx_one);
+    if (rc) { delete c; return YOHO_ERR_CUDA; }
+    if ((rc = yoho_ws_reserve(c, (size_t)64 << 20))) { delete c; return rc; }
+    *out = c;
+    return YOHO_OK;
+}
+
+static void free_layer(GLayer& L) {
+    cudaFree(L.w); cudaFree(L.bias); cudaFree(L.w_hi); cudaFree(L.w_lo);
+    L = GLayer();
+}
+static void free_bn(GBn& b) {
+    cudaFree(b.scale); cudaFree(b.shift);
+    b = GBn();
+}
+
+extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
+    if (!c) return YOHO_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3};
+    for (GLayer* l : layers) free_layer(*l);
+    GBn* bns[] = {&c->p1_bn_a, &c->p1_bn_b, &c->p1_bn_out, &c->p2_bn_init, &c->p2_bn_a, &c->p2_bn_b, &c->p2_bn1, &c->p2_bn2};
+    for (GBn* b : bns) free_bn(*b);
+    cudaFree(c->d_rot); cudaFree(c->d_rot32); cudaFree(c->d_perm); cudaFree(c->d_perm_t);
+    cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one);
+    cudaFree(c->ws);
+    delete c;
+    return YOHO_OK;
+}
+
+int gconv_tc_pack(yoho_ctx* ctx, GLayer& L, const std::vector<float>& w_kco);   // gconv_tc.cu
+
+// W[o][c][0][k] (reference layout) -> W_k[c][o]
+static int pack_conv(yoho_ctx* ctx, GLayer& L, const yoho_conv_host& h, int cin, int cout, int taps) {
+    YARG(h.weight_host && h.bias_host);
+    free_layer(L);
+    L.cin = cin; L.cout = cout; L.taps = taps;
+    std::vector<float> w((size_t)taps * cin * cout);
+    for (int o = 0; o < cout; ++o)
+        for (int c = 0; c < cin; ++c)
+            for (int k = 0; k < taps; ++k) w[((size_t)k * cin + c) * cout + o] = h.weight_host[((size_t)o * cin + c) * taps + k];
+    std::vector<float> b(h.bias_host, h.bias_host + cout);
+    if (int rc = upload(&L.w, w)) return rc;
+    if (int rc = upload(&L.bias, b)) return rc;
+    if (taps == YT) return gconv_tc_pack(ctx, L, w);
+    return YOHO_OK;
+}
+
+// eval-mode BatchNorm2d, eps = 1e-5: y = (x - mean) / sqrt(var + eps) * weight + bias = x*scale + shift
+static int pack_bn(GBn& B, const yoho_bn_host& h, int c) {
+    YARG(h.weight_host && h.bias_host && h.running_mean_host && h.running_var_host);
+    free_bn(B);
+    B.c = c;
+    std::vector<float> sc(c), sh(c);
+    for (int i = 0; i < c; ++i) {
+        const double s = (double)h.weight_host[i] / sqrt((double)h.running_var_host[i] + 1e-5);
+        sc[i] = (float)s;
+        sh[i] = (float)((double)h.bias_host[i] - (double)h.running_mean_host[i] * s);
+    }
+    if (int rc = upload(&B.scale, sc)) return rc;
+    return upload(&B.shift, sh);
+}
+
+extern "C" int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w) {
+    YARG(ctx && w);
+    YCHECK(cudaSetDevice(ctx->device));
+    ctx->has_p1 = false;
+    int rc = 0;
+    if ((rc = pack_conv(ctx, ctx->p1_in, w->conv_in, 32, 256, YT))) return rc;
+    if ((rc = pack_bn(ctx->p1_bn_a, w->bn_a, 256))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p1_a, w->conv_a, 256, 512, YT))) return rc;
+    if ((rc = pack_bn(ctx->p1_bn_b, w->bn_b, 512))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p1_b, w->conv_b, 512, 256, YT))) return rc;
+    if ((rc = pack_bn(ctx->p1_bn_out, w->bn_out, 256))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p1_out, w->conv_out, 256, 32, YT))) return rc;
+    ctx->has_p1 = true;
+    return YOHO_OK;
+}
+
+extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
+    YARG(ctx && w);
+    YCHECK(cudaSetDevice(ctx->device));
+    ctx->has_p2 = false;
+    int rc = 0;
+    if ((rc = pack_bn(ctx->p2_bn_init, w->bn_init, 128))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p2_init, w->conv_init, 128, 256, YT))) return rc;
+    if ((rc = pack_bn(ctx->p2_bn_a, w->bn_a, 256))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p2_a, w->conv_a, 256, 512, YT))) return rc;
+    if ((rc = pack_bn(ctx->p2_bn_b, w->bn_b, 512))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p2_b, w->conv_b, 512, 256, YT))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p2_fc1, w->fc1, 256, 512, 1))) return rc;
+    if ((rc = pack_bn(ctx->p2_bn1, w->bn1, 512))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p2_fc2, w->fc2, 512, 128, 1))) return rc;
+    if ((rc = pack_bn(ctx->p2_bn2, w->bn2, 128))) return rc;
+    if ((rc = pack_conv(ctx, ctx->p2_fc3, w->fc3, 128, 4, 1))) return rc;   // packed [128][4]
+    ctx->has_p2 = true;
+    return YOHO_OK;
+}
+
+extern "C" int yoho_set_gconv_impl(yoho_ctx* ctx, int impl) {
+    YARG(ctx && (impl == 0 || impl == 1));
+    ctx->gconv_impl = impl;
+    return YOHO_OK;
+}
+
+extern "C" int64_t yoho_launch_count(const yoho_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gconv_simt_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
+int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
+bool gconv_tc_eligible(const GLayer& L, const GConvArgs& a);
+
+int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
+    if (ctx->gconv_impl == 1 && gconv_tc_eligible(L, a)) return gconv_tc_forward(ctx, L, a, st);
+    return gconv_simt_forward(ctx, L, a, st);
+}

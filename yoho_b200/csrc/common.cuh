@@ -1,0 +1,107 @@
+// Shared declarations of the yoho_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/yoho_b200.h"
+
+#define YG 60
+#define YT 13
+#define YF 32
+
+void yoho_set_error(const char* fmt, ...);
+
+#define YCHECK(expr)                                                                            \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            yoho_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return YOHO_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define YARG(cond)                                                                 \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            yoho_set_error("%s:%d: bad argument: %s", __FILE__, __LINE__, #cond);  \
+            return YOHO_ERR_ARG;                                                   \
+        }                                                                          \
+    } while (0)
+
+// One group-convolution (or 1x1) layer, packed for the kernels.
+struct GLayer {
+    int cin = 0, cout = 0, taps = 0;
+    float* w = nullptr;       // [taps][cin][cout] fp32
+    float* bias = nullptr;    // [cout]
+    // tcgen05 path: bf16 hi/lo split of the weights, [taps][cout][cin] (K-major B operand)
+    void* w_hi = nullptr;
+    void* w_lo = nullptr;
+};
+
+// Folded eval-mode BatchNorm: y = x*scale + shift.
+struct GBn {
+    int c = 0;
+    float* scale = nullptr;
+    float* shift = nullptr;
+};
+
+struct yoho_ctx {
+    int device = 0;
+    int num_sms = 148;
+    int gconv_impl = 0;
+    int64_t launches = 0;
+    // group tables on the device
+    double* d_rot = nullptr;        // [60][9] f64
+    float* d_rot32 = nullptr;       // [60][9] f32 (Rgroup.astype(float32), tests/extractor.py:110)
+    uint8_t* d_perm_t = nullptr;    // [60 g][60 a] = P[a][g]
+    uint8_t* d_perm = nullptr;      // [60 a][60 g] = P[a][g]
+    int* d_idx_full = nullptr;      // [60][13]
+    int* d_idx_p2_init = nullptr;   // [45][13] -> 60
+    int* d_idx_p2_a = nullptr;      // [13][13] -> 45
+    int* d_idx_p2_b = nullptr;      // [1][13]  -> 13
+    int* d_idx_one = nullptr;       // [1][1] = 0
+    int hop2_zero_pos = 0;
+    // PartI
+    bool has_p1 = false;
+    GLayer p1_in, p1_a, p1_b, p1_out;
+    GBn p1_bn_a, p1_bn_b, p1_bn_out;
+    // PartII
+    bool has_p2 = false;
+    GLayer p2_init, p2_a, p2_b, p2_fc1, p2_fc2, p2_fc3;
+    GBn p2_bn_init, p2_bn_a, p2_bn_b, p2_bn1, p2_bn2;
+    // grow-only workspace
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+int yoho_ws_reserve(yoho_ctx* ctx, size_t bytes);
+
+// ---- generic gather-GEMM (gconv_simt.cu) ---------------------------------------------------------
+struct GConvArgs {
+    const float* act;        // [B][Jin][Cin], already activated if the layer has a pre-activation
+    const int* idx;          // [Jout][taps] -> row in [0,Jin)
+    int B, Jin, Jout;
+    const float* resid;      // nullable: [B][Jres][Cout]; row(b,j) = b*Jres + resid_off + (Jres_per_j ? j : 0)
+    int Jres, resid_off, resid_per_j;
+    float* out_raw;          // nullable [B][Jout][Cout]   = acc + bias (+ resid)
+    float* out_act;          // nullable [B][Jout][Cout]   = relu(out_raw*scale + shift)
+    const float* scale;      // folded BN of the NEXT layer's pre-activation (with out_act)
+    const float* shift;
+};
+int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
+
+// ---- small device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    // src-size 0 zero-fills the 16 destination bytes (used for rows past the end of the tile)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 16 : 0));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}

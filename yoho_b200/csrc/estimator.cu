@@ -1,0 +1,370 @@
+// YOHO-C / YOHO-O transformation estimators (tests/estimator.py:28-141,279-340) in FP64 on the device.
+//
+// COMPILED WITH -fmad=false: every FP64 operation below rounds exactly as written (fma() only where it is
+// spelled out), so the selected hypothesis and the inlier mask are reproducible bit for bit against the
+// C restatement in oracle/estimator_oracle.c.  Arithmetic specification: DESIGN.md "Estimator arithmetic".
+//
+//   hypothesis  (E2, Threepps2Tran :55-63)  Kabsch from three matches, R = V U^T with NO reflection fix.
+//       np.linalg.svd's sign for the null-space pair of the rank-2 cross-covariance is LAPACK noise; here the
+//       SVD is a one-sided Jacobi iteration and the sign is s = sign(det H) (or the caller's override).
+//   score       (E3, overlap_cal :66-70)    #{ m : ||k0_m - (R k1_m + t)||^2 < d^2 }, strict.
+//   selection   (E4/E5 :132,:333)           first hypothesis with the strictly largest count (> 0).
+#include "common.cuh"
+
+namespace {
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ double dotp(const V3& a, const V3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 crossp(const V3& a, const V3& b) {
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// Jacobi rotation of columns (p,q) of W and V (column-major storage: w[col]).
+__device__ __forceinline__ void jacobi_pair(V3& wp, V3& wq, V3& vp, V3& vq) {
+    const double alpha = dotp(wp, wp), beta = dotp(wq, wq), gamma = dotp(wp, wq);
+    if (gamma == 0.0) return;
+    const double zeta = (beta - alpha) / (2.0 * gamma);
+    double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    if (zeta < 0.0) t = -t;
+    const double c = 1.0 / sqrt(1.0 + t * t);
+    const double s = c * t;
+    V3 a = wp, b = wq;
+    wp = V3{c * a.x - s * b.x, c * a.y - s * b.y, c * a.z - s * b.z};
+    wq = V3{s * a.x + c * b.x, s * a.y + c * b.y, s * a.z + c * b.z};
+    a = vp; b = vq;
+    vp = V3{c * a.x - s * b.x, c * a.y - s * b.y, c * a.z - s * b.z};
+    vq = V3{s * a.x + c * b.x, s * a.y + c * b.y, s * a.z + c * b.z};
+}
+
+__device__ void kabsch3(const double* __restrict__ k0, const double* __restrict__ k1, int i0, int i1, int i2,
+                        int sign_override, double T[12]) {
+    // centroids: ((p0 + p1) + p2) / 3
+    double c0[3], c1[3], a[3][3], b[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        c0[d] = ((k0[3 * i0 + d] + k0[3 * i1 + d]) + k0[3 * i2 + d]) / 3.0;
+        c1[d] = ((k1[3 * i0 + d] + k1[3 * i1 + d]) + k1[3 * i2 + d]) / 3.0;
+    }
+    const int id[3] = {i0, i1, i2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            a[i][d] = k1[3 * id[i] + d] - c1[d];
+            b[i][d] = k0[3 * id[i] + d] - c0[d];
+        }
+    double H[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[r][c] = fma(a[2][r], b[2][c], fma(a[1][r], b[1][c], a[0][r] * b[0][c]));
+
+    double s;
+    if (sign_override > 0) s = 1.0;
+    else if (sign_override < 0) s = -1.0;
+    else {
+        const double m0 = H[1][1] * H[2][2] - H[1][2] * H[2][1];
+        const double m1 = H[1][0] * H[2][2] - H[1][2] * H[2][0];
+        const double m2 = H[1][0] * H[2][1] - H[1][1] * H[2][0];
+        const double det = (H[0][0] * m0 - H[0][1] * m1) + H[0][2] * m2;
+        s = det < 0.0 ? -1.0 : 1.0;
+    }
+
+    V3 w[3] = {{H[0][0], H[1][0], H[2][0]}, {H[0][1], H[1][1], H[2][1]}, {H[0][2], H[1][2], H[2][2]}};
+    V3 v[3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        jacobi_pair(w[0], w[1], v[0], v[1]);
+        jacobi_pair(w[0], w[2], v[0], v[2]);
+        jacobi_pair(w[1], w[2], v[1], v[2]);
+    }
+    const double n0 = dotp(w[0], w[0]), n1 = dotp(w[1], w[1]), n2 = dotp(w[2], w[2]);
+    const double nn[3] = {n0, n1, n2};
+    int i1st = 0;
+    if (nn[1] > nn[i1st]) i1st = 1;
+    if (nn[2] > nn[i1st]) i1st = 2;
+    int i2nd = -1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (j == i1st) continue;
+        if (i2nd < 0 || nn[j] > nn[i2nd]) i2nd = j;
+    }
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (nn[i1st] != 0.0) {
+        const double s1 = sqrt(nn[i1st]);
+        const V3 wa = w[i1st], wb = w[i2nd];
+        const V3 u1{wa.x / s1, wa.y / s1, wa.z / s1};
+        const V3 v1 = v[i1st], v2 = v[i2nd];
+        V3 u2;
+        if (nn[i2nd] <= 1e-28 * nn[i1st]) {
+            int j = 0;
+            const double au[3] = {fabs(u1.x), fabs(u1.y), fabs(u1.z)};
+            if (au[1] < au[j]) j = 1;
+            if (au[2] < au[j]) j = 2;
+            const double uj = j == 0 ? u1.x : (j == 1 ? u1.y : u1.z);
+            u2 = V3{(j == 0 ? 1.0 : 0.0) - uj * u1.x, (j == 1 ? 1.0 : 0.0) - uj * u1.y, (j == 2 ? 1.0 : 0.0) - uj * u1.z};
+        } else {
+            const double s2 = sqrt(nn[i2nd]);
+            u2 = V3{wb.x / s2, wb.y / s2, wb.z / s2};
+            const double pr = dotp(u1, u2);
+            u2 = V3{u2.x - pr * u1.x, u2.y - pr * u1.y, u2.z - pr * u1.z};
+        }
+        const double l2 = sqrt(dotp(u2, u2));
+        u2 = V3{u2.x / l2, u2.y / l2, u2.z / l2};
+        const V3 u3 = crossp(u1, u2), v3 = crossp(v1, v2);
+        const double V1[3] = {v1.x, v1.y, v1.z}, V2[3] = {v2.x, v2.y, v2.z}, V3_[3] = {v3.x, v3.y, v3.z};
+        const double U1[3] = {u1.x, u1.y, u1.z}, U2[3] = {u2.x, u2.y, u2.z}, U3[3] = {u3.x, u3.y, u3.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[r][c] = (V1[r] * U1[c] + V2[r] * U2[c]) + s * (V3_[r] * U3[c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        T[4 * r + 0] = R[r][0]; T[4 * r + 1] = R[r][1]; T[4 * r + 2] = R[r][2];
+        T[4 * r + 3] = c0[r] - fma(R[r][2], c1[2], fma(R[r][1], c1[1], R[r][0] * c1[0]));
+    }
+}
+
+__device__ __forceinline__ bool is_inlier(const double* __restrict__ k0, const double* __restrict__ k1, int m,
+                                          const double T[12], double thr2) {
+    const double x = k1[3 * m], y = k1[3 * m + 1], z = k1[3 * m + 2];
+    const double px = fma(T[2], z, fma(T[1], y, T[0] * x)) + T[3];
+    const double py = fma(T[6], z, fma(T[5], y, T[4] * x)) + T[7];
+    const double pz = fma(T[10], z, fma(T[9], y, T[8] * x)) + T[11];
+    const double dx = k0[3 * m] - px, dy = k0[3 * m + 1] - py, dz = k0[3 * m + 2] - pz;
+    return fma(dz, dz, fma(dy, dy, dx * dx)) < thr2;
+}
+
+// One warp per hypothesis.  mode 0: Kabsch from hyp triplets; mode 1: given transforms (YOHO-O).
+__global__ void __launch_bounds__(256) score_kernel(const double* __restrict__ k0, const double* __restrict__ k1, int M,
+                                                   const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
+                                                   const double* __restrict__ trans, const int32_t* __restrict__ order,
+                                                   int n_hyp, double thr2, int32_t* __restrict__ counts) {
+    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (h >= n_hyp) return;
+    double T[12];
+    if (trans) {
+        const double* src = trans + 12 * (size_t)(order ? order[h] : h);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[i] = src[i];
+    } else {
+        kabsch3(k0, k1, hyp[3 * h], hyp[3 * h + 1], hyp[3 * h + 2], signs ? (int)signs[h] : 0, T);
+    }
+    int n = 0;
+    for (int m = lane; m < M; m += 32) n += is_inlier(k0, k1, m, T, thr2) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) counts[h] = n;
+}
+
+// First strictly-best hypothesis, its transform and inlier mask.  Single CTA.
+__global__ void __launch_bounds__(1024) select_kernel(const double* __restrict__ k0, const double* __restrict__ k1, int M,
+                                                     const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
+                                                     const double* __restrict__ trans, const int32_t* __restrict__ order,
+                                                     int n_hyp, double thr2, const int32_t* __restrict__ counts,
+                                                     double* __restrict__ T_out, int32_t* __restrict__ best_iter,
+                                                     int32_t* __restrict__ n_inl, uint8_t* __restrict__ mask) {
+    __shared__ unsigned long long red[32];
+    __shared__ double Ts[12];
+    __shared__ int bi_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    // key: larger count first, then smaller index  ->  maximise (count << 32) | (0xffffffff - index)
+    unsigned long long best = 0;
+    for (int h = t; h < n_hyp; h += 1024) {
+        const unsigned long long k = ((unsigned long long)(unsigned)counts[h] << 32) | (unsigned)(0xffffffffu - (unsigned)h);
+        best = k > best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long u = __shfl_xor_sync(0xffffffffu, best, o);
+        best = u > best ? u : best;
+    }
+    if (lane == 0) red[w] = best;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long b = 0;
+        for (int i = 0; i < 32; ++i) b = red[i] > b ? red[i] : b;
+        const int cnt = (int)(b >> 32);
+        const int bi = cnt > 0 ? (int)(0xffffffffu - (unsigned)(b & 0xffffffffu)) : -1;
+        bi_s = bi;
+        *best_iter = bi;
+        *n_inl = cnt > 0 ? cnt : 0;
+        double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (bi >= 0) {
+            if (trans) {
+                const double* src = trans + 12 * (size_t)(order ? order[bi] : bi);
+                for (int i = 0; i < 12; ++i) T[i] = src[i];
+            } else {
+                kabsch3(k0, k1, hyp[3 * bi], hyp[3 * bi + 1], hyp[3 * bi + 2], signs ? (int)signs[bi] : 0, T);
+            }
+        }
+        for (int i = 0; i < 12; ++i) { Ts[i] = T[i]; T_out[i] = T[i]; }
+    }
+    __syncthreads();
+    if (mask) {
+        double T[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[i] = Ts[i];
+        const bool any = bi_s >= 0;
+        for (int m = t; m < M; m += 1024) mask[m] = (any && is_inlier(k0, k1, m, T, thr2)) ? 1 : 0;
+    }
+}
+
+// ---- Philox4x32-10 ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * ctr.x;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * ctr.z;
+        ctr = make_uint4((unsigned)(p1 >> 32) ^ ctr.y ^ key.x, (unsigned)p1, (unsigned)(p0 >> 32) ^ ctr.w ^ key.y, (unsigned)p0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// E1 + draws.  Single CTA.  members are kept in ascending match order per bin, as the reference's lists.
+__global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict__ dr_index, int M, int iters,
+                                                     unsigned long long seed, int32_t* __restrict__ members_ws,
+                                                     int32_t* __restrict__ hyp, int32_t* __restrict__ status) {
+    __shared__ int cnt[YG];
+    __shared__ int off[YG + 1];
+    __shared__ double cdf[YG];
+    __shared__ int ok_s;
+    const int t = threadIdx.x;
+    if (t < YG) cnt[t] = 0;
+    __syncthreads();
+    for (int m = t; m < M; m += 1024) atomicAdd(&cnt[(int)dr_index[m]], 1);
+    __syncthreads();
+    if (t == 0) {
+        double tot = 0.0, w[YG];
+        int o = 0;
+        for (int i = 0; i < YG; ++i) {
+            off[i] = o;
+            o += cnt[i];
+            double p = 0.0;
+            if (cnt[i] >= 2) {
+                const double num = (double)cnt[i] / 100.0;
+                p = num * (num - 0.01) * (num - 0.02);
+            }
+            w[i] = p;
+            tot += p;
+        }
+        off[YG] = o;
+        ok_s = !(tot < 1e-4);
+        if (ok_s) {
+            // np.random.choice: cdf = cumsum(p / sum); cdf /= cdf[-1]
+            double c = 0.0;
+            for (int i = 0; i < YG; ++i) { c += w[i] / tot; cdf[i] = c; }
+            const double last = cdf[YG - 1];
+            for (int i = 0; i < YG; ++i) cdf[i] = cdf[i] / last;
+        }
+        *status = ok_s ? 0 : 1;
+    }
+    __syncthreads();
+    // stable bucket fill: thread b owns bin b and scans the matches in order (M is a few thousand at most)
+    if (t < YG) {
+        int o = off[t];
+        for (int m = 0; m < M; ++m)
+            if ((int)dr_index[m] == t) members_ws[o++] = m;
+    }
+    __syncthreads();
+    if (!ok_s) {
+        for (int i = t; i < 3 * iters; i += 1024) hyp[i] = 0;
+        return;
+    }
+    for (int it = t; it < iters; it += 1024) {
+        const uint4 r = philox4x32(make_uint4((unsigned)it, 0u, 0x59484f43u, 0u),
+                                   make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+        // 53-bit uniform in [0,1) like random_sample(): (a >> 5, b >> 6)
+        const double u = ((double)(r.x >> 5) * 67108864.0 + (double)(r.y >> 6)) / 9007199254740992.0;
+        int bin = 0;
+        while (bin < YG - 1 && !(u < cdf[bin])) ++bin;     // searchsorted(cdf, u, side='right')
+        while (cnt[bin] == 0 && bin > 0) --bin;            // unreachable guard
+        const uint4 r2 = philox4x32(make_uint4((unsigned)it, 1u, 0x59484f43u, 0u),
+                                    make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+        const unsigned c = (unsigned)cnt[bin];
+        const int base = off[bin];
+        hyp[3 * it + 0] = members_ws[base + (int)(((unsigned long long)r2.x * c) >> 32)];
+        hyp[3 * it + 1] = members_ws[base + (int)(((unsigned long long)r2.y * c) >> 32)];
+        hyp[3 * it + 2] = members_ws[base + (int)(((unsigned long long)r2.z * c) >> 32)];
+    }
+}
+
+// Random evaluation order: rank of a Philox key (ties by index).  O(M^2) compares, M is a few thousand.
+__global__ void o_order_kernel(int M, unsigned long long seed, int32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    auto key = [&](int j) {
+        const uint4 r = philox4x32(make_uint4((unsigned)j, 2u, 0x59484f4fu, 0u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+        return ((unsigned long long)r.x << 32) | r.y;
+    };
+    const unsigned long long ki = key(i);
+    int rank = 0;
+    for (int j = 0; j < M; ++j) {
+        const unsigned long long kj = key(j);
+        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    order[rank] = i;
+}
+
+}  // namespace
+
+extern "C" int yoho_c_draw(yoho_ctx* ctx, const int64_t* dr_index, int M, int iters, uint64_t seed, int32_t* hyp,
+                           int32_t* status, void* stream) {
+    YARG(ctx && dr_index && hyp && status && M >= 0 && iters >= 0);
+    YCHECK(cudaSetDevice(ctx->device));
+    if (int rc = yoho_ws_reserve(ctx, (size_t)(M + 1) * 4)) return rc;
+    c_draw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dr_index, M, iters, seed, (int32_t*)ctx->ws, hyp, status);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+static int score_and_select(yoho_ctx* ctx, const double* k0, const double* k1, int M, const int32_t* hyp,
+                            const int8_t* signs, const double* trans, const int32_t* order, int n_hyp, double dist,
+                            double* T, int32_t* best_iter, int32_t* n_inl, uint8_t* mask, int32_t* counts, cudaStream_t st) {
+    int32_t* cnt = counts;
+    if (!cnt) {
+        if (int rc = yoho_ws_reserve(ctx, (size_t)(n_hyp + 1) * 4)) return rc;
+        cnt = (int32_t*)ctx->ws;
+    }
+    const double thr2 = dist * dist;
+    if (n_hyp > 0) {
+        score_kernel<<<(n_hyp + 7) / 8, 256, 0, st>>>(k0, k1, M, hyp, signs, trans, order, n_hyp, thr2, cnt);
+        ctx->launches++;
+    }
+    select_kernel<<<1, 1024, 0, st>>>(k0, k1, M, hyp, signs, trans, order, n_hyp, thr2, cnt, T, best_iter, n_inl, mask);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+extern "C" int yoho_c_ransac(yoho_ctx* ctx, const double* k0, const double* k1, int M, const int32_t* hyp,
+                             const int8_t* signs, int iters, double inlier_dist, double* T, int32_t* best_iter,
+                             int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream) {
+    YARG(ctx && k0 && k1 && T && best_iter && n_inl && M >= 0 && iters >= 0 && (iters == 0 || hyp));
+    YCHECK(cudaSetDevice(ctx->device));
+    return score_and_select(ctx, k0, k1, M, hyp, signs, nullptr, nullptr, iters, inlier_dist, T, best_iter, n_inl, mask,
+                            counts, (cudaStream_t)stream);
+}
+
+extern "C" int yoho_o_order(yoho_ctx* ctx, int M, uint64_t seed, int32_t* order, void* stream) {
+    YARG(ctx && order && M >= 0);
+    if (M == 0) return YOHO_OK;
+    YCHECK(cudaSetDevice(ctx->device));
+    o_order_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, seed, order);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+extern "C" int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, int M, const double* trans,
+                            const int32_t* order, int H, double inlier_dist, double* T, int32_t* best_iter,
+                            int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream) {
+    YARG(ctx && k0 && k1 && T && best_iter && n_inl && M >= 0 && H >= 0 && (H == 0 || trans));
+    YCHECK(cudaSetDevice(ctx->device));
+    return score_and_select(ctx, k0, k1, M, nullptr, nullptr, trans, order, H, inlier_dist, T, best_iter, n_inl, mask,
+                            counts, (cudaStream_t)stream);
+}

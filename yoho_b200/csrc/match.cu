@@ -1,0 +1,309 @@
+// Descriptor matching (tests/matcher.py:19-49, utils/knn_search.py:17-66,138-154) and the 60-way
+// rotation-correlation argmax (tests/extractor.py:74-78).
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// Mutual 1-NN.  One pass over the Ka x Kb distance matrix in 64x64 tiles; each CTA reduces its tile to
+// 64 row minima and 64 column minima and merges them into global 64-bit keys with atomicMin:
+//     key = (float_bits(sqrt(d2 + 1e-7)) << 32) | index
+// Distances are positive, so the unsigned order of the key is the lexicographic (distance, index) order:
+// equal float distances resolve to the LOWEST index, which is torch.min's first-occurrence rule
+// (utils/knn_search.py:41).  d2 is the reference's direct form sum_f (a_f - b_f)^2 accumulated in FP32 with
+// one FMA per channel in ascending channel order (the reference's summation order is library-defined).
+// ---------------------------------------------------------------------------------------------------
+constexpr int MT = 64;
+
+__global__ void __launch_bounds__(256) nn_tile_kernel(const float* __restrict__ dA, int Ka, const float* __restrict__ dB,
+                                                     int Kb, unsigned long long* __restrict__ rowbest,
+                                                     unsigned long long* __restrict__ colbest) {
+    __shared__ float As[YF][MT + 4];
+    __shared__ float Bs[YF][MT + 4];
+    __shared__ unsigned long long colred[16][MT];
+    const int t = threadIdx.x;
+    const int a0 = blockIdx.y * MT, b0 = blockIdx.x * MT;
+    for (int i = t; i < MT * YF; i += 256) {
+        const int r = i / YF, f = i % YF;
+        As[f][r] = (a0 + r < Ka) ? dA[(size_t)(a0 + r) * YF + f] : 0.f;
+        Bs[f][r] = (b0 + r < Kb) ? dB[(size_t)(b0 + r) * YF + f] : 0.f;
+    }
+    __syncthreads();
+    const int ta = t >> 4, tb = t & 15;   // 16 x 16 threads, 4 x 4 distances each
+    float d2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d2[i][j] = 0.f;
+#pragma unroll 8
+    for (int f = 0; f < YF; ++f) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[f][ta * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[f][tb * 4]);
+        const float a[4] = {av.x, av.y, av.z, av.w};
+        const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float df = __fsub_rn(a[i], b[j]);
+                d2[i][j] = __fmaf_rn(df, df, d2[i][j]);
+            }
+    }
+    unsigned long long rkey[4], ckey[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { rkey[i] = ~0ull; ckey[i] = ~0ull; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ia = a0 + ta * 4 + i, ib = b0 + tb * 4 + j;
+            if (ia < Ka && ib < Kb) {
+                const float d = __fsqrt_rn(__fadd_rn(d2[i][j], 1e-7f));
+                const unsigned long long hi = (unsigned long long)__float_as_uint(d) << 32;
+                const unsigned long long kr = hi | (unsigned)ib;
+                const unsigned long long kc = hi | (unsigned)ia;
+                rkey[i] = kr < rkey[i] ? kr : rkey[i];
+                ckey[j] = kc < ckey[j] ? kc : ckey[j];
+            }
+        }
+    // row minima: reduce over the 16 tb lanes (consecutive lanes of a half-warp)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        unsigned long long v = rkey[i];
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = u < v ? u : v;
+        }
+        if (tb == 0 && a0 + ta * 4 + i < Ka) atomicMin(&rowbest[a0 + ta * 4 + i], v);
+    }
+    // column minima: reduce over the 16 ta groups through shared memory
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colred[ta][tb * 4 + j] = ckey[j];
+    __syncthreads();
+    if (t < MT) {
+        unsigned long long v = colred[0][t];
+#pragma unroll
+        for (int r = 1; r < 16; ++r) v = colred[r][t] < v ? colred[r][t] : v;
+        if (b0 + t < Kb) atomicMin(&colbest[b0 + t], v);
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Mutual filter + ordered compaction (tests/matcher.py:41-48).  Single CTA, 1024 threads.
+__global__ void __launch_bounds__(1024) mutual_compact_kernel(const unsigned long long* __restrict__ rowbest, int Ka,
+                                                             const unsigned long long* __restrict__ colbest, int Kb,
+                                                             int64_t* __restrict__ pairs, int32_t* __restrict__ n_pairs,
+                                                             int32_t* __restrict__ nnA, int32_t* __restrict__ nnB) {
+    __shared__ int warp_tot[32];
+    __shared__ int base_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) base_s = 0;
+    __syncthreads();
+    if (nnB)
+        for (int i = t; i < Kb; i += 1024) nnB[i] = (int32_t)(colbest[i] & 0xffffffffu);
+    for (int start = 0; start < Ka; start += 1024) {
+        const int a = start + t;
+        int flag = 0, j = 0;
+        if (a < Ka) {
+            j = (int)(rowbest[a] & 0xffffffffu);
+            if (nnA) nnA[a] = j;
+            flag = ((int)(colbest[j] & 0xffffffffu) == a);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        const int pre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[w] = __popc(bal);
+        __syncthreads();
+        int woff = 0;
+        for (int i = 0; i < w; ++i) woff += warp_tot[i];
+        const int base = base_s;
+        if (flag) {
+            const int o = base + woff + pre;
+            pairs[2 * (size_t)o] = a;
+            pairs[2 * (size_t)o + 1] = j;
+        }
+        __syncthreads();
+        if (t == 0) {
+            int tot = 0;
+            for (int i = 0; i < 32; ++i) tot += warp_tot[i];
+            base_s = base + tot;
+        }
+        __syncthreads();
+    }
+    if (t == 0) *n_pairs = base_s;
+}
+
+__global__ void nn1_out_kernel(const unsigned long long* __restrict__ best, int m, float* dist, int64_t* idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        const unsigned long long k = best[i];
+        if (dist) dist[i] = __uint_as_float((unsigned)(k >> 32));
+        if (idx) idx[i] = (int64_t)(k & 0xffffffffu);
+    }
+}
+
+__global__ void pad32_kernel(const float* __restrict__ src, int n, int F, float* __restrict__ dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)n * YF) {
+        const int r = (int)(i / YF), f = (int)(i % YF);
+        dst[i] = f < F ? src[(size_t)r * F + f] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Rotation-correlation argmax.  One CTA per match: both [32x60] tiles (7680 B each, contiguous in HBM)
+// are staged in shared memory by two 1-D TMA bulk copies that signal one mbarrier; 240 threads then form
+// the 60 permuted dot products (4 channel-quarters x 60 rotations), quarters are summed in a fixed order
+// and warp 0 takes the argmax with lowest-index tie-break (torch.argmax).
+// ---------------------------------------------------------------------------------------------------
+constexpr int TILE_FLOATS = YF * YG;           // 1920
+constexpr int TILE_BYTES = TILE_FLOATS * 4;    // 7680
+
+__global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict__ des1, const int64_t* __restrict__ rows1,
+                                                        const float* __restrict__ des2, const int64_t* __restrict__ rows2,
+                                                        int row_stride, int M, const uint8_t* __restrict__ perm_t,
+                                                        int64_t* __restrict__ idx_out, float* __restrict__ cor_out) {
+    __shared__ __align__(128) float s1[TILE_FLOATS];
+    __shared__ __align__(128) float s2[TILE_FLOATS];
+    __shared__ __align__(16) uint8_t pt[YG * 64];   // pt[g*64 + a] = P[a][g]
+    __shared__ float part[4][64];
+    __shared__ __align__(8) unsigned long long bar;
+    const int m = blockIdx.x;
+    const int t = threadIdx.x;
+    const int64_t r1 = rows1 ? rows1[(size_t)m * row_stride] : m;
+    const int64_t r2 = rows2 ? rows2[(size_t)m * row_stride] : m;
+    const uint32_t bar_a = smem_u32(&bar);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_a), "r"(2 * TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         smem_u32(s1)),
+                     "l"(des1 + (size_t)r1 * TILE_FLOATS), "r"(TILE_BYTES), "r"(bar_a)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         smem_u32(s2)),
+                     "l"(des2 + (size_t)r2 * TILE_FLOATS), "r"(TILE_BYTES), "r"(bar_a)
+                     : "memory");
+    }
+    for (int i = t; i < YG * 64; i += 256) {
+        const int g = i >> 6, a = i & 63;
+        pt[i] = a < YG ? perm_t[g * YG + a] : 0;
+    }
+    {   // wait for both tiles (phase 0)
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(ok)
+                : "r"(bar_a), "r"(0)
+                : "memory");
+        }
+    }
+    __syncthreads();
+    const int a = t & 63, q = t >> 6;   // rotation a, channel quarter q
+    float acc = 0.f;
+    if (a < YG) {
+        for (int f = q * 8; f < q * 8 + 8; ++f) {
+            const float* p1 = s1 + f * YG;
+            const float* p2 = s2 + f * YG;
+#pragma unroll 4
+            for (int g = 0; g < YG; ++g) acc = fmaf(p1[pt[g * 64 + a]], p2[g], acc);
+        }
+    }
+    part[q][a] = acc;
+    __syncthreads();
+    if (t < 32) {
+        float best = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int aa = t + 32 * h;
+            if (aa < YG) {
+                const float c = ((part[0][aa] + part[1][aa]) + part[2][aa]) + part[3][aa];
+                if (cor_out) cor_out[(size_t)m * YG + aa] = c;
+                if (c > best) { best = c; bi = aa; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (t == 0) idx_out[m] = bi;
+    }
+}
+
+int nn_pass(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, unsigned long long* rowbest,
+            unsigned long long* colbest, cudaStream_t st) {
+    const size_t n = (size_t)Ka + Kb;   // rowbest and colbest are contiguous
+    fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowbest, n, ~0ull);
+    dim3 grid((Kb + MT - 1) / MT, (Ka + MT - 1) / MT);
+    nn_tile_kernel<<<grid, 256, 0, st>>>(dA, Ka, dB, Kb, rowbest, colbest);
+    ctx->launches += 2;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+}  // namespace
+
+extern "C" int yoho_mutual_nn(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, int64_t* pairs,
+                              int32_t* n_pairs, int32_t* nnA, int32_t* nnB, void* stream) {
+    YARG(ctx && dA && dB && pairs && n_pairs && Ka > 0 && Kb > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    YCHECK(cudaSetDevice(ctx->device));
+    if (int rc = yoho_ws_reserve(ctx, ((size_t)Ka + Kb) * 8)) return rc;
+    unsigned long long* rowbest = (unsigned long long*)ctx->ws;
+    unsigned long long* colbest = rowbest + Ka;
+    if (int rc = nn_pass(ctx, dA, Ka, dB, Kb, rowbest, colbest, st)) return rc;
+    mutual_compact_kernel<<<1, 1024, 0, st>>>(rowbest, Ka, colbest, Kb, pairs, n_pairs, nnA, nnB);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+extern "C" int yoho_nn1(yoho_ctx* ctx, const float* source, int m, const float* target, int n, int F, float* dist,
+                        int64_t* idx, void* stream) {
+    YARG(ctx && source && target && m > 0 && n > 0 && F >= 1 && F <= YF);
+    cudaStream_t st = (cudaStream_t)stream;
+    YCHECK(cudaSetDevice(ctx->device));
+    const size_t keys = ((size_t)m + n) * 8;
+    const size_t padb = F == YF ? 0 : ((size_t)m + n) * YF * 4;
+    if (int rc = yoho_ws_reserve(ctx, keys + padb)) return rc;
+    unsigned long long* rowbest = (unsigned long long*)ctx->ws;
+    unsigned long long* colbest = rowbest + m;
+    const float* s = source;
+    const float* tg = target;
+    if (F != YF) {   // zero channels add exactly 0 to every distance
+        float* ps = (float*)((char*)ctx->ws + keys);
+        float* pt = ps + (size_t)m * YF;
+        pad32_kernel<<<(unsigned)(((size_t)m * YF + 255) / 256), 256, 0, st>>>(source, m, F, ps);
+        pad32_kernel<<<(unsigned)(((size_t)n * YF + 255) / 256), 256, 0, st>>>(target, n, F, pt);
+        ctx->launches += 2;
+        s = ps; tg = pt;
+    }
+    if (int rc = nn_pass(ctx, s, m, tg, n, rowbest, colbest, st)) return rc;
+    nn1_out_kernel<<<(m + 255) / 256, 256, 0, st>>>(rowbest, m, dist, idx);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+extern "C" int yoho_rot_argmax(yoho_ctx* ctx, const float* des1, const int64_t* rows1, const float* des2,
+                               const int64_t* rows2, int row_stride, int M, int64_t* idx, float* cor_out, void* stream) {
+    YARG(ctx && des1 && des2 && idx && M >= 0 && row_stride >= 1);
+    if (M == 0) return YOHO_OK;
+    YCHECK(cudaSetDevice(ctx->device));
+    rot_argmax_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(des1, rows1, des2, rows2, row_stride, M, ctx->d_perm_t, idx, cor_out);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}

@@ -1,0 +1,162 @@
+// PartI descriptor network (utils/network.py:67-105,140-147) around the gather-GEMM layers.
+//
+//   x0[B,32,60] --transpose--> [B,60,32]
+//   y1 = GC_in(x0)                       raw kept (shortcut), a1 = relu(BN_a(y1))           (:87-88, :55)
+//   a2 = relu(BN_b(GC_a(a1)))                                                                  (:55-57)
+//   a3 = relu(BN_o(GC_b(a2) + y1))                                                             (:57-65,:91)
+//   y4 = GC_out(a3)                                                                            (:92)
+//   e = y4 + x0 ; inv = normalise(mean_g e) ; eqv = e / max(||e||_c, 1e-4) ; desc = mean_g eqv (:98-103, tests/matcher.py:35)
+#include "common.cuh"
+
+namespace {
+
+// [B][32][60] -> [B][60][32]; one CTA per keypoint.
+__global__ void __launch_bounds__(128) transpose_in_kernel(const float* __restrict__ x, float* __restrict__ xt, int B) {
+    __shared__ float s[YF][YG + 1];
+    const int b = blockIdx.x;
+    const float* src = x + (size_t)b * YF * YG;
+    for (int i = threadIdx.x; i < YF * YG; i += blockDim.x) s[i / YG][i % YG] = src[i];
+    __syncthreads();
+    float* dst = xt + (size_t)b * YF * YG;
+    for (int i = threadIdx.x; i < YF * YG; i += blockDim.x) dst[i] = s[i % YF][i / YF];
+}
+
+// numpy's float32 pairwise summation of 60 contiguous values followed by /60
+// (np.mean(feats, axis=-1), tests/matcher.py:35): 8 strided partial sums, tree-combined, 4-element tail.
+__device__ __forceinline__ float numpy_mean60(const float* a, int stride) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j * stride];
+    for (int i = 8; i < 56; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[(i + j) * stride]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (int i = 56; i < 60; ++i) res = __fadd_rn(res, a[i * stride]);
+    return __fdiv_rn(res, 60.0f);
+}
+
+// One CTA (64 threads) per keypoint.  y4 [B][60][32] (bias included), x [B][32][60].
+__global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restrict__ y4, const float* __restrict__ x,
+                                                           float* __restrict__ eqv, float* __restrict__ inv,
+                                                           float* __restrict__ desc, int B) {
+    __shared__ float e[YF][YG + 1];
+    __shared__ float invn[YG];
+    __shared__ float red[YF];
+    const int b = blockIdx.x;
+    const int t = threadIdx.x;
+    const float* xs = x + (size_t)b * YF * YG;
+    const float* ys = y4 + (size_t)b * YG * YF;
+    // e[c][g] = y4[g][c] + x[c][g]
+    for (int i = t; i < YF * YG; i += 64) {
+        const int g = i / YF, c = i % YF;
+        e[c][g] = ys[i];
+    }
+    __syncthreads();
+    for (int i = t; i < YF * YG; i += 64) {
+        const int c = i / YG, g = i % YG;
+        e[c][g] = e[c][g] + xs[i];
+    }
+    __syncthreads();
+    if (t < YG) {
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < YF; ++c) ss = fmaf(e[c][t], e[c][t], ss);
+        invn[t] = fmaxf(sqrtf(ss), 1e-4f);   // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
+    }
+    // invariant pooling uses the UN-normalised e (utils/network.py:99 precedes :102)
+    float m = 0.f;
+    if (t < YF) {
+        float s = 0.f;
+        for (int g = 0; g < YG; ++g) s += e[t][g];
+        m = s / 60.0f;
+        red[t] = m * m;
+    }
+    __syncthreads();
+    if (t < YF && inv) {
+        float ss = 0.f;
+        for (int c = 0; c < YF; ++c) ss += red[c];
+        inv[(size_t)b * YF + t] = m / fmaxf(sqrtf(ss), 1e-4f);
+    }
+    float* out = eqv + (size_t)b * YF * YG;
+    for (int i = t; i < YF * YG; i += 64) {
+        const int c = i / YG, g = i % YG;
+        const float v = e[c][g] / invn[g];
+        e[c][g] = v;
+        out[i] = v;
+    }
+    __syncthreads();
+    if (t < YF && desc) desc[(size_t)b * YF + t] = numpy_mean60(&e[t][0], 1);
+}
+
+__global__ void __launch_bounds__(64) group_mean_kernel(const float* __restrict__ eqv, float* __restrict__ desc, int K) {
+    __shared__ float e[YF][YG + 1];
+    const int b = blockIdx.x;
+    const float* src = eqv + (size_t)b * YF * YG;
+    for (int i = threadIdx.x; i < YF * YG; i += 64) e[i / YG][i % YG] = src[i];
+    __syncthreads();
+    if (threadIdx.x < YF) desc[(size_t)b * YF + threadIdx.x] = numpy_mean60(&e[threadIdx.x][0], 1);
+}
+
+constexpr int P1_CHUNK = 2048;  // keypoints per pass: bounds the workspace at ~0.63 GB
+
+}  // namespace
+
+extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* eqv, float* inv, float* desc_mean,
+                                  void* stream) {
+    YARG(ctx && x && eqv && B >= 0);
+    if (!ctx->has_p1) {
+        yoho_set_error("No model exists: yoho_part1_load has not been called");
+        return YOHO_ERR_NOWEIGHTS;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    YCHECK(cudaSetDevice(ctx->device));
+    const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 32) * sizeof(float);
+    const int chunk = B < P1_CHUNK ? B : P1_CHUNK;
+    if (int rc = yoho_ws_reserve(ctx, per_kp * (size_t)chunk)) return rc;
+    for (int s = 0; s < B; s += chunk) {
+        const int n = (B - s) < chunk ? (B - s) : chunk;
+        float* xt = (float*)ctx->ws;
+        float* y1 = xt + (size_t)n * YG * 32;
+        float* a1 = y1 + (size_t)n * YG * 256;
+        float* a2 = a1 + (size_t)n * YG * 256;
+        float* a3 = a2 + (size_t)n * YG * 512;
+        float* y4 = a3 + (size_t)n * YG * 256;
+        const float* xs = x + (size_t)s * YF * YG;
+        transpose_in_kernel<<<n, 128, 0, st>>>(xs, xt, n);
+        ctx->launches++;
+        GConvArgs a{};
+        a.idx = ctx->d_idx_full; a.B = n; a.Jin = YG; a.Jout = YG;
+        // layer 1: raw y1 (shortcut) + a1 = relu(BN_a(y1))
+        a.act = xt; a.resid = nullptr; a.out_raw = y1; a.out_act = a1;
+        a.scale = ctx->p1_bn_a.scale; a.shift = ctx->p1_bn_a.shift;
+        if (int rc = gconv_forward(ctx, ctx->p1_in, a, st)) return rc;
+        // layer 2: a2 = relu(BN_b(GC_a(a1)))
+        a.act = a1; a.out_raw = nullptr; a.out_act = a2;
+        a.scale = ctx->p1_bn_b.scale; a.shift = ctx->p1_bn_b.shift;
+        if (int rc = gconv_forward(ctx, ctx->p1_a, a, st)) return rc;
+        // layer 3: a3 = relu(BN_o(GC_b(a2) + y1))
+        a.act = a2; a.resid = y1; a.Jres = YG; a.resid_off = 0; a.resid_per_j = 1; a.out_act = a3;
+        a.scale = ctx->p1_bn_out.scale; a.shift = ctx->p1_bn_out.shift;
+        if (int rc = gconv_forward(ctx, ctx->p1_b, a, st)) return rc;
+        // layer 4: y4 = GC_out(a3)
+        a.act = a3; a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.scale = a.shift = nullptr;
+        if (int rc = gconv_forward(ctx, ctx->p1_out, a, st)) return rc;
+        part1_finalize_kernel<<<n, 64, 0, st>>>(y4, xs, eqv + (size_t)s * YF * YG, inv ? inv + (size_t)s * YF : nullptr,
+                                                desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
+        ctx->launches++;
+    }
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+extern "C" int yoho_group_mean(yoho_ctx* ctx, const float* eqv, int K, float* desc, void* stream) {
+    YARG(ctx && eqv && desc && K >= 0);
+    if (K == 0) return YOHO_OK;
+    YCHECK(cudaSetDevice(ctx->device));
+    group_mean_kernel<<<K, 64, 0, (cudaStream_t)stream>>>(eqv, desc, K);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}

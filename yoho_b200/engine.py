@@ -1,0 +1,249 @@
+"""Device engine: one `Engine` per GPU wraps a `yoho_ctx` of the C ABI and exposes every stage of the hot
+path on torch CUDA tensors (torch is used for device memory and streams only — the arithmetic is in
+libyoho_b200.so).  All methods enqueue on the current torch stream and do not synchronise unless they
+return host values.
+"""
+import ctypes
+import threading
+import numpy as np
+import torch
+
+from . import _lib
+from . import group as _group
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, device=None, so3_dir=None):
+        if not torch.cuda.is_available():
+            raise _lib.YohoError("yoho_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+        self.lib = _lib.load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.tables = _group.load(so3_dir)
+        rot = np.ascontiguousarray(self.tables.R, np.float64)
+        perm = np.ascontiguousarray(self.tables.P, np.int32)
+        nei = np.ascontiguousarray(self.tables.N, np.int32)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.yoho_ctx_create(self.device.index, rot.ctypes.data, perm.ctypes.data, nei.ctypes.data,
+                                            ctypes.byref(h)))
+        self.h = h
+        self.has_part1 = False
+        self.has_part2 = False
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.yoho_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights -----------------------------------------------------------------------------------
+    def load_part1(self, state_dict):
+        w, keep = _lib.part1_struct(state_dict)
+        _lib.check(self.lib.yoho_part1_load(self.h, ctypes.byref(w)))
+        self.has_part1 = True
+
+    def load_part2(self, state_dict):
+        w, keep = _lib.part2_struct(state_dict)
+        _lib.check(self.lib.yoho_part2_load(self.h, ctypes.byref(w)))
+        self.has_part2 = True
+
+    def set_gconv_impl(self, impl):
+        _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1}.get(impl, impl)))
+
+    def launch_count(self):
+        return int(self.lib.yoho_launch_count(self.h))
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _f32(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return x.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _f64(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        return x.to(device=self.device, dtype=torch.float64).contiguous()
+
+    def _i64(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64))
+        return x.to(device=self.device, dtype=torch.int64).contiguous()
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, device=self.device, dtype=dtype)
+
+    # ---- A: PartI ----------------------------------------------------------------------------------
+    def part1(self, x, want_inv=True, want_desc=True):
+        """x [B,32,60] -> dict(eqv [B,32,60], inv [B,32], desc [B,32])."""
+        x = self._f32(x)
+        assert x.dim() == 3 and x.shape[1] == 32 and x.shape[2] == 60, "group feature must be [B,32,60]"
+        B = x.shape[0]
+        eqv = self._empty((B, 32, 60), torch.float32)
+        inv = self._empty((B, 32), torch.float32) if want_inv else None
+        desc = self._empty((B, 32), torch.float32) if want_desc else None
+        _lib.check(self.lib.yoho_part1_forward(self.h, _ptr(x), B, _ptr(eqv), _ptr(inv), _ptr(desc), _stream()))
+        return {"eqv": eqv, "inv": inv, "desc": desc}
+
+    # ---- B: matching -------------------------------------------------------------------------------
+    def group_mean(self, eqv):
+        eqv = self._f32(eqv)
+        K = eqv.shape[0]
+        desc = self._empty((K, 32), torch.float32)
+        _lib.check(self.lib.yoho_group_mean(self.h, _ptr(eqv), K, _ptr(desc), _stream()))
+        return desc
+
+    def nn1(self, source, target):
+        """For every source row [m,F] the nearest target row [n,F] -> (dist [m] f32, idx [m] i64)."""
+        s, t = self._f32(source), self._f32(target)
+        m, F = s.shape
+        n = t.shape[0]
+        dist = self._empty((m,), torch.float32)
+        idx = self._empty((m,), torch.int64)
+        _lib.check(self.lib.yoho_nn1(self.h, _ptr(s), m, _ptr(t), n, F, _ptr(dist), _ptr(idx), _stream()))
+        return dist, idx
+
+    def mutual_nn(self, dA, dB, want_nn=False):
+        """dA [Ka,32], dB [Kb,32] -> (pairs buffer [min,2] i64, n_pairs device i32[1]) (+ nnA, nnB)."""
+        dA, dB = self._f32(dA), self._f32(dB)
+        Ka, Kb = dA.shape[0], dB.shape[0]
+        pairs = self._empty((min(Ka, Kb), 2), torch.int64)
+        n = self._empty((1,), torch.int32)
+        nnA = self._empty((Ka,), torch.int32) if want_nn else None
+        nnB = self._empty((Kb,), torch.int32) if want_nn else None
+        _lib.check(self.lib.yoho_mutual_nn(self.h, _ptr(dA), Ka, _ptr(dB), Kb, _ptr(pairs), _ptr(n), _ptr(nnA),
+                                           _ptr(nnB), _stream()))
+        if want_nn:
+            return pairs, n, nnA, nnB
+        return pairs, n
+
+    # ---- C: rotation index -------------------------------------------------------------------------
+    def rot_argmax(self, des1, des2, pairs=None, want_cor=False):
+        """idx[m] = argmax_a sum_{f,g} des1[r1(m),f,P[a][g]] des2[r2(m),f,g].
+        With `pairs` [M,2] (row in fragment 0, row in fragment 1): r1 = pairs[:,1] indexes des1 (fragment 1's eqv)
+        and r2 = pairs[:,0] indexes des2 (fragment 0's eqv) — the reference's call order
+        (tests/extractor.py:97-99).  Without pairs the rows are matched one to one."""
+        des1, des2 = self._f32(des1), self._f32(des2)
+        if pairs is not None:
+            pairs = self._i64(pairs)
+            M = pairs.shape[0]
+            r1 = ctypes.c_void_p(pairs.data_ptr() + 8) if M else None
+            r2 = ctypes.c_void_p(pairs.data_ptr()) if M else None
+            stride = 2
+        else:
+            M = des1.shape[0]
+            r1 = r2 = None
+            stride = 1
+        idx = self._empty((M,), torch.int64)
+        cor = self._empty((M, 60), torch.float32) if want_cor else None
+        _lib.check(self.lib.yoho_rot_argmax(self.h, _ptr(des1), r1, _ptr(des2), r2, stride, M, _ptr(idx), _ptr(cor),
+                                            _stream()))
+        return (idx, cor) if want_cor else idx
+
+    # ---- D: PartII ---------------------------------------------------------------------------------
+    def part2(self, fcgf0, fcgf1, yoho0, yoho1, pre_idx, pairs=None, kps0=None, kps1=None):
+        """Fragment tensors [K,32,60] + pairs [M,2] (or per-match rows when pairs is None), pre_idx [M]
+        -> quat [M,4] f32 and, when keypoints are given, trans [M,3,4] f64."""
+        f0, f1, y0, y1 = self._f32(fcgf0), self._f32(fcgf1), self._f32(yoho0), self._f32(yoho1)
+        pre = self._i64(pre_idx)
+        M = pre.shape[0]
+        pr = self._i64(pairs) if pairs is not None else None
+        quat = self._empty((M, 4), torch.float32)
+        trans = None
+        k0 = k1 = None
+        if kps0 is not None:
+            k0, k1 = self._f64(kps0), self._f64(kps1)
+            trans = self._empty((M, 3, 4), torch.float64)
+        _lib.check(self.lib.yoho_part2_forward(self.h, _ptr(f0), _ptr(f1), _ptr(y0), _ptr(y1), _ptr(pr), _ptr(pre), M,
+                                               _ptr(k0), _ptr(k1), _ptr(quat), _ptr(trans), _stream()))
+        return quat, trans
+
+    # ---- E: estimators -----------------------------------------------------------------------------
+    def gather_kps(self, kps0, kps1, pairs):
+        k0, k1, pr = self._f64(kps0), self._f64(kps1), self._i64(pairs)
+        M = pr.shape[0]
+        o0 = self._empty((M, 3), torch.float64)
+        o1 = self._empty((M, 3), torch.float64)
+        _lib.check(self.lib.yoho_gather_kps(self.h, _ptr(k0), _ptr(k1), _ptr(pr), M, _ptr(o0), _ptr(o1), _stream()))
+        return o0, o1
+
+    def c_draw(self, dr_index, iters, seed):
+        dr = self._i64(dr_index)
+        hyp = self._empty((iters, 3), torch.int32)
+        status = self._empty((1,), torch.int32)
+        _lib.check(self.lib.yoho_c_draw(self.h, _ptr(dr), dr.shape[0], iters, ctypes.c_uint64(seed), _ptr(hyp),
+                                        _ptr(status), _stream()))
+        return hyp, status
+
+    def _est_out(self, M, n_hyp, want_counts):
+        T = self._empty((3, 4), torch.float64)
+        bi = self._empty((1,), torch.int32)
+        ni = self._empty((1,), torch.int32)
+        mask = self._empty((M,), torch.uint8)
+        counts = self._empty((n_hyp,), torch.int32) if want_counts else None
+        return T, bi, ni, mask, counts
+
+    def c_ransac(self, k0, k1, hyp, dist, signs=None, want_counts=False):
+        k0, k1 = self._f64(k0), self._f64(k1)
+        if isinstance(hyp, np.ndarray):
+            hyp = torch.from_numpy(np.ascontiguousarray(hyp, np.int32))
+        hyp = hyp.to(device=self.device, dtype=torch.int32).contiguous()
+        sg = None
+        if signs is not None:
+            sg = torch.as_tensor(np.ascontiguousarray(signs, np.int8)).to(self.device)
+        M, iters = k0.shape[0], hyp.shape[0]
+        T, bi, ni, mask, counts = self._est_out(M, iters, want_counts)
+        _lib.check(self.lib.yoho_c_ransac(self.h, _ptr(k0), _ptr(k1), M, _ptr(hyp), _ptr(sg), iters, float(dist),
+                                          _ptr(T), _ptr(bi), _ptr(ni), _ptr(mask), _ptr(counts), _stream()))
+        return dict(T=T, best_iter=bi, n_inl=ni, mask=mask, counts=counts)
+
+    def o_order(self, M, seed):
+        order = self._empty((M,), torch.int32)
+        _lib.check(self.lib.yoho_o_order(self.h, M, ctypes.c_uint64(seed), _ptr(order), _stream()))
+        return order
+
+    def o_score(self, k0, k1, trans, dist, order=None, max_hyp=None, want_counts=False):
+        k0, k1, tr = self._f64(k0), self._f64(k1), self._f64(trans)
+        od = None
+        H = tr.shape[0]
+        if order is not None:
+            if isinstance(order, np.ndarray):
+                order = torch.from_numpy(np.ascontiguousarray(order, np.int32))
+            od = order.to(device=self.device, dtype=torch.int32).contiguous()
+            H = od.shape[0]
+        if max_hyp is not None:
+            H = min(H, int(max_hyp))
+        M = k0.shape[0]
+        T, bi, ni, mask, counts = self._est_out(M, H, want_counts)
+        _lib.check(self.lib.yoho_o_score(self.h, _ptr(k0), _ptr(k1), M, _ptr(tr), _ptr(od), H, float(dist), _ptr(T),
+                                         _ptr(bi), _ptr(ni), _ptr(mask), _ptr(counts), _stream()))
+        return dict(T=T, best_iter=bi, n_inl=ni, mask=mask, counts=counts)
+
+
+_engines = {}
+_lock = threading.Lock()
+
+
+def get_engine(device=None, so3_dir=None) -> Engine:
+    """Process-wide engine per (device, table dir)."""
+    if not torch.cuda.is_available():
+        raise _lib.YohoError("yoho_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    t = _group.load(so3_dir)
+    # same table contents -> same engine, whichever directory they were read from
+    key = (dev, hash((t.R.tobytes(), t.P.tobytes(), t.N.tobytes())))
+    with _lock:
+        if key not in _engines:
+            _engines[key] = Engine(dev, so3_dir)
+        return _engines[key]

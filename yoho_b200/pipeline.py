@@ -1,0 +1,86 @@
+"""In-memory fragment-pair pipeline: FCGF group features + keypoints of two fragments -> YOHO-C and YOHO-O
+transforms, device resident between stages (the reference round-trips every stage through .npy files:
+tests/evaluator.py:41-47,112-117).  This is the unit of work of BASELINE.json's metric: one cold pair =
+PartI on both fragments, mutual matching, rotation index, YOHO-C, PartII, YOHO-O.
+
+One host synchronisation per pair (the match count M sizes the downstream launches).
+"""
+import numpy as np
+import torch
+
+from .engine import get_engine
+
+
+class PairResult(dict):
+    __getattr__ = dict.get
+
+
+class PairPipeline:
+    def __init__(self, engine=None, c_iters=1000, o_iters=1000, c_dist=0.07, o_dist=0.09, seed=0):
+        self.eng = engine or get_engine()
+        if not (self.eng.has_part1 and self.eng.has_part2):
+            raise RuntimeError("load PartI and PartII weights into the engine first (No model exists)")
+        self.c_iters, self.o_iters = int(c_iters), int(o_iters)
+        self.c_dist, self.o_dist = float(c_dist), float(o_dist)
+        self.seed = int(seed)
+        self._pinned = {}
+
+    # ---- device-resident pair ------------------------------------------------------------------------
+    def register(self, featA, featB, kpsA, kpsB, eqvA=None, eqvB=None, descA=None, descB=None):
+        """All inputs CUDA tensors: feat [K,32,60] f32, kps [K,3] f64.  Pass precomputed eqv/desc to skip PartI
+        (the amortised regime: one PartI pass per fragment per dataset, tests/extractor.py:46-47)."""
+        e = self.eng
+        if eqvA is None:
+            oa = e.part1(featA, want_inv=False, want_desc=True)
+            eqvA, descA = oa["eqv"], oa["desc"]
+        if eqvB is None:
+            ob = e.part1(featB, want_inv=False, want_desc=True)
+            eqvB, descB = ob["eqv"], ob["desc"]
+        pairs_buf, n_dev = e.mutual_nn(descA, descB)
+        M = int(n_dev.item())                               # the one host sync of the pair
+        pairs = pairs_buf[:M]
+        out = PairResult(M=M, pairs=pairs, eqvA=eqvA, eqvB=eqvB)
+        if M == 0:
+            eye = torch.eye(4, dtype=torch.float64, device=e.device)[:3]
+            out.update(dr_index=pairs.new_zeros((0,)), T_c=eye, T_o=eye.clone(), c_best=-1, o_best=-1)
+            return out
+        dr = e.rot_argmax(eqvB, eqvA, pairs=pairs)          # Batch_Des2R_torch(feats1[m1], feats0[m0])
+        k0, k1 = e.gather_kps(kpsA, kpsB, pairs)
+        self.seed += 1
+        hyp, status = e.c_draw(dr, self.c_iters, self.seed)
+        rc = e.c_ransac(k0, k1, hyp, self.c_dist)
+        quat, trans = e.part2(featA, featB, eqvA, eqvB, dr, pairs=pairs, kps0=kpsA, kps1=kpsB)
+        order = e.o_order(M, self.seed)
+        ro = e.o_score(k0, k1, trans, self.o_dist, order=order, max_hyp=self.o_iters)
+        out.update(dr_index=dr, k0=k0, k1=k1, hyp=hyp, c_status=status, T_c=rc["T"], c_best=rc["best_iter"],
+                   c_inl=rc["n_inl"], c_mask=rc["mask"], quat=quat, trans_pre=trans, T_o=ro["T"],
+                   o_best=ro["best_iter"], o_inl=ro["n_inl"], o_mask=ro["mask"])
+        return out
+
+    # ---- host-facing call (the e2e path: host buffers in, host transforms out) -----------------------------
+    def _stage(self, name, arr, dtype):
+        t = self._pinned.get(name)
+        if t is None or t.shape != arr.shape or t.dtype != dtype:
+            t = torch.empty(arr.shape, dtype=dtype, pin_memory=True)
+            self._pinned[name] = t
+        t.copy_(torch.from_numpy(arr))
+        return t
+
+    def register_host(self, featA, featB, kpsA, kpsB):
+        """numpy in (feat [K,32,60] f32, kps [K,3] f64) -> numpy transforms out; H2D/D2H inside."""
+        dev = self.eng.device
+        fa = self._stage("fa", featA, torch.float32).to(dev, non_blocking=True)
+        fb = self._stage("fb", featB, torch.float32).to(dev, non_blocking=True)
+        ka = self._stage("ka", kpsA, torch.float64).to(dev, non_blocking=True)
+        kb = self._stage("kb", kpsB, torch.float64).to(dev, non_blocking=True)
+        r = self.register(fa, fb, ka, kb)
+        res = torch.stack([r["T_c"], r["T_o"]]).cpu().numpy()
+        return dict(T_c=res[0], T_o=res[1], M=r["M"])
+
+    @staticmethod
+    def h2d_bytes(K):
+        return 2 * K * 32 * 60 * 4 + 2 * K * 3 * 8
+
+    @staticmethod
+    def d2h_bytes():
+        return 2 * 12 * 8 + 4     # two 3x4 f64 transforms + the match count

@@ -1,0 +1,138 @@
+"""Seeded synthetic inputs and weights.  Pure numpy, bit-reproducible on any box
+(legacy `np.random.RandomState` streams are stable across numpy versions), so the goldens generated
+in the authoring container and the tensors regenerated on the GPU box are identical.
+
+* `synth_state_dict(part, seed)` — a state-dict with the reference's key names and shapes
+  (SURVEY.md §8a "Checkpoint key names"), variance-preserving random conv weights and BatchNorm
+  statistics drawn analytically (no calibration pass, so no dependence on a BLAS build).
+* `make_fragment_pair(K, seed, ...)` — FCGF-like unit-norm group features [K,32,60] for two fragments
+  with a planted group rotation r, residual rotation, translation and overlap (BASELINE.json configs).
+"""
+import numpy as np
+from . import group as _group
+
+
+# --------------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------------
+def _conv(rs, o, c, taps, gain):
+    std = np.sqrt(gain / (c * taps))
+    w = (rs.standard_normal((o, c, 1, taps)) * std).astype(np.float32)
+    b = (rs.standard_normal((o,)) * 0.02).astype(np.float32)
+    return w, b
+
+
+def _bn(rs, c, mean_scale=0.3, var_lo=0.5, var_hi=2.0):
+    return {
+        "weight": rs.uniform(0.5, 1.5, (c,)).astype(np.float32),
+        "bias": (rs.standard_normal((c,)) * 0.3).astype(np.float32),
+        "running_mean": (rs.standard_normal((c,)) * mean_scale).astype(np.float32),
+        "running_var": rs.uniform(var_lo, var_hi, (c,)).astype(np.float32),
+        "num_batches_tracked": np.array(1000, dtype=np.int64),
+    }
+
+
+def _put_bn(sd, prefix, bn):
+    for k, v in bn.items():
+        sd[f"{prefix}.{k}"] = v
+
+
+def synth_state_dict(part: str, seed: int = 0):
+    """part in {'PartI','PartII'} -> dict name -> np.ndarray with the reference's key names."""
+    rs = np.random.RandomState(1000 + seed + (0 if part == "PartI" else 500))
+    sd = {}
+    if part == "PartI":
+        p = "PartI_net."
+        w, b = _conv(rs, 256, 32, 13, 32.0)            # inputs have variance 1/32 per channel
+        sd[p + "Conv_in.0.weight"], sd[p + "Conv_in.0.bias"] = w, b
+        blk = p + "SO3_Conv_layers.0."
+        _put_bn(sd, blk + "comb_layer_in.0", _bn(rs, 256))
+        w, b = _conv(rs, 512, 256, 13, 2.0)
+        sd[blk + "comb_layer_in.2.weight"], sd[blk + "comb_layer_in.2.bias"] = w, b
+        _put_bn(sd, blk + "comb_layer_out.0", _bn(rs, 512))
+        w, b = _conv(rs, 256, 512, 13, 2.0)
+        sd[blk + "comb_layer_out.2.weight"], sd[blk + "comb_layer_out.2.bias"] = w, b
+        _put_bn(sd, p + "Conv_out.comb_layer.0", _bn(rs, 256, var_lo=1.0, var_hi=3.0))
+        w, b = _conv(rs, 32, 256, 13, 0.05)            # keeps the residual branch ~ the input scale
+        sd[p + "Conv_out.comb_layer.2.weight"], sd[p + "Conv_out.comb_layer.2.bias"] = w, b
+    elif part == "PartII":
+        _put_bn(sd, "Conv_init.comb_layer.0", _bn(rs, 128, mean_scale=0.02, var_lo=0.02, var_hi=0.05))
+        w, b = _conv(rs, 256, 128, 13, 2.0)
+        sd["Conv_init.comb_layer.2.weight"], sd["Conv_init.comb_layer.2.bias"] = w, b
+        blk = "PartII_SO3_Conv_layers.0."
+        _put_bn(sd, blk + "comb_layer_in.0", _bn(rs, 256))
+        w, b = _conv(rs, 512, 256, 13, 2.0)
+        sd[blk + "comb_layer_in.2.weight"], sd[blk + "comb_layer_in.2.bias"] = w, b
+        _put_bn(sd, blk + "comb_layer_out.0", _bn(rs, 512))
+        w, b = _conv(rs, 256, 512, 13, 2.0)
+        sd[blk + "comb_layer_out.2.weight"], sd[blk + "comb_layer_out.2.bias"] = w, b
+        fc = "PartII_To_R_FC."
+        w, b = _conv(rs, 512, 256, 1, 1.0)
+        sd[fc + "0.weight"], sd[fc + "0.bias"] = w, b
+        _put_bn(sd, fc + "1", _bn(rs, 512, var_lo=1.0, var_hi=3.0))
+        w, b = _conv(rs, 128, 512, 1, 2.0)
+        sd[fc + "3.weight"], sd[fc + "3.bias"] = w, b
+        _put_bn(sd, fc + "4", _bn(rs, 128))
+        w, b = _conv(rs, 4, 128, 1, 2.0)
+        sd[fc + "6.weight"] = w
+        sd[fc + "6.bias"] = (b + np.array([0.9, 0.0, 0.0, 0.0], np.float32)).astype(np.float32)
+    else:
+        raise ValueError(part)
+    return sd
+
+
+def to_torch_state_dict(sd):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+# --------------------------------------------------------------------------------------------
+# inputs
+# --------------------------------------------------------------------------------------------
+def _unit(x, axis):
+    n = np.sqrt((x * x).sum(axis=axis, keepdims=True))
+    return x / np.maximum(n, 1e-12)
+
+
+def _small_rotation(rs, max_deg):
+    axis = rs.standard_normal(3)
+    axis /= np.linalg.norm(axis)
+    ang = np.deg2rad(rs.uniform(0, max_deg))
+    kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * kx + (1 - np.cos(ang)) * (kx @ kx)
+
+
+def make_fragment(K, seed):
+    """One fragment: FCGF-like group feature [K,32,60] f32 (unit-norm over the 32 channels for every
+    (keypoint, g), as the backbone's normalize_feature=True produces) and keypoints [K,3] f64."""
+    rs = np.random.RandomState(seed)
+    feat = _unit(rs.standard_normal((K, 32, 60)), 1).astype(np.float32)
+    kps = rs.uniform(0.0, 3.0, (K, 3))
+    return feat, kps
+
+
+def make_fragment_pair(K, seed=0, overlap=0.5, sigma=0.05, max_residual_deg=15.0, kp_noise=0.01,
+                       so3_dir=None):
+    """Pair (A,B) with planted transform  pts_A = R_gt pts_B + t_gt  on an overlapping subset.
+
+    Returns dict: feat_A, feat_B [K,32,60] f32; kps_A, kps_B [K,3] f64; r (planted group index, such
+    that F_A[:, :, g] ~= F_B[:, :, P[r][g]], i.e. pts_A ~= R_r pts_B); R_gt, t_gt; subset ids.
+    """
+    gt = _group.load(so3_dir)
+    rs = np.random.RandomState(seed)
+    feat_B = _unit(rs.standard_normal((K, 32, 60)), 1).astype(np.float32)
+    kps_B = rs.uniform(0.0, 3.0, (K, 3))
+    r = int(rs.randint(0, 60))
+    dR = _small_rotation(rs, max_residual_deg)
+    R_gt = dR @ gt.R[r]
+    t_gt = rs.uniform(-1.0, 1.0, 3)
+    n_ov = int(round(overlap * K))
+    ids_B = rs.permutation(K)[:n_ov]
+    ids_A = rs.permutation(K)[:n_ov]
+    feat_A = _unit(rs.standard_normal((K, 32, 60)), 1).astype(np.float32)
+    kps_A = rs.uniform(-2.0, 5.0, (K, 3))
+    fa = feat_B[ids_B][:, :, gt.P[r]] + sigma * rs.standard_normal((n_ov, 32, 60))
+    feat_A[ids_A] = _unit(fa, 1).astype(np.float32)
+    kps_A[ids_A] = kps_B[ids_B] @ R_gt.T + t_gt + kp_noise * rs.standard_normal((n_ov, 3))
+    return dict(feat_A=feat_A, feat_B=feat_B, kps_A=kps_A, kps_B=kps_B, r=r, R_gt=R_gt, t_gt=t_gt,
+                ids_A=ids_A, ids_B=ids_B)
