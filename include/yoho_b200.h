@@ -173,6 +173,15 @@ int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, int M, const
 /* Launch accounting for bench.py's "gpu_launches": kernels launched by this context since creation. */
 int64_t yoho_launch_count(const yoho_ctx* ctx);
 
+/* Per-layer timing of the group-convolution launches with CUDA events on the launching stream (bench.py's
+ * roofline object).  enable=1 starts/clears recording, enable=0 stops.  yoho_profile_read synchronises the
+ * device and returns, for layer class c in [0, YOHO_PROF_CLASSES): total milliseconds, launches and algorithmic
+ * FLOPs (2 * rows * taps * Cin * Cout per launch).  Classes: 0..3 = PartI layers 1..4, 4..6 = PartII group
+ * convolutions (init, a, b), 7 = PartII 1x1 head layers. */
+#define YOHO_PROF_CLASSES 8
+int yoho_profile_enable(yoho_ctx* ctx, int enable);
+int yoho_profile_read(yoho_ctx* ctx, double* ms_host, int64_t* launches_host, double* flops_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,73 @@
+"""CPU, world_size 2, gloo: the N>1 host logic — sharding, the result gather and the cross-rank mutual-NN merge
+(config 5) — with the oracle standing in for the single-device search."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from yoho_b200 import dist as yd
+    import yoho_oracle as O
+    r, lr, w = yd.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    try:
+        # 1. sharding + gather restores the original pair order
+        pairs = list(range(7))
+        mine = yd.shard(pairs)
+        T = torch.zeros((len(mine), 3, 4), dtype=torch.float64)
+        for i, p in enumerate(mine):
+            T[i] = float(p)
+        allT = yd.gather_transforms(T)
+        assert allT.shape == (7, 3, 4) and [int(allT[i, 0, 0]) for i in range(7)] == pairs
+        # 2. config-5 style sharded mutual NN == single-process result
+        rs = np.random.RandomState(0)
+        Ka, Kb = 301, 257
+        dA = (rs.standard_normal((Ka, 32)) * 0.1).astype(np.float32)
+        dB = (rs.standard_normal((Kb, 32)) * 0.1).astype(np.float32)
+        dB[:120] = dA[rs.permutation(Ka)[:120]] + (rs.standard_normal((120, 32)) * 0.01).astype(np.float32)
+        dB[200:210] = dB[100:110]                       # exact duplicates across the shard boundary: lowest index wins
+        bounds = np.linspace(0, Kb, world + 1).astype(int)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        nn1 = lambda s, t: O.nn1(s, t)
+        got = yd.sharded_mutual_nn(torch.from_numpy(dA), torch.from_numpy(dB[lo:hi]), lo, Kb, nn1).numpy()
+        want, _, _ = O.mutual_matches(dA, dB)
+        assert np.array_equal(got, want), (got.shape, want.shape)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_unshard_roundtrip():
+    sys.path.insert(0, ROOT)
+    from yoho_b200 import dist as yd
+    for n in (0, 1, 5, 16):
+        for w in (1, 2, 3, 8):
+            items = list(range(n))
+            assert yd.unshard([yd.shard(items, r, w) for r in range(w)]) == items
+    k = yd.pack_key(torch.tensor([0.5, 0.25, 0.25]), torch.tensor([7, 9, 3]))
+    assert int(torch.argmin(k)) == 2
+    d, i = yd.unpack_key(k)
+    assert d.tolist() == [0.5, 0.25, 0.25] and i.tolist() == [7, 9, 3]

@@ -56,7 +56,12 @@ SYMBOLS = {
     "yoho_o_order": (_i, [_vp, _i, ctypes.c_uint64, _vp, _vp]),
     "yoho_o_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_launch_count": (ctypes.c_int64, [_vp]),
+    "yoho_profile_enable": (_i, [_vp, _i]),
+    "yoho_profile_read": (_i, [_vp, _vp, _vp, _vp]),
 }
+PROF_CLASSES = 8
+PROF_NAMES = ["p1_L1_32x256", "p1_L2_256x512", "p1_L3_512x256", "p1_L4_256x32",
+              "p2_init_128x256", "p2_a_256x512", "p2_b_512x256", "p2_head_1x1"]
 
 _lib = None
 

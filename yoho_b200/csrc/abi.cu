@@ -181,6 +181,7 @@ extern "C" int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w) {
     if ((rc = pack_conv(ctx, ctx->p1_b, w->conv_b, 512, 256, YT))) return rc;
     if ((rc = pack_bn(ctx->p1_bn_out, w->bn_out, 256))) return rc;
     if ((rc = pack_conv(ctx, ctx->p1_out, w->conv_out, 256, 32, YT))) return rc;
+    ctx->p1_in.prof_class = 0; ctx->p1_a.prof_class = 1; ctx->p1_b.prof_class = 2; ctx->p1_out.prof_class = 3;
     ctx->has_p1 = true;
     return YOHO_OK;
 }
@@ -201,6 +202,8 @@ extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
     if ((rc = pack_conv(ctx, ctx->p2_fc2, w->fc2, 512, 128, 1))) return rc;
     if ((rc = pack_bn(ctx->p2_bn2, w->bn2, 128))) return rc;
     if ((rc = pack_conv(ctx, ctx->p2_fc3, w->fc3, 128, 4, 1))) return rc;   // packed [128][4]
+    ctx->p2_init.prof_class = 4; ctx->p2_a.prof_class = 5; ctx->p2_b.prof_class = 6;
+    ctx->p2_fc1.prof_class = 7; ctx->p2_fc2.prof_class = 7; ctx->p2_fc3.prof_class = 7;
     ctx->has_p2 = true;
     return YOHO_OK;
 }
@@ -217,7 +220,46 @@ int gconv_simt_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaS
 int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
 bool gconv_tc_eligible(const GLayer& L, const GConvArgs& a);
 
+static cudaEvent_t prof_event(yoho_ctx* ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
 int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
-    if (ctx->gconv_impl == 1 && gconv_tc_eligible(L, a)) return gconv_tc_forward(ctx, L, a, st);
-    return gconv_simt_forward(ctx, L, a, st);
+    yoho_ctx::ProfRec rec{};
+    const bool prof = ctx->prof_on && a.B > 0;
+    if (prof) {
+        rec.a = prof_event(ctx); rec.b = prof_event(ctx); rec.cls = L.prof_class;
+        rec.flops = 2.0 * (double)a.B * a.Jout * L.taps * L.cin * L.cout;
+        cudaEventRecord(rec.a, st);
+    }
+    int rc;
+    if (ctx->gconv_impl == 1 && gconv_tc_eligible(L, a)) rc = gconv_tc_forward(ctx, L, a, st);
+    else rc = gconv_simt_forward(ctx, L, a, st);
+    if (prof) { cudaEventRecord(rec.b, st); ctx->prof.push_back(rec); }
+    return rc;
+}
+
+extern "C" int yoho_profile_enable(yoho_ctx* ctx, int enable) {
+    YARG(ctx);
+    YCHECK(cudaSetDevice(ctx->device));
+    for (auto& r : ctx->prof) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->prof_on = enable != 0;
+    return YOHO_OK;
+}
+
+extern "C" int yoho_profile_read(yoho_ctx* ctx, double* ms_host, int64_t* launches_host, double* flops_host) {
+    YARG(ctx && ms_host && launches_host && flops_host);
+    YCHECK(cudaSetDevice(ctx->device));
+    YCHECK(cudaDeviceSynchronize());
+    for (int c = 0; c < YOHO_PROF_CLASSES; ++c) { ms_host[c] = 0; launches_host[c] = 0; flops_host[c] = 0; }
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        YCHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cls >= 0 && r.cls < YOHO_PROF_CLASSES) { ms_host[r.cls] += ms; launches_host[r.cls] += 1; flops_host[r.cls] += r.flops; }
+    }
+    return YOHO_OK;
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include "../../include/yoho_b200.h"
 
 #define YG 60
@@ -32,6 +33,7 @@ void yoho_set_error(const char* fmt, ...);
 // One group-convolution (or 1x1) layer, packed for the kernels.
 struct GLayer {
     int cin = 0, cout = 0, taps = 0;
+    int prof_class = 0;
     float* w = nullptr;       // [taps][cin][cout] fp32
     float* bias = nullptr;    // [cout]
     // tcgen05 path: bf16 hi/lo split of the weights, [taps][cout][cin] (K-major B operand)
@@ -73,6 +75,11 @@ struct yoho_ctx {
     // grow-only workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // optional per-layer event timing (yoho_profile_enable)
+    bool prof_on = false;
+    struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 int yoho_ws_reserve(yoho_ctx* ctx, size_t bytes);

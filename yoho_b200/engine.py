@@ -65,6 +65,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.yoho_launch_count(self.h))
 
+    def profile(self, enable):
+        _lib.check(self.lib.yoho_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> list of dict(name, ms, launches, flops) per group-convolution layer class (device sync)."""
+        n = _lib.PROF_CLASSES
+        ms = np.zeros(n, np.float64); ln = np.zeros(n, np.int64); fl = np.zeros(n, np.float64)
+        _lib.check(self.lib.yoho_profile_read(self.h, ms.ctypes.data, ln.ctypes.data, fl.ctypes.data))
+        return [dict(name=_lib.PROF_NAMES[i], ms=float(ms[i]), launches=int(ln[i]), flops=float(fl[i])) for i in range(n)]
+
     # ---- helpers -----------------------------------------------------------------------------------
     def _f32(self, x):
         if isinstance(x, np.ndarray):
