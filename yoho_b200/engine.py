@@ -103,6 +103,8 @@ class Engine:
         eqv = self._empty((B, 32, 60), torch.float32)
         inv = self._empty((B, 32), torch.float32) if want_inv else None
         desc = self._empty((B, 32), torch.float32) if want_desc else None
+        if B == 0:
+            return {"eqv": eqv, "inv": inv, "desc": desc}
         _lib.check(self.lib.yoho_part1_forward(self.h, _ptr(x), B, _ptr(eqv), _ptr(inv), _ptr(desc), _stream()))
         return {"eqv": eqv, "inv": inv, "desc": desc}
 
@@ -157,6 +159,8 @@ class Engine:
             stride = 1
         idx = self._empty((M,), torch.int64)
         cor = self._empty((M, 60), torch.float32) if want_cor else None
+        if M == 0:
+            return (idx, cor) if want_cor else idx
         _lib.check(self.lib.yoho_rot_argmax(self.h, _ptr(des1), r1, _ptr(des2), r2, stride, M, _ptr(idx), _ptr(cor),
                                             _stream()))
         return (idx, cor) if want_cor else idx
@@ -175,6 +179,8 @@ class Engine:
         if kps0 is not None:
             k0, k1 = self._f64(kps0), self._f64(kps1)
             trans = self._empty((M, 3, 4), torch.float64)
+        if M == 0:
+            return quat, trans
         _lib.check(self.lib.yoho_part2_forward(self.h, _ptr(f0), _ptr(f1), _ptr(y0), _ptr(y1), _ptr(pr), _ptr(pre), M,
                                                _ptr(k0), _ptr(k1), _ptr(quat), _ptr(trans), _stream()))
         return quat, trans
