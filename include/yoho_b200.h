@@ -178,6 +178,11 @@ int64_t yoho_launch_count(const yoho_ctx* ctx);
  * device and returns, for layer class c in [0, YOHO_PROF_CLASSES): total milliseconds, launches and algorithmic
  * FLOPs (2 * rows * taps * Cin * Cout per launch).  Classes: 0..3 = PartI layers 1..4, 4..6 = PartII group
  * convolutions (init, a, b), 7 = PartII 1x1 head layers. */
+/* Test hook: one PartI/PartII group-convolution layer in isolation on FP32 activations act [B,60,Cin]
+ * (full 60-element index table), raw output [B,60,Cout] = conv + bias.  layer: 0..3 = PartI layers 1..4,
+ * 4..6 = PartII init/a/b.  impl as in yoho_set_gconv_impl. */
+int yoho_debug_layer(yoho_ctx* ctx, int layer, int impl, const float* act, int B, float* out_raw, void* stream);
+
 #define YOHO_PROF_CLASSES 8
 int yoho_profile_enable(yoho_ctx* ctx, int enable);
 int yoho_profile_read(yoho_ctx* ctx, double* ms_host, int64_t* launches_host, double* flops_host);

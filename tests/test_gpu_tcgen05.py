@@ -1,0 +1,84 @@
+"""GPU: the tcgen05 split-BF16 group convolution against the FP32 SIMT kernel and the oracle.
+Runs last among the GPU files: a protocol bug in this kernel traps (by design) and poisons the CUDA context."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import real_ckpt
+import yoho_oracle as O
+from yoho_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DESC_TOL = 1e-4
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _report(name, got, want):
+    d = np.abs(got - want)
+    scale = np.abs(want).max()
+    print(f"[tc] {name}: max|d|={d.max():.3e} mean|d|={d.mean():.3e} ref_max={scale:.3e} rel={d.max() / max(scale, 1e-30):.3e}")
+    return d.max(), scale
+
+
+@pytest.mark.parametrize("layer,cin,cout", [(1, 256, 512), (2, 512, 256)])
+@pytest.mark.parametrize("B", [3, 64, 333])
+def test_layer_tc_vs_simt(engine, layer, cin, cout, B):
+    engine.load_part1(synth.synth_state_dict("PartI", 0))
+    rs = np.random.RandomState(B + layer)
+    act = np.maximum(rs.standard_normal((B, 60, cin)), 0).astype(np.float32)     # post-ReLU like the real operands
+    ref = _np(engine.debug_layer(layer, "simt", act, cout))
+    got = _np(engine.debug_layer(layer, "tcgen05", act, cout))
+    torch.cuda.synchronize()
+    err, scale = _report(f"layer{layer} B={B}", got, ref)
+    if err > 1e-3 * scale:      # diagnostics for a blind debug session: where is it wrong?
+        d = np.abs(got - ref)
+        print("[tc] worst rows (b,g):", np.argsort(d.max(axis=2).reshape(-1))[-8:], "worst cols:", np.argsort(d.max(axis=(0, 1)))[-8:])
+        print("[tc] err by 32-col block:", d.reshape(B * 60, cout // 32, 32).max(axis=(0, 2)))
+        print("[tc] err by row%8:", [float(d.reshape(-1, cout)[i::8].max()) for i in range(8)])
+        print("[tc] ratio got/ref sample:", (got.reshape(-1)[:8] / ref.reshape(-1)[:8]))
+    assert err <= 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("K", [3, 130, 2100])
+def test_part1_tc_vs_oracle(engine, tables, K):
+    _, _, N = tables
+    sd = synth.synth_state_dict("PartI", 2)
+    engine.load_part1(sd)
+    x, _ = synth.make_fragment(K, 200 + K)
+    engine.set_gconv_impl("tcgen05")
+    try:
+        o = engine.part1(x)
+        o2 = engine.part1(x)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_gconv_impl("simt")
+    s = engine.part1(x)
+    ref = O.part1_forward(x[:400], sd, N)
+    _report(f"part1 K={K} tc vs simt", _np(o["eqv"]), _np(s["eqv"]))
+    err, _ = _report(f"part1 K={K} tc vs oracle", _np(o["eqv"])[:400], ref["eqv"].numpy())
+    assert err <= DESC_TOL
+    assert np.abs(_np(o["inv"])[:400] - ref["inv"].numpy()).max() <= DESC_TOL
+    assert torch.equal(o["eqv"], o2["eqv"])                      # deterministic
+
+
+def test_part1_tc_realckpt(engine, tables):
+    sd = real_ckpt("PartI")
+    if sd is None:
+        pytest.skip("oracle/_ref/ckpt not present")
+    _, _, N = tables
+    engine.load_part1(sd)
+    x, _ = synth.make_fragment(300, 5)
+    engine.set_gconv_impl("tcgen05")
+    try:
+        o = engine.part1(x)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_gconv_impl("simt")
+    ref = O.part1_forward(x, sd, N)
+    ref64 = O.part1_forward(x, sd, N, torch.float64)
+    err, _ = _report("part1 real ckpt tc vs oracle f32", _np(o["eqv"]), ref["eqv"].numpy())
+    _report("part1 real ckpt tc vs oracle f64", _np(o["eqv"]), ref64["eqv"].numpy())
+    assert err <= DESC_TOL

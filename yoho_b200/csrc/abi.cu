@@ -237,6 +237,7 @@ int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream
     }
     int rc;
     if (ctx->gconv_impl == 1 && gconv_tc_eligible(L, a)) rc = gconv_tc_forward(ctx, L, a, st);
+    else if (!a.act) { yoho_set_error("group convolution: FP32 activations missing for the SIMT path"); rc = YOHO_ERR_ARG; }
     else rc = gconv_simt_forward(ctx, L, a, st);
     if (prof) { cudaEventRecord(rec.b, st); ctx->prof.push_back(rec); }
     return rc;
@@ -262,4 +263,34 @@ extern "C" int yoho_profile_read(yoho_ctx* ctx, double* ms_host, int64_t* launch
         if (r.cls >= 0 && r.cls < YOHO_PROF_CLASSES) { ms_host[r.cls] += ms; launches_host[r.cls] += 1; flops_host[r.cls] += r.flops; }
     }
     return YOHO_OK;
+}
+
+int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
+
+extern "C" int yoho_debug_layer(yoho_ctx* ctx, int layer, int impl, const float* act, int B, float* out_raw, void* stream) {
+    YARG(ctx && act && out_raw && B > 0 && layer >= 0 && layer <= 6 && (impl == 0 || impl == 1));
+    YARG(layer < 4 ? ctx->has_p1 : ctx->has_p2);
+    YCHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const GLayer* Ls[] = {&ctx->p1_in, &ctx->p1_a, &ctx->p1_b, &ctx->p1_out, &ctx->p2_init, &ctx->p2_a, &ctx->p2_b};
+    const GLayer& L = *Ls[layer];
+    GConvArgs a{};
+    a.idx = ctx->d_idx_full; a.B = B; a.Jin = YG; a.Jout = YG; a.act = act; a.out_raw = out_raw;
+    const int saved = ctx->gconv_impl;
+    int rc;
+    if (impl == 1) {
+        const size_t n = (size_t)B * YG * L.cin;
+        if ((rc = yoho_ws_reserve(ctx, n * 4))) return rc;
+        void* hi = ctx->ws;
+        void* lo = (char*)ctx->ws + n * 2;
+        if ((rc = gconv_split_bf16(ctx, act, hi, lo, n, st))) return rc;
+        a.act_hi = hi; a.act_lo = lo;
+        YARG(gconv_tc_eligible(L, a));
+        ctx->gconv_impl = 1;
+    } else {
+        ctx->gconv_impl = 0;
+    }
+    rc = gconv_forward(ctx, L, a, st);
+    ctx->gconv_impl = saved;
+    return rc;
 }

@@ -95,6 +95,11 @@ struct GConvArgs {
     float* out_act;          // nullable [B][Jout][Cout]   = relu(out_raw*scale + shift)
     const float* scale;      // folded BN of the NEXT layer's pre-activation (with out_act)
     const float* shift;
+    // bf16 hi/lo split of the activations (tensor-core path): inputs of this layer / outputs for the next
+    const void* act_hi;      // [B][Jin][Cin] bf16
+    const void* act_lo;
+    void* out_hi;            // nullable [B][Jout][Cout] bf16: hi/lo of relu(out_raw*scale + shift)
+    void* out_lo;
 };
 int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
 

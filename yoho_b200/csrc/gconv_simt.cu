@@ -11,6 +11,7 @@
 // at row idx[j][k]; the gather costs nothing but address arithmetic in the cp.async producer.
 // Tile 128 rows x BN cols x 16 k, 256 threads, 8 x (BN/16) outputs per thread, 3-stage cp.async pipeline.
 // Accumulation order is fixed (taps outer, channels ascending, FP32 FMA), so results are deterministic.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -42,6 +43,8 @@ struct KArgs {
     float* out_act;
     const float* scale;
     const float* shift;
+    unsigned short* out_hi;   // optional bf16 hi/lo split of out_act (feeds the tensor-core layers)
+    unsigned short* out_lo;
     int n_tiles;   // Cout / BN
     int m_total;   // B * Jout
 };
@@ -169,8 +172,8 @@ __global__ void __launch_bounds__(THREADS, 2) gconv_f32_kernel(const KArgs p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
         bias[j] = p.bias[col[j]];
-        sc[j] = p.out_act ? p.scale[col[j]] : 1.f;
-        sh[j] = p.out_act ? p.shift[col[j]] : 0.f;
+        sc[j] = (p.out_act || p.out_hi) ? p.scale[col[j]] : 1.f;
+        sh[j] = (p.out_act || p.out_hi) ? p.shift[col[j]] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -197,10 +200,19 @@ __global__ void __launch_bounds__(THREADS, 2) gconv_f32_kernel(const KArgs p) {
                 *reinterpret_cast<float2*>(p.out_raw + o + col[0]) = make_float2(v[0], v[1]);
             }
         }
-        if (p.out_act) {
+        if (p.out_act || p.out_hi) {
             float w[TN];
 #pragma unroll
             for (int j = 0; j < TN; ++j) w[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+            if (p.out_hi) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(w[j]);
+                    p.out_hi[o + col[j]] = __bfloat16_as_ushort(h);
+                    p.out_lo[o + col[j]] = __bfloat16_as_ushort(__float2bfloat16_rn(w[j] - __bfloat162float(h)));
+                }
+            }
+            if (p.out_act) {
             if constexpr (TN == 8) {
                 *reinterpret_cast<float4*>(p.out_act + o + col[0]) = make_float4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<float4*>(p.out_act + o + col[4]) = make_float4(w[4], w[5], w[6], w[7]);
@@ -208,6 +220,7 @@ __global__ void __launch_bounds__(THREADS, 2) gconv_f32_kernel(const KArgs p) {
                 *reinterpret_cast<float4*>(p.out_act + o + col[0]) = make_float4(w[0], w[1], w[2], w[3]);
             } else {
                 *reinterpret_cast<float2*>(p.out_act + o + col[0]) = make_float2(w[0], w[1]);
+            }
             }
         }
     }
@@ -239,6 +252,7 @@ int gconv_simt_forward(yoho_ctx* ctx, const GLayer& Lr, const GConvArgs& a, cuda
     k.B = a.B; k.Jin = a.Jin; k.Jout = a.Jout; k.Cin = Lr.cin; k.Cout = Lr.cout; k.taps = Lr.taps;
     k.resid = a.resid; k.Jres = a.Jres; k.resid_off = a.resid_off; k.resid_per_j = a.resid_per_j;
     k.out_raw = a.out_raw; k.out_act = a.out_act; k.scale = a.scale; k.shift = a.shift;
+    k.out_hi = (unsigned short*)a.out_hi; k.out_lo = (unsigned short*)a.out_lo;
     k.m_total = a.B * a.Jout;
     const int m_tiles = (k.m_total + BM - 1) / BM;
     // widest tile that still gives every SM at least two CTAs; narrow tiles for small-M layers

@@ -1,10 +1,431 @@
-// tcgen05 split-BF16 group convolution (placeholder until the tensor-core kernel lands in this file).
+// tcgen05 group convolution: the gather-GEMM of gconv_simt.cu on 5th-generation tensor cores.
+//
+//   D[(b,j), o] = sum_k sum_c act[b, idx[j][k], c] * W_k[c][o]          FP32-accurate via a 2-term BF16 split
+//       act = a_hi + a_lo,  W = w_hi + w_lo   (bf16 each)      D = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  (+O(2^-17))
+//
+// The 1e-4 descriptor bar rules out single-pass TF32/BF16 (measured 6e-4 / 4e-3 on the shipped checkpoint,
+// SURVEY.md §7 hard part 1); three BF16 products per MAC measure 8e-6, at one third of the dense
+// BF16 peak by construction.
+//
+// Kernel (persistent, one CTA per SM, 320 threads, warp-specialised):
+//   warps 0-3   A producers: each thread owns one of the 128 tile rows and gathers its 64-channel slice (hi and
+//               lo) for the current tap straight from L2 with 16-byte cp.async into the 128B-swizzled K-major
+//               layout UMMA expects — the group gather idx[j][k] is pure address arithmetic here.
+//   warp  8     W producer: the weights are pre-packed on the host as ready-made swizzled 32 KB tiles, so one
+//               cp.async.bulk (TMA, 1-D) per tile lands them in shared memory and signals the stage mbarrier.
+//   warp  9     MMA issuer: one thread issues 12 tcgen05.mma (M128 x N256 x K16, kind::f16) per 64-wide K block,
+//               accumulating all 13 taps x Cin channels of a tile in TMEM; tcgen05.commit releases the stage.
+//   warps 4-7   epilogue: tcgen05.ld the 128x256 FP32 accumulator (double-buffered in the 512 TMEM columns, so the
+//               next tile's MMAs overlap), add bias / residual, apply the NEXT layer's folded BN + ReLU, and write
+//               the activation as a bf16 hi/lo pair (the next layer's A operand) and/or FP32.
 #include <vector>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
-int gconv_tc_pack(yoho_ctx*, GLayer&, const std::vector<float>&) { return YOHO_OK; }
-bool gconv_tc_eligible(const GLayer&, const GConvArgs&) { return false; }
-int gconv_tc_forward(yoho_ctx*, const GLayer&, const GConvArgs&, cudaStream_t) {
-    yoho_set_error("tcgen05 group convolution not built");
-    return YOHO_ERR_ARG;
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;                       // bf16 elements per K block = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int A_TILE = BM * BK * 2;          // 16 KB (hi or lo)
+constexpr int W_TILE = BN * BK * 2;          // 32 KB (hi or lo)
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;   // 96 KB
+constexpr int THREADS = 320;
+constexpr int TMEM_COLS = 512;               // two 256-column FP32 accumulators
+
+struct TcArgs {
+    const __nv_bfloat16* a_hi;   // [B][Jin][Cin]
+    const __nv_bfloat16* a_lo;
+    const uint8_t* w_hi;         // [n_tiles][nkb] swizzled 32 KB tiles
+    const uint8_t* w_lo;
+    const float* bias;
+    const int* idx;
+    int Jin, Jout, Cin, Cout, taps;
+    int m_total, m_tiles, n_tiles, nkb;
+    const float* resid;
+    int Jres, resid_off, resid_per_j;
+    float* out_raw;
+    float* out_act;              // FP32 activation (optional)
+    __nv_bfloat16* out_hi;       // bf16 split activation (optional)
+    __nv_bfloat16* out_lo;
+    const float* scale;
+    const float* shift;
+};
+
+struct __align__(8) Barriers {
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+    unsigned long long tmem_full[2];
+    unsigned long long tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    const uint32_t a = smem_u32(b);
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (spins > (1u << 26)) asm volatile("trap;\n");   // a protocol bug must fail loudly, not hang the box
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t umma_desc(const void* smem_tile) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem_tile) >> 4) & 0x3FFFull;
+    return addr | (1ull << 16) /* LBO (unused for swizzled K-major) */ | (64ull << 32) /* SBO = 1024 B */ |
+           (1ull << 46) /* descriptor version: Blackwell */ | (2ull << 61) /* SWIZZLE_128B */;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor).
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    float* ep_bias = (float*)(smem + STAGES * STAGE_BYTES);
+    float* ep_scale = ep_bias + 512;
+    float* ep_shift = ep_scale + 512;
+    int* idx_s = (int*)(ep_shift + 512);
+    Barriers* bars = (Barriers*)(idx_s + 64 * 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < p.Jout * p.taps; i += THREADS) idx_s[i] = p.idx[i];
+    for (int i = threadIdx.x; i < p.Cout; i += THREADS) {
+        ep_bias[i] = p.bias[i];
+        ep_scale[i] = p.scale ? p.scale[i] : 1.f;
+        ep_shift[i] = p.shift ? p.shift[i] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bars->full[s], 128 + 1);   // 128 A-producer threads + the W producer's expect_tx arrive
+            mbar_init(&bars->empty[s], 1);        // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->tmem_full[a], 1);    // tcgen05.commit
+            mbar_init(&bars->tmem_empty[a], 128); // epilogue threads
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int cblocks = p.Cin / BK;
+
+    if (warp < 4) {
+        // ================= A producers =================
+        const int r = threadIdx.x;                 // tile row 0..127
+        const uint32_t swz = (uint32_t)(r & 7);
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles;
+            const int row = m_tile * BM + r;
+            const bool ok = row < p.m_total;
+            const int rr = ok ? row : 0;
+            const int b = rr / p.Jout;
+            const int j = rr - b * p.Jout;
+            const size_t rowbase = (size_t)b * p.Jin;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int k = kb / cblocks;
+                const int c0 = (kb - k * cblocks) * BK;
+                const size_t off = ((rowbase + idx_s[j * p.taps + k]) * p.Cin + c0);
+                const uint8_t* src_hi = (const uint8_t*)(p.a_hi + off);
+                const uint8_t* src_lo = (const uint8_t*)(p.a_lo + off);
+                uint8_t* dst_hi = stage_base + stage * STAGE_BYTES + r * 128;
+                uint8_t* dst_lo = dst_hi + A_TILE;
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) {
+                    cp_async16(dst_hi + ((c ^ swz) << 4), src_hi + (c << 4), ok);
+                    cp_async16(dst_lo + ((c ^ swz) << 4), src_lo + (c << 4), ok);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(&bars->full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 8) {
+        // ================= W producer (one thread) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const uint8_t* wh = p.w_hi + (size_t)n_tile * p.nkb * W_TILE;
+                const uint8_t* wl = p.w_lo + (size_t)n_tile * p.nkb * W_TILE;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    uint8_t* dst = stage_base + stage * STAGE_BYTES + 2 * A_TILE;
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bars->full[stage], 2 * W_TILE);
+                    bulk_g2s(dst, wh + (size_t)kb * W_TILE, W_TILE, &bars->full[stage]);
+                    bulk_g2s(dst + W_TILE, wl + (size_t)kb * W_TILE, W_TILE, &bars->full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint8_t* st = stage_base + stage * STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
+                    const uint64_t w_hi = umma_desc(st + 2 * A_TILE), w_lo = umma_desc(st + 2 * A_TILE + W_TILE);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per 16 bf16, in 16-byte units
+                        tc_mma(d_tmem, a_hi + adv, w_hi + adv, IDESC, (kb | (int)ks) ? 1u : 0u);
+                        tc_mma(d_tmem, a_lo + adv, w_hi + adv, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + adv, w_lo + adv, IDESC, 1u);
+                    }
+                    tc_commit(&bars->empty[stage]);            // stage reusable once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&bars->tmem_full[acc]);              // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue warps 4..7 =================
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles;
+            const int n_tile = tile - m_tile * p.n_tiles;
+            const int row = m_tile * BM + q * 32 + lane;
+            const bool ok = row < p.m_total;
+            const int n0 = n_tile * BN;
+            const float* rres = nullptr;
+            if (p.resid && ok) {
+                const int b = row / p.Jout;
+                const int j = row - b * p.Jout;
+                rres = p.resid + ((size_t)b * p.Jres + p.resid_off + (p.resid_per_j ? j : 0)) * p.Cout + n0;
+            }
+            mbar_wait(&bars->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+            const size_t orow = (size_t)(ok ? row : 0) * p.Cout + n0;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(t_addr + cc * 32, v);     // .sync.aligned: executed by the whole warp, rows past the end included
+                if (ok) {
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + ep_bias[n0 + cc * 32 + i];
+                if (rres) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 rv = *reinterpret_cast<const float4*>(rres + cc * 32 + i);
+                        f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
+                    }
+                }
+                if (p.out_raw) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(p.out_raw + orow + cc * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                }
+                if (p.out_act || p.out_hi) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        f[i] = fmaxf(fmaf(f[i], ep_scale[n0 + cc * 32 + i], ep_shift[n0 + cc * 32 + i]), 0.f);
+                    if (p.out_act) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(p.out_act + orow + cc * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                    }
+                    if (p.out_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
+                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + orow + cc * 32);
+                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + orow + cc * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                            dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                        }
+                    }
+                }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + 3 * 512 * sizeof(float) +
+                              64 * 13 * sizeof(int) + sizeof(Barriers) + 64;
+
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(f[k]);
+        h[k] = __bfloat16_as_ushort(hh);
+        l[k] = __bfloat16_as_ushort(__float2bfloat16_rn(f[k] - __bfloat162float(hh)));
+    }
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+inline unsigned short f2bf(float f) {   // round-to-nearest-even, host side (weights are finite)
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+inline float bf2f(unsigned short h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+// Host-side packing: W_k[c][o] fp32 -> bf16 hi/lo, laid out as [n_tile][kb] ready-to-copy 32 KB tiles in the UMMA
+// K-major SWIZZLE_128B image (row r at r*128 bytes, 16-byte chunk j stored at position j ^ (r & 7)).
+int gconv_tc_pack(yoho_ctx*, GLayer& L, const std::vector<float>& w) {
+    if (L.taps != YT || L.cin % BK != 0 || L.cout % BN != 0) return YOHO_OK;   // not a tensor-core layer
+    const int nkb = L.taps * (L.cin / BK), n_tiles = L.cout / BN, cblocks = L.cin / BK;
+    const size_t bytes = (size_t)n_tiles * nkb * W_TILE;
+    std::vector<unsigned short> hi(bytes / 2), lo(bytes / 2);
+    for (int nt = 0; nt < n_tiles; ++nt)
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int k = kb / cblocks, c0 = (kb % cblocks) * BK;
+            const size_t tile = ((size_t)nt * nkb + kb) * (W_TILE / 2);
+            for (int r = 0; r < BN; ++r)
+                for (int i = 0; i < BK; ++i) {
+                    const float v = w[((size_t)k * L.cin + c0 + i) * L.cout + nt * BN + r];
+                    const unsigned short h = f2bf(v);
+                    const size_t pos = tile + (size_t)r * 64 + (size_t)(((i >> 3) ^ (r & 7)) << 3) + (i & 7);
+                    hi[pos] = h;
+                    lo[pos] = f2bf(v - bf2f(h));
+                }
+        }
+    YCHECK(cudaMalloc(&L.w_hi, bytes));
+    YCHECK(cudaMalloc(&L.w_lo, bytes));
+    YCHECK(cudaMemcpy(L.w_hi, hi.data(), bytes, cudaMemcpyHostToDevice));
+    YCHECK(cudaMemcpy(L.w_lo, lo.data(), bytes, cudaMemcpyHostToDevice));
+    return YOHO_OK;
+}
+
+bool gconv_tc_eligible(const GLayer& L, const GConvArgs& a) {
+    return L.w_hi && L.w_lo && a.act_hi && a.act_lo && a.B * a.Jout >= BM && a.Jout * L.taps <= 64 * 13;
+}
+
+int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n, cudaStream_t st) {
+    YARG(n % 4 == 0);
+    const size_t n4 = n / 4;
+    split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n4);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
+    YARG(gconv_tc_eligible(L, a));
+    static bool attr_done = false;
+    if (!attr_done) {
+        YCHECK(cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_done = true;
+    }
+    TcArgs p;
+    p.a_hi = (const __nv_bfloat16*)a.act_hi; p.a_lo = (const __nv_bfloat16*)a.act_lo;
+    p.w_hi = (const uint8_t*)L.w_hi; p.w_lo = (const uint8_t*)L.w_lo;
+    p.bias = L.bias; p.idx = a.idx;
+    p.Jin = a.Jin; p.Jout = a.Jout; p.Cin = L.cin; p.Cout = L.cout; p.taps = L.taps;
+    p.m_total = a.B * a.Jout; p.m_tiles = (p.m_total + BM - 1) / BM; p.n_tiles = L.cout / BN;
+    p.nkb = L.taps * (L.cin / BK);
+    p.resid = a.resid; p.Jres = a.Jres; p.resid_off = a.resid_off; p.resid_per_j = a.resid_per_j;
+    p.out_raw = a.out_raw; p.out_act = a.out_act;
+    p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
+    p.scale = a.scale; p.shift = a.shift;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    gconv_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
 }

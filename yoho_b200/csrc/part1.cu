@@ -112,36 +112,48 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
     }
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
+    const bool tc_on = ctx->gconv_impl == 1 && ctx->p1_a.w_hi && ctx->p1_b.w_hi;
+    // per keypoint: xt 32, y1 256, a1 256 (fp32, or bf16 hi+lo = same bytes), a2 512 (same), a3 256, y4 32 floats x 60
     const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 32) * sizeof(float);
     const int chunk = B < P1_CHUNK ? B : P1_CHUNK;
     if (int rc = yoho_ws_reserve(ctx, per_kp * (size_t)chunk)) return rc;
     for (int s = 0; s < B; s += chunk) {
         const int n = (B - s) < chunk ? (B - s) : chunk;
+        const bool tc = tc_on && n * YG >= 128;   // a tensor-core tile is 128 rows
         float* xt = (float*)ctx->ws;
         float* y1 = xt + (size_t)n * YG * 32;
         float* a1 = y1 + (size_t)n * YG * 256;
         float* a2 = a1 + (size_t)n * YG * 256;
         float* a3 = a2 + (size_t)n * YG * 512;
         float* y4 = a3 + (size_t)n * YG * 256;
+        // tensor-core path: the same regions hold bf16 hi|lo halves instead of fp32
+        unsigned short* a1_hi = (unsigned short*)a1;
+        unsigned short* a1_lo = a1_hi + (size_t)n * YG * 256;
+        unsigned short* a2_hi = (unsigned short*)a2;
+        unsigned short* a2_lo = a2_hi + (size_t)n * YG * 512;
         const float* xs = x + (size_t)s * YF * YG;
         transpose_in_kernel<<<n, 128, 0, st>>>(xs, xt, n);
         ctx->launches++;
         GConvArgs a{};
         a.idx = ctx->d_idx_full; a.B = n; a.Jin = YG; a.Jout = YG;
         // layer 1: raw y1 (shortcut) + a1 = relu(BN_a(y1))
-        a.act = xt; a.resid = nullptr; a.out_raw = y1; a.out_act = a1;
+        a.act = xt; a.resid = nullptr; a.out_raw = y1;
         a.scale = ctx->p1_bn_a.scale; a.shift = ctx->p1_bn_a.shift;
+        if (tc) { a.out_act = nullptr; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.out_act = a1; }
         if (int rc = gconv_forward(ctx, ctx->p1_in, a, st)) return rc;
         // layer 2: a2 = relu(BN_b(GC_a(a1)))
-        a.act = a1; a.out_raw = nullptr; a.out_act = a2;
+        a.out_raw = nullptr;
         a.scale = ctx->p1_bn_b.scale; a.shift = ctx->p1_bn_b.shift;
+        if (tc) { a.act = nullptr; a.act_hi = a1_hi; a.act_lo = a1_lo; a.out_act = nullptr; a.out_hi = a2_hi; a.out_lo = a2_lo; }
+        else { a.act = a1; a.out_act = a2; }
         if (int rc = gconv_forward(ctx, ctx->p1_a, a, st)) return rc;
         // layer 3: a3 = relu(BN_o(GC_b(a2) + y1))
-        a.act = a2; a.resid = y1; a.Jres = YG; a.resid_off = 0; a.resid_per_j = 1; a.out_act = a3;
+        a.resid = y1; a.Jres = YG; a.resid_off = 0; a.resid_per_j = 1; a.out_act = a3; a.out_hi = a.out_lo = nullptr;
         a.scale = ctx->p1_bn_out.scale; a.shift = ctx->p1_bn_out.shift;
+        if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; } else { a.act = a2; }
         if (int rc = gconv_forward(ctx, ctx->p1_b, a, st)) return rc;
         // layer 4: y4 = GC_out(a3)
-        a.act = a3; a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.scale = a.shift = nullptr;
+        a.act = a3; a.act_hi = a.act_lo = nullptr; a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.scale = a.shift = nullptr;
         if (int rc = gconv_forward(ctx, ctx->p1_out, a, st)) return rc;
         part1_finalize_kernel<<<n, 64, 0, st>>>(y4, xs, eqv + (size_t)s * YF * YG, inv ? inv + (size_t)s * YF : nullptr,
                                                 desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);

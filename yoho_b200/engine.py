@@ -65,6 +65,14 @@ class Engine:
     def launch_count(self):
         return int(self.lib.yoho_launch_count(self.h))
 
+    def debug_layer(self, layer, impl, act, cout):
+        """Test hook: one group-convolution layer on FP32 activations [B,60,Cin] -> raw [B,60,cout]."""
+        act = self._f32(act)
+        B = act.shape[0]
+        out = self._empty((B, 60, cout), torch.float32)
+        _lib.check(self.lib.yoho_debug_layer(self.h, layer, {"simt": 0, "tcgen05": 1}[impl], _ptr(act), B, _ptr(out), _stream()))
+        return out
+
     def profile(self, enable):
         _lib.check(self.lib.yoho_profile_enable(self.h, 1 if enable else 0))
 
