@@ -23,7 +23,7 @@ def _report(name, got, want):
     return d.max(), scale
 
 
-@pytest.mark.parametrize("layer,cin,cout", [(1, 256, 512), (2, 512, 256)])
+@pytest.mark.parametrize("layer,cin,cout", [(1, 256, 512), (2, 512, 256), (0, 32, 256), (3, 256, 32)])
 @pytest.mark.parametrize("B", [3, 64, 333])
 def test_layer_tc_vs_simt(engine, layer, cin, cout, B):
     engine.load_part1(synth.synth_state_dict("PartI", 0))
@@ -81,4 +81,49 @@ def test_part1_tc_realckpt(engine, tables):
     ref64 = O.part1_forward(x, sd, N, torch.float64)
     err, _ = _report("part1 real ckpt tc vs oracle f32", _np(o["eqv"]), ref["eqv"].numpy())
     _report("part1 real ckpt tc vs oracle f64", _np(o["eqv"]), ref64["eqv"].numpy())
+    assert err <= DESC_TOL
+
+
+@pytest.mark.parametrize("M", [130, 700])
+def test_part2_tc_vs_oracle(engine, tables, M):
+    R, P, N = tables
+    sd = synth.synth_state_dict("PartII", 4)
+    engine.load_part2(sd)
+    rs = np.random.RandomState(M)
+    fA, _ = synth.make_fragment(M, 40 + M)
+    fB, _ = synth.make_fragment(M, 50 + M)
+    yA, _ = synth.make_fragment(M, 60 + M)
+    yB, _ = synth.make_fragment(M, 70 + M)
+    pre = rs.randint(0, 60, M).astype(np.int64)
+    engine.set_gconv_impl("tcgen05")
+    try:
+        q, _ = engine.part2(fA, fB, yA, yB, pre)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_gconv_impl("simt")
+    q2, _ = engine.part2(fA, fB, yA, yB, pre)
+    _report(f"part2 M={M} tc vs simt", _np(q), _np(q2))
+    want = O.part2_forward(fA[:200], fB[:200], yA[:200], yB[:200], pre[:200], sd, P, N)
+    err, _ = _report(f"part2 M={M} tc vs oracle", _np(q)[:200], want.numpy())
+    assert err <= DESC_TOL
+
+
+def test_part2_tc_realckpt(engine, tables):
+    sd = real_ckpt("PartII")
+    if sd is None:
+        pytest.skip("oracle/_ref/ckpt not present")
+    R, P, N = tables
+    engine.load_part2(sd)
+    M = 256
+    fA, _ = synth.make_fragment(M, 1); fB, _ = synth.make_fragment(M, 2)
+    yA, _ = synth.make_fragment(M, 3); yB, _ = synth.make_fragment(M, 4)
+    pre = np.random.RandomState(0).randint(0, 60, M).astype(np.int64)
+    engine.set_gconv_impl("tcgen05")
+    try:
+        q, _ = engine.part2(fA, fB, yA, yB, pre)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_gconv_impl("simt")
+    want = O.part2_forward(fA, fB, yA, yB, pre, sd, P, N)
+    err, _ = _report("part2 real ckpt tc vs oracle", _np(q), want.numpy())
     assert err <= DESC_TOL

@@ -25,14 +25,24 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
 constexpr int BK = 64;                       // bf16 elements per K block = one 128-byte swizzle row
-constexpr int STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;          // 16 KB (hi or lo)
-constexpr int W_TILE = BN * BK * 2;          // 32 KB (hi or lo)
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;   // 96 KB
 constexpr int THREADS = 320;
-constexpr int TMEM_COLS = 512;               // two 256-column FP32 accumulators
+constexpr int MAX_STAGES = 4;
+
+// Tile width BN = 256 for the wide layers (2 stages of 96 KB, two 256-column accumulators = all of TMEM) and
+// BN = 32 for the 256 -> 32 output layer (4 stages of 40 KB; that layer is bound by streaming A from L2).
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = BN == 256 ? 2 : 4;
+    static constexpr int W_TILE = BN * BK * 2;                        // bytes (hi or lo)
+    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;       // two accumulators, power of two >= 32
+    // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=128 (cute::UMMA::InstrDescriptor)
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + 3 * 512 * sizeof(float) +
+                                         64 * 13 * sizeof(int) + 256;
+};
 
 struct TcArgs {
     const __nv_bfloat16* a_hi;   // [B][Jin][Cin]
@@ -54,8 +64,8 @@ struct TcArgs {
 };
 
 struct __align__(8) Barriers {
-    unsigned long long full[STAGES];
-    unsigned long long empty[STAGES];
+    unsigned long long full[MAX_STAGES];
+    unsigned long long empty[MAX_STAGES];
     unsigned long long tmem_full[2];
     unsigned long long tmem_empty[2];
     uint32_t tmem_base;
@@ -106,8 +116,6 @@ __device__ __forceinline__ uint64_t umma_desc(const void* smem_tile) {
     return addr | (1ull << 16) /* LBO (unused for swizzled K-major) */ | (64ull << 32) /* SBO = 1024 B */ |
            (1ull << 46) /* descriptor version: Blackwell */ | (2ull << 61) /* SWIZZLE_128B */;
 }
-// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor).
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -122,7 +130,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
+    constexpr int STAGES = Cfg<BN>::STAGES;
+    constexpr int W_TILE = Cfg<BN>::W_TILE;
+    constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
+    constexpr uint32_t IDESC = Cfg<BN>::IDESC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const int total_tiles = p.m_tiles * p.n_tiles;
-    const int cblocks = p.Cin / BK;
+    const int cblocks = p.Cin >= BK ? p.Cin / BK : 1;
 
     if (warp < 4) {
         // ================= A producers =================
@@ -180,18 +194,34 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             const int j = rr - b * p.Jout;
             const size_t rowbase = (size_t)b * p.Jin;
             for (int kb = 0; kb < p.nkb; ++kb) {
-                const int k = kb / cblocks;
-                const int c0 = (kb - k * cblocks) * BK;
-                const size_t off = ((rowbase + idx_s[j * p.taps + k]) * p.Cin + c0);
-                const uint8_t* src_hi = (const uint8_t*)(p.a_hi + off);
-                const uint8_t* src_lo = (const uint8_t*)(p.a_lo + off);
+                // K axis = tap-major, channel-minor.  Cin >= 64: one tap per K block.  Cin == 32: two taps per block
+                // (chunks 0-3 from tap 2kb, chunks 4-7 from tap 2kb+1; the 14th half-block is zero padding).
+                const uint8_t *src_hi[2], *src_lo[2];
+                bool okh[2];
+                if (p.Cin >= BK) {
+                    const int k = kb / cblocks;
+                    const int c0 = (kb - k * cblocks) * BK;
+                    const size_t off = ((rowbase + idx_s[j * p.taps + k]) * p.Cin + c0);
+                    src_hi[0] = (const uint8_t*)(p.a_hi + off); src_lo[0] = (const uint8_t*)(p.a_lo + off);
+                    src_hi[1] = src_hi[0] + 64; src_lo[1] = src_lo[0] + 64;
+                    okh[0] = okh[1] = ok;
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = 2 * kb + h;
+                        okh[h] = ok && k < p.taps;
+                        const size_t off = (rowbase + idx_s[j * p.taps + (k < p.taps ? k : 0)]) * p.Cin;
+                        src_hi[h] = (const uint8_t*)(p.a_hi + off); src_lo[h] = (const uint8_t*)(p.a_lo + off);
+                    }
+                }
                 uint8_t* dst_hi = stage_base + stage * STAGE_BYTES + r * 128;
                 uint8_t* dst_lo = dst_hi + A_TILE;
                 mbar_wait(&bars->empty[stage], phase ^ 1);
 #pragma unroll
                 for (uint32_t c = 0; c < 8; ++c) {
-                    cp_async16(dst_hi + ((c ^ swz) << 4), src_hi + (c << 4), ok);
-                    cp_async16(dst_lo + ((c ^ swz) << 4), src_lo + (c << 4), ok);
+                    const int h = c >> 2;
+                    cp_async16(dst_hi + ((c ^ swz) << 4), src_hi[h] + ((c & 3) << 4), okh[h]);
+                    cp_async16(dst_lo + ((c ^ swz) << 4), src_lo[h] + ((c & 3) << 4), okh[h]);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -330,9 +360,6 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     }
 }
 
-constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + 3 * 512 * sizeof(float) +
-                              64 * 13 * sizeof(int) + sizeof(Barriers) + 64;
-
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -364,35 +391,49 @@ inline float bf2f(unsigned short h) {
 
 }  // namespace
 
-// Host-side packing: W_k[c][o] fp32 -> bf16 hi/lo, laid out as [n_tile][kb] ready-to-copy 32 KB tiles in the UMMA
-// K-major SWIZZLE_128B image (row r at r*128 bytes, 16-byte chunk j stored at position j ^ (r & 7)).
+// Host-side packing: W_k[c][o] fp32 -> bf16 hi/lo, laid out as [n_tile][kb] ready-to-copy tiles (BN rows x 128 B) in the
+// UMMA K-major SWIZZLE_128B image (row r at r*128 bytes, 16-byte chunk j stored at position j ^ (r & 7)).
+// K axis = tap-major, channel-minor, zero-padded to a multiple of 64 (only Cin = 32 needs padding: 416 -> 448).
+static int tc_tile_n(const GLayer& L) {
+    if (L.taps != YT) return 0;
+    if (!(L.cin == 32 || L.cin % BK == 0)) return 0;
+    if (L.cout % 256 == 0) return 256;
+    if (L.cout == 32) return 32;
+    return 0;
+}
+
 int gconv_tc_pack(yoho_ctx*, GLayer& L, const std::vector<float>& w) {
-    if (L.taps != YT || L.cin % BK != 0 || L.cout % BN != 0) return YOHO_OK;   // not a tensor-core layer
-    const int nkb = L.taps * (L.cin / BK), n_tiles = L.cout / BN, cblocks = L.cin / BK;
-    const size_t bytes = (size_t)n_tiles * nkb * W_TILE;
-    std::vector<unsigned short> hi(bytes / 2), lo(bytes / 2);
+    const int bn = tc_tile_n(L);
+    if (!bn) return YOHO_OK;   // not a tensor-core layer
+    const int ktot = L.taps * L.cin;
+    const int nkb = (ktot + BK - 1) / BK, n_tiles = L.cout / bn;
+    const size_t tile_elems = (size_t)bn * BK;
+    const size_t elems = (size_t)n_tiles * nkb * tile_elems;
+    std::vector<unsigned short> hi(elems, 0), lo(elems, 0);
     for (int nt = 0; nt < n_tiles; ++nt)
         for (int kb = 0; kb < nkb; ++kb) {
-            const int k = kb / cblocks, c0 = (kb % cblocks) * BK;
-            const size_t tile = ((size_t)nt * nkb + kb) * (W_TILE / 2);
-            for (int r = 0; r < BN; ++r)
+            const size_t tile = ((size_t)nt * nkb + kb) * tile_elems;
+            for (int r = 0; r < bn; ++r)
                 for (int i = 0; i < BK; ++i) {
-                    const float v = w[((size_t)k * L.cin + c0 + i) * L.cout + nt * BN + r];
+                    const int kk = kb * BK + i;
+                    if (kk >= ktot) continue;
+                    const int k = kk / L.cin, c = kk - k * L.cin;
+                    const float v = w[((size_t)k * L.cin + c) * L.cout + nt * bn + r];
                     const unsigned short h = f2bf(v);
                     const size_t pos = tile + (size_t)r * 64 + (size_t)(((i >> 3) ^ (r & 7)) << 3) + (i & 7);
                     hi[pos] = h;
                     lo[pos] = f2bf(v - bf2f(h));
                 }
         }
-    YCHECK(cudaMalloc(&L.w_hi, bytes));
-    YCHECK(cudaMalloc(&L.w_lo, bytes));
-    YCHECK(cudaMemcpy(L.w_hi, hi.data(), bytes, cudaMemcpyHostToDevice));
-    YCHECK(cudaMemcpy(L.w_lo, lo.data(), bytes, cudaMemcpyHostToDevice));
+    YCHECK(cudaMalloc(&L.w_hi, elems * 2));
+    YCHECK(cudaMalloc(&L.w_lo, elems * 2));
+    YCHECK(cudaMemcpy(L.w_hi, hi.data(), elems * 2, cudaMemcpyHostToDevice));
+    YCHECK(cudaMemcpy(L.w_lo, lo.data(), elems * 2, cudaMemcpyHostToDevice));
     return YOHO_OK;
 }
 
 bool gconv_tc_eligible(const GLayer& L, const GConvArgs& a) {
-    return L.w_hi && L.w_lo && a.act_hi && a.act_lo && a.B * a.Jout >= BM && a.Jout * L.taps <= 64 * 13;
+    return L.w_hi && L.w_lo && tc_tile_n(L) && a.act_hi && a.act_lo && a.B * a.Jout >= BM && a.Jout * L.taps <= 64 * 13;
 }
 
 int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n, cudaStream_t st) {
@@ -404,28 +445,34 @@ int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n
     return YOHO_OK;
 }
 
-int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
-    YARG(gconv_tc_eligible(L, a));
+template <int BN>
+static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        YCHECK(cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES));
         attr_done = true;
     }
+    p.n_tiles = p.Cout / BN;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    gconv_tc_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(p);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
+
+int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
+    YARG(gconv_tc_eligible(L, a));
     TcArgs p;
     p.a_hi = (const __nv_bfloat16*)a.act_hi; p.a_lo = (const __nv_bfloat16*)a.act_lo;
     p.w_hi = (const uint8_t*)L.w_hi; p.w_lo = (const uint8_t*)L.w_lo;
     p.bias = L.bias; p.idx = a.idx;
     p.Jin = a.Jin; p.Jout = a.Jout; p.Cin = L.cin; p.Cout = L.cout; p.taps = L.taps;
-    p.m_total = a.B * a.Jout; p.m_tiles = (p.m_total + BM - 1) / BM; p.n_tiles = L.cout / BN;
-    p.nkb = L.taps * (L.cin / BK);
+    p.m_total = a.B * a.Jout; p.m_tiles = (p.m_total + BM - 1) / BM;
+    p.nkb = (L.taps * L.cin + BK - 1) / BK;
     p.resid = a.resid; p.Jres = a.Jres; p.resid_off = a.resid_off; p.resid_per_j = a.resid_per_j;
     p.out_raw = a.out_raw; p.out_act = a.out_act;
     p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
     p.scale = a.scale; p.shift = a.shift;
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    gconv_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
-    ctx->launches++;
-    YCHECK(cudaGetLastError());
-    return YOHO_OK;
+    return tc_tile_n(L) == 256 ? tc_launch<256>(ctx, p, st) : tc_launch<32>(ctx, p, st);
 }

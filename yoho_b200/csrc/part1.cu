@@ -6,19 +6,31 @@
 //   a3 = relu(BN_o(GC_b(a2) + y1))                                                             (:57-65,:91)
 //   y4 = GC_out(a3)                                                                            (:92)
 //   e = y4 + x0 ; inv = normalise(mean_g e) ; eqv = e / max(||e||_c, 1e-4) ; desc = mean_g eqv (:98-103, tests/matcher.py:35)
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
 
 // [B][32][60] -> [B][60][32]; one CTA per keypoint.
-__global__ void __launch_bounds__(128) transpose_in_kernel(const float* __restrict__ x, float* __restrict__ xt, int B) {
+// With hi/lo given the transposed tile is written as a bf16 split instead (tensor-core path).
+__global__ void __launch_bounds__(128) transpose_in_kernel(const float* __restrict__ x, float* __restrict__ xt,
+                                                          unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
     __shared__ float s[YF][YG + 1];
     const int b = blockIdx.x;
     const float* src = x + (size_t)b * YF * YG;
     for (int i = threadIdx.x; i < YF * YG; i += blockDim.x) s[i / YG][i % YG] = src[i];
     __syncthreads();
-    float* dst = xt + (size_t)b * YF * YG;
-    for (int i = threadIdx.x; i < YF * YG; i += blockDim.x) dst[i] = s[i % YF][i / YF];
+    const size_t o = (size_t)b * YF * YG;
+    for (int i = threadIdx.x; i < YF * YG; i += blockDim.x) {
+        const float v = s[i % YF][i / YF];
+        if (hi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            hi[o + i] = __bfloat16_as_ushort(h);
+            lo[o + i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+        } else {
+            xt[o + i] = v;
+        }
+    }
 }
 
 // numpy's float32 pairwise summation of 60 contiguous values followed by /60
@@ -112,7 +124,7 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
     }
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
-    const bool tc_on = ctx->gconv_impl == 1 && ctx->p1_a.w_hi && ctx->p1_b.w_hi;
+    const bool tc_on = ctx->gconv_impl == 1 && ctx->p1_in.w_hi && ctx->p1_a.w_hi && ctx->p1_b.w_hi && ctx->p1_out.w_hi;
     // per keypoint: xt 32, y1 256, a1 256 (fp32, or bf16 hi+lo = same bytes), a2 512 (same), a3 256, y4 32 floats x 60
     const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 32) * sizeof(float);
     const int chunk = B < P1_CHUNK ? B : P1_CHUNK;
@@ -127,33 +139,37 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         float* a3 = a2 + (size_t)n * YG * 512;
         float* y4 = a3 + (size_t)n * YG * 256;
         // tensor-core path: the same regions hold bf16 hi|lo halves instead of fp32
+        unsigned short* xt_hi = (unsigned short*)xt;
+        unsigned short* xt_lo = xt_hi + (size_t)n * YG * 32;
         unsigned short* a1_hi = (unsigned short*)a1;
         unsigned short* a1_lo = a1_hi + (size_t)n * YG * 256;
         unsigned short* a2_hi = (unsigned short*)a2;
         unsigned short* a2_lo = a2_hi + (size_t)n * YG * 512;
+        unsigned short* a3_hi = (unsigned short*)a3;
+        unsigned short* a3_lo = a3_hi + (size_t)n * YG * 256;
         const float* xs = x + (size_t)s * YF * YG;
-        transpose_in_kernel<<<n, 128, 0, st>>>(xs, xt, n);
+        transpose_in_kernel<<<n, 128, 0, st>>>(xs, xt, tc ? xt_hi : nullptr, tc ? xt_lo : nullptr, n);
         ctx->launches++;
         GConvArgs a{};
         a.idx = ctx->d_idx_full; a.B = n; a.Jin = YG; a.Jout = YG;
         // layer 1: raw y1 (shortcut) + a1 = relu(BN_a(y1))
-        a.act = xt; a.resid = nullptr; a.out_raw = y1;
+        a.resid = nullptr; a.out_raw = y1;
         a.scale = ctx->p1_bn_a.scale; a.shift = ctx->p1_bn_a.shift;
-        if (tc) { a.out_act = nullptr; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.out_act = a1; }
+        if (tc) { a.act_hi = xt_hi; a.act_lo = xt_lo; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.act = xt; a.out_act = a1; }
         if (int rc = gconv_forward(ctx, ctx->p1_in, a, st)) return rc;
         // layer 2: a2 = relu(BN_b(GC_a(a1)))
         a.out_raw = nullptr;
         a.scale = ctx->p1_bn_b.scale; a.shift = ctx->p1_bn_b.shift;
-        if (tc) { a.act = nullptr; a.act_hi = a1_hi; a.act_lo = a1_lo; a.out_act = nullptr; a.out_hi = a2_hi; a.out_lo = a2_lo; }
-        else { a.act = a1; a.out_act = a2; }
+        if (tc) { a.act_hi = a1_hi; a.act_lo = a1_lo; a.out_hi = a2_hi; a.out_lo = a2_lo; } else { a.act = a1; a.out_act = a2; }
         if (int rc = gconv_forward(ctx, ctx->p1_a, a, st)) return rc;
         // layer 3: a3 = relu(BN_o(GC_b(a2) + y1))
-        a.resid = y1; a.Jres = YG; a.resid_off = 0; a.resid_per_j = 1; a.out_act = a3; a.out_hi = a.out_lo = nullptr;
+        a.resid = y1; a.Jres = YG; a.resid_off = 0; a.resid_per_j = 1;
         a.scale = ctx->p1_bn_out.scale; a.shift = ctx->p1_bn_out.shift;
-        if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; } else { a.act = a2; }
+        if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; a.out_hi = a3_hi; a.out_lo = a3_lo; } else { a.act = a2; a.out_act = a3; }
         if (int rc = gconv_forward(ctx, ctx->p1_b, a, st)) return rc;
         // layer 4: y4 = GC_out(a3)
-        a.act = a3; a.act_hi = a.act_lo = nullptr; a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.scale = a.shift = nullptr;
+        a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.out_hi = a.out_lo = nullptr; a.scale = a.shift = nullptr;
+        if (tc) { a.act_hi = a3_hi; a.act_lo = a3_lo; } else { a.act = a3; }
         if (int rc = gconv_forward(ctx, ctx->p1_out, a, st)) return rc;
         part1_finalize_kernel<<<n, 64, 0, st>>>(y4, xs, eqv + (size_t)s * YF * YG, inv ? inv + (size_t)s * YF : nullptr,
                                                 desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);

@@ -5,6 +5,7 @@
 // code and the head output is sliced at [:,:,0,0]), so the layers are evaluated on the receptive field of
 // g=0 only: Conv_init at the 45 two-hop elements, comb_layer_in at the 13 one-hop elements, comb_layer_out and
 // the 1x1 head at g=0.  This is exact (same sums, same order) and 5.6x cheaper.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -16,7 +17,8 @@ __global__ void __launch_bounds__(256) part2_assemble_kernel(const float* __rest
                                                             const float* __restrict__ yoho0, const float* __restrict__ yoho1,
                                                             const int64_t* __restrict__ pairs, const int64_t* __restrict__ pre_idx,
                                                             const uint8_t* __restrict__ perm, const float* __restrict__ scale,
-                                                            const float* __restrict__ shift, float* __restrict__ z0a, int M) {
+                                                            const float* __restrict__ shift, float* __restrict__ z0a,
+                                                            unsigned short* __restrict__ z_hi, unsigned short* __restrict__ z_lo, int M) {
     __shared__ float s[4][YF][YG + 1];
     __shared__ uint8_t pr[64];
     const int m = blockIdx.x, t = threadIdx.x;
@@ -30,12 +32,19 @@ __global__ void __launch_bounds__(256) part2_assemble_kernel(const float* __rest
     for (int q = 0; q < 4; ++q)
         for (int i = t; i < YF * YG; i += 256) s[q][i / YG][i % YG] = src[q][i];
     __syncthreads();
-    float* dst = z0a + (size_t)m * YG * 128;
+    const size_t o = (size_t)m * YG * 128;
     for (int i = t; i < YG * 128; i += 256) {
         const int g = i >> 7, c = i & 127;
         const int q = c >> 5, cc = c & 31;
         const int gs = (q == 0 || q == 2) ? pr[g] : g;
-        dst[i] = fmaxf(fmaf(s[q][cc][gs], scale[c], shift[c]), 0.f);
+        const float v = fmaxf(fmaf(s[q][cc][gs], scale[c], shift[c]), 0.f);
+        if (z_hi) {   // tensor-core path: bf16 hi/lo split
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            z_hi[o + i] = __bfloat16_as_ushort(h);
+            z_lo[o + i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+        } else {
+            z0a[o + i] = v;
+        }
     }
 }
 
@@ -141,24 +150,37 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
         const int64_t* pr = pairs ? pairs + 2 * (size_t)s : nullptr;
         // without a match list the inputs are already per-match rows: advance them with the chunk
         const size_t adv = pairs ? 0 : (size_t)s * YF * YG;
+        // tensor-core path (>= 128 rows in the smallest layer): the activation regions hold bf16 hi|lo halves
+        const bool tc = ctx->gconv_impl == 1 && ctx->p2_init.w_hi && ctx->p2_a.w_hi && ctx->p2_b.w_hi && n >= 128;
+        unsigned short* z0_hi = (unsigned short*)z0a;
+        unsigned short* z0_lo = z0_hi + (size_t)n * YG * 128;
+        unsigned short* a1_hi = (unsigned short*)a1;
+        unsigned short* a1_lo = a1_hi + (size_t)n * 45 * 256;
+        unsigned short* a2_hi = (unsigned short*)a2;
+        unsigned short* a2_lo = a2_hi + (size_t)n * 13 * 512;
         part2_assemble_kernel<<<n, 256, 0, st>>>(fcgf0 + adv, fcgf1 + adv, yoho0 + adv, yoho1 + adv, pr, pre_idx + s,
-                                                 ctx->d_perm, ctx->p2_bn_init.scale, ctx->p2_bn_init.shift, z0a, n);
+                                                 ctx->d_perm, ctx->p2_bn_init.scale, ctx->p2_bn_init.shift, z0a,
+                                                 tc ? z0_hi : nullptr, tc ? z0_lo : nullptr, n);
         ctx->launches++;
         GConvArgs a{};
         a.B = n;
         // Conv_init at the 45 two-hop elements: raw z1 (shortcut) + a1 = relu(BN_a(z1))
-        a.act = z0a; a.idx = ctx->d_idx_p2_init; a.Jin = YG; a.Jout = 45;
-        a.out_raw = z1; a.out_act = a1; a.scale = ctx->p2_bn_a.scale; a.shift = ctx->p2_bn_a.shift;
+        a.idx = ctx->d_idx_p2_init; a.Jin = YG; a.Jout = 45;
+        a.out_raw = z1; a.scale = ctx->p2_bn_a.scale; a.shift = ctx->p2_bn_a.shift;
+        if (tc) { a.act_hi = z0_hi; a.act_lo = z0_lo; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.act = z0a; a.out_act = a1; }
         if (int rc = gconv_forward(ctx, ctx->p2_init, a, st)) return rc;
         // comb_layer_in at the 13 one-hop elements
-        a.act = a1; a.idx = ctx->d_idx_p2_a; a.Jin = 45; a.Jout = 13;
-        a.out_raw = nullptr; a.out_act = a2; a.scale = ctx->p2_bn_b.scale; a.shift = ctx->p2_bn_b.shift;
+        a.idx = ctx->d_idx_p2_a; a.Jin = 45; a.Jout = 13;
+        a.out_raw = nullptr; a.scale = ctx->p2_bn_b.scale; a.shift = ctx->p2_bn_b.shift;
+        if (tc) { a.act_hi = a1_hi; a.act_lo = a1_lo; a.out_hi = a2_hi; a.out_lo = a2_lo; } else { a.act = a1; a.out_act = a2; }
         if (int rc = gconv_forward(ctx, ctx->p2_a, a, st)) return rc;
         // comb_layer_out at g=0 + shortcut z1[:, g=0]
-        a.act = a2; a.idx = ctx->d_idx_p2_b; a.Jin = 13; a.Jout = 1;
+        a.idx = ctx->d_idx_p2_b; a.Jin = 13; a.Jout = 1;
         a.resid = z1; a.Jres = 45; a.resid_off = ctx->hop2_zero_pos; a.resid_per_j = 0;
-        a.out_raw = z3; a.out_act = nullptr; a.scale = a.shift = nullptr;
+        a.out_raw = z3; a.out_act = nullptr; a.out_hi = a.out_lo = nullptr; a.scale = a.shift = nullptr;
+        if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; } else { a.act = a2; }
         if (int rc = gconv_forward(ctx, ctx->p2_b, a, st)) return rc;
+        a.act_hi = a.act_lo = nullptr;
         // head: 256 -> 512 -> 128 with BN+ReLU, as 1-tap layers
         a.resid = nullptr; a.idx = ctx->d_idx_one; a.Jin = 1; a.Jout = 1;
         a.act = z3; a.out_raw = nullptr; a.out_act = h1; a.scale = ctx->p2_bn1.scale; a.shift = ctx->p2_bn1.shift;
