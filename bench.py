@@ -261,7 +261,7 @@ def run_ours(args):
                 "launches": dln, "avg_launch_ms": dms / dln if dln else None,
                 "algorithmic_flops_per_launch": dfl / dln if dln else None,
                 "share_of_step": dms / ms if ms else None, "all_gconv_share_of_step": gconv_ms / ms if ms else None,
-                "impl": args.gconv or "simt", "traffic": traffic,
+                "impl": eng.impl_name, "traffic": traffic,
                 "note": "FP32 results at 1e-4 parity need >=3 bf16 products per MAC on tensor cores: frac <= 1/3 by construction"}
 
     line = None
@@ -273,7 +273,8 @@ def run_ours(args):
                    "seconds_per_cold_pair": sec}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32" if eng.impl_name == "simt" else "f32 via bf16x3 split products, f32 accumulate (tcgen05)",
+                "data": "synthetic",
                 "config": {"workload": f"configs[1]: one cold {K}-keypoint 3DMatch-shaped pair per rank per step: PartI x2, "
                                        "mutual 1-NN, rotation argmax, YOHO-C 1000 iters, PartII, YOHO-O",
                            "kpts": K, "pairs_per_step_per_gpu": 1, "matches_per_pair": int(np.mean(Ms)),
@@ -299,7 +300,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kpts", type=int, default=5000)
-    ap.add_argument("--gconv", default=None, choices=[None, "simt", "tcgen05"])
+    ap.add_argument("--gconv", default=None, choices=[None, "simt", "tcgen05", "tcgen05_split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -96,7 +96,8 @@ int yoho_ctx_destroy(yoho_ctx* ctx);
 int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w);
 int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w);
 
-/* Implementation of the four group-convolution layers: 0 = FP32 SIMT (default), 1 = tcgen05 split-BF16. */
+/* Implementation of the group-convolution layers: 0 = FP32 SIMT (default), 1 = tcgen05 split-BF16,
+ * 2 = tcgen05 split-BF16 with the small (lo) products in a separate TMEM accumulator (shorter rounding chain). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
 /* A1-A6 — PartI_test.forward (utils/network.py:86-105,140-147) on B keypoints.

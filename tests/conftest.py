@@ -49,9 +49,21 @@ def tables():
 
 
 @pytest.fixture(scope="session")
-def engine():
+def _engine_session():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from yoho_b200.engine import get_engine
     return get_engine()
+
+
+GCONV_IMPLS = ["simt", "tcgen05", "tcgen05_split"]
+
+
+@pytest.fixture(params=GCONV_IMPLS)
+def engine(request, _engine_session):
+    """Every GPU test runs once per group-convolution implementation (FP32 SIMT, tcgen05, tcgen05 split-accumulator)."""
+    _engine_session.set_gconv_impl(request.param)
+    _engine_session.impl_name = request.param
+    yield _engine_session
+    _engine_session.set_gconv_impl("tcgen05")

@@ -20,13 +20,6 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-@pytest.fixture(scope="module")
-def eng_synth0(engine):
-    engine.load_part1(synth.synth_state_dict("PartI", 0))
-    engine.load_part2(synth.synth_state_dict("PartII", 0))
-    return engine
-
-
 # ------------------------------------------------------------------------------------------------ PartI
 def test_part1_golden_stage(engine):
     g = load_golden("stages_synth.npz")
@@ -35,8 +28,8 @@ def test_part1_golden_stage(engine):
     o = engine.part1(x)
     assert np.abs(_np(o["eqv"]) - g["p1_eqv"]).max() <= DESC_TOL
     assert np.abs(_np(o["inv"]) - g["p1_inv"]).max() <= DESC_TOL
-    # FP32 SIMT path is far inside the bar; keep it honest
-    assert np.abs(_np(o["eqv"]) - g["p1_eqv"]).max() <= 2e-5
+    if engine.impl_name == "simt":      # the FP32 SIMT path is far inside the bar; keep it honest
+        assert np.abs(_np(o["eqv"]) - g["p1_eqv"]).max() <= 2e-5
 
 
 @pytest.mark.parametrize("K", [1, 2, 59, 130, 700])

@@ -106,6 +106,9 @@ extern "C" int yoho_ctx_create(int device, const double* rotation_host, const in
     rc |= upload(&c->d_idx_p2_a, idx_a);
     rc |= upload(&c->d_idx_p2_b, idx_b);
     rc |= upload(&c->d_idx_one, idx_one);
+    std::vector<int> idx_ident(YG);
+    for (int g = 0; g < YG; ++g) idx_ident[g] = g;
+    rc |= upload(&c->d_idx_ident, idx_ident);
     if (rc) { delete c; return YOHO_ERR_CUDA; }
     if ((rc = yoho_ws_reserve(c, (size_t)64 << 20))) { delete c; return rc; }
     *out = c;
@@ -125,12 +128,12 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     if (!c) return YOHO_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3};
+    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p1_out_cat, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3};
     for (GLayer* l : layers) free_layer(*l);
     GBn* bns[] = {&c->p1_bn_a, &c->p1_bn_b, &c->p1_bn_out, &c->p2_bn_init, &c->p2_bn_a, &c->p2_bn_b, &c->p2_bn1, &c->p2_bn2};
     for (GBn* b : bns) free_bn(*b);
     cudaFree(c->d_rot); cudaFree(c->d_rot32); cudaFree(c->d_perm); cudaFree(c->d_perm_t);
-    cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one);
+    cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one); cudaFree(c->d_idx_ident);
     cudaFree(c->ws);
     delete c;
     return YOHO_OK;
@@ -181,6 +184,17 @@ extern "C" int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w) {
     if ((rc = pack_conv(ctx, ctx->p1_b, w->conv_b, 512, 256, YT))) return rc;
     if ((rc = pack_bn(ctx->p1_bn_out, w->bn_out, 256))) return rc;
     if ((rc = pack_conv(ctx, ctx->p1_out, w->conv_out, 256, 32, YT))) return rc;
+    {   // layer 4 with the gather on the OUTPUT side: Z = a3 . W_cat (dense), y4[g] = sum_k Z[N[g][k]][k*32 : k*32+32]
+        GLayer& L = ctx->p1_out_cat;
+        free_layer(L);
+        L.cin = 256; L.cout = 512; L.taps = 1; L.tc_dense = 1; L.prof_class = 3;
+        std::vector<float> wc((size_t)256 * 512, 0.f), zb(512, 0.f);
+        for (int k = 0; k < YT; ++k)
+            for (int c = 0; c < 256; ++c)
+                for (int o = 0; o < 32; ++o) wc[(size_t)c * 512 + k * 32 + o] = w->conv_out.weight_host[((size_t)o * 256 + c) * YT + k];
+        if ((rc = upload(&L.bias, zb))) return rc;
+        if ((rc = gconv_tc_pack(ctx, L, wc))) return rc;
+    }
     ctx->p1_in.prof_class = 0; ctx->p1_a.prof_class = 1; ctx->p1_b.prof_class = 2; ctx->p1_out.prof_class = 3;
     ctx->has_p1 = true;
     return YOHO_OK;
@@ -209,7 +223,7 @@ extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
 }
 
 extern "C" int yoho_set_gconv_impl(yoho_ctx* ctx, int impl) {
-    YARG(ctx && (impl == 0 || impl == 1));
+    YARG(ctx && impl >= 0 && impl <= 2);
     ctx->gconv_impl = impl;
     return YOHO_OK;
 }
@@ -232,11 +246,11 @@ int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream
     const bool prof = ctx->prof_on && a.B > 0;
     if (prof) {
         rec.a = prof_event(ctx); rec.b = prof_event(ctx); rec.cls = L.prof_class;
-        rec.flops = 2.0 * (double)a.B * a.Jout * L.taps * L.cin * L.cout;
+        rec.flops = 2.0 * (double)a.B * a.Jout * L.taps * L.cin * (a.n_valid > 0 ? a.n_valid : L.cout);   // algorithmic
         cudaEventRecord(rec.a, st);
     }
     int rc;
-    if (ctx->gconv_impl == 1 && gconv_tc_eligible(L, a)) rc = gconv_tc_forward(ctx, L, a, st);
+    if (ctx->gconv_impl >= 1 && gconv_tc_eligible(L, a)) rc = gconv_tc_forward(ctx, L, a, st);
     else if (!a.act) { yoho_set_error("group convolution: FP32 activations missing for the SIMT path"); rc = YOHO_ERR_ARG; }
     else rc = gconv_simt_forward(ctx, L, a, st);
     if (prof) { cudaEventRecord(rec.b, st); ctx->prof.push_back(rec); }
@@ -268,7 +282,7 @@ extern "C" int yoho_profile_read(yoho_ctx* ctx, double* ms_host, int64_t* launch
 int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
 extern "C" int yoho_debug_layer(yoho_ctx* ctx, int layer, int impl, const float* act, int B, float* out_raw, void* stream) {
-    YARG(ctx && act && out_raw && B > 0 && layer >= 0 && layer <= 6 && (impl == 0 || impl == 1));
+    YARG(ctx && act && out_raw && B > 0 && layer >= 0 && layer <= 6 && impl >= 0 && impl <= 2);
     YARG(layer < 4 ? ctx->has_p1 : ctx->has_p2);
     YCHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -278,7 +292,7 @@ extern "C" int yoho_debug_layer(yoho_ctx* ctx, int layer, int impl, const float*
     a.idx = ctx->d_idx_full; a.B = B; a.Jin = YG; a.Jout = YG; a.act = act; a.out_raw = out_raw;
     const int saved = ctx->gconv_impl;
     int rc;
-    if (impl == 1) {
+    if (impl >= 1) {
         const size_t n = (size_t)B * YG * L.cin;
         if ((rc = yoho_ws_reserve(ctx, n * 4))) return rc;
         void* hi = ctx->ws;
@@ -286,7 +300,7 @@ extern "C" int yoho_debug_layer(yoho_ctx* ctx, int layer, int impl, const float*
         if ((rc = gconv_split_bf16(ctx, act, hi, lo, n, st))) return rc;
         a.act_hi = hi; a.act_lo = lo;
         YARG(gconv_tc_eligible(L, a));
-        ctx->gconv_impl = 1;
+        ctx->gconv_impl = impl;
     } else {
         ctx->gconv_impl = 0;
     }

@@ -39,6 +39,7 @@ struct GLayer {
     // tcgen05 path: bf16 hi/lo split of the weights, [taps][cout][cin] (K-major B operand)
     void* w_hi = nullptr;
     void* w_lo = nullptr;
+    int tc_dense = 0;         // 1: tensor-core layer with taps == 1 (dense GEMM, e.g. PartI layer 4 "all taps at once")
 };
 
 // Folded eval-mode BatchNorm: y = x*scale + shift.
@@ -67,6 +68,8 @@ struct yoho_ctx {
     // PartI
     bool has_p1 = false;
     GLayer p1_in, p1_a, p1_b, p1_out;
+    GLayer p1_out_cat;              // PartI layer 4 as one dense GEMM: W_cat[c][k*32+o] = W_k[c][o], 416 -> 512 columns
+    int* d_idx_ident = nullptr;     // [60][1] identity
     GBn p1_bn_a, p1_bn_b, p1_bn_out;
     // PartII
     bool has_p2 = false;
@@ -100,6 +103,7 @@ struct GConvArgs {
     const void* act_lo;
     void* out_hi;            // nullable [B][Jout][Cout] bf16: hi/lo of relu(out_raw*scale + shift)
     void* out_lo;
+    int n_valid;             // tensor-core path: only columns < n_valid are written (0 = all)
 };
 int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
 

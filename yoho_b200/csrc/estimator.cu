@@ -292,21 +292,30 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
     }
 }
 
-// Random evaluation order: rank of a Philox key (ties by index).  O(M^2) compares, M is a few thousand.
-__global__ void o_order_kernel(int M, unsigned long long seed, int32_t* __restrict__ order) {
+// Random evaluation order: rank of a Philox key (ties by index).  Keys are generated once, then ranked with
+// O(M^2) compares on cached keys (M is a few thousand).
+__global__ void o_keys_kernel(int M, unsigned long long seed, unsigned long long* __restrict__ keys) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
-    auto key = [&](int j) {
-        const uint4 r = philox4x32(make_uint4((unsigned)j, 2u, 0x59484f4fu, 0u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-        return ((unsigned long long)r.x << 32) | r.y;
-    };
-    const unsigned long long ki = key(i);
+    const uint4 r = philox4x32(make_uint4((unsigned)i, 2u, 0x59484f4fu, 0u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    keys[i] = ((unsigned long long)r.x << 32) | r.y;
+}
+__global__ void __launch_bounds__(256) o_rank_kernel(int M, const unsigned long long* __restrict__ keys, int32_t* __restrict__ order) {
+    __shared__ unsigned long long ks[1024];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long ki = i < M ? keys[i] : 0ull;
     int rank = 0;
-    for (int j = 0; j < M; ++j) {
-        const unsigned long long kj = key(j);
-        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    for (int base = 0; base < M; base += 1024) {
+        for (int j = threadIdx.x; j < 1024; j += 256) ks[j] = base + j < M ? keys[base + j] : ~0ull;
+        __syncthreads();
+        const int lim = M - base < 1024 ? M - base : 1024;
+        for (int j = 0; j < lim; ++j) {
+            const unsigned long long kj = ks[j];
+            rank += (kj < ki || (kj == ki && base + j < i)) ? 1 : 0;
+        }
+        __syncthreads();
     }
-    order[rank] = i;
+    if (i < M) order[rank] = i;
 }
 
 }  // namespace
@@ -354,8 +363,11 @@ extern "C" int yoho_o_order(yoho_ctx* ctx, int M, uint64_t seed, int32_t* order,
     YARG(ctx && order && M >= 0);
     if (M == 0) return YOHO_OK;
     YCHECK(cudaSetDevice(ctx->device));
-    o_order_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, seed, order);
-    ctx->launches++;
+    if (int rc = yoho_ws_reserve(ctx, (size_t)M * 8)) return rc;
+    unsigned long long* keys = (unsigned long long*)ctx->ws;
+    o_keys_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, seed, keys);
+    o_rank_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, keys, order);
+    ctx->launches += 2;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
 }

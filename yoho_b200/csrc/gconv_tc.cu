@@ -32,12 +32,18 @@ constexpr int MAX_STAGES = 4;
 
 // Tile width BN = 256 for the wide layers (2 stages of 96 KB, two 256-column accumulators = all of TMEM) and
 // BN = 32 for the 256 -> 32 output layer (4 stages of 40 KB; that layer is bound by streaming A from L2).
-template <int BN>
+// SPLIT: the hi*hi products accumulate in one TMEM accumulator and the two small cross products (a_lo*w_hi, a_hi*w_lo)
+// in a second one, summed in FP32 (round-to-nearest) by the epilogue.  The tensor core truncates when it adds into
+// the accumulator, so the error grows with the number of accumulation steps at full magnitude: SPLIT cuts that chain
+// from 3*K/16 to K/16 steps.  With BN = 256 it uses all 512 TMEM columns for one tile (no epilogue overlap).
+template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr int STAGES = BN == 256 ? 2 : 4;
     static constexpr int W_TILE = BN * BK * 2;                        // bytes (hi or lo)
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;       // two accumulators, power of two >= 32
+    static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * BN;             // TMEM columns of one tile's accumulator(s)
+    static constexpr int NACC = (512 / ACC_COLS) >= 2 ? 2 : 1;        // accumulator buffers in flight
+    static constexpr int TMEM_COLS = NACC * ACC_COLS < 32 ? 32 : NACC * ACC_COLS;   // power of two >= 32
     // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=128 (cute::UMMA::InstrDescriptor)
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     static constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + 3 * 512 * sizeof(float) +
@@ -61,6 +67,7 @@ struct TcArgs {
     __nv_bfloat16* out_lo;
     const float* scale;
     const float* shift;
+    int n_valid;                 // columns >= n_valid are not written
 };
 
 struct __align__(8) Barriers {
@@ -130,13 +137,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-template <int BN>
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
-    constexpr int STAGES = Cfg<BN>::STAGES;
-    constexpr int W_TILE = Cfg<BN>::W_TILE;
-    constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
-    constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
-    constexpr uint32_t IDESC = Cfg<BN>::IDESC;
+    using C = Cfg<BN, SPLIT>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int W_TILE = C::W_TILE;
+    constexpr int STAGE_BYTES = C::STAGE_BYTES;
+    constexpr int TMEM_COLS = C::TMEM_COLS;
+    constexpr int ACC_COLS = C::ACC_COLS;
+    constexpr int NACC = C::NACC;
+    constexpr uint32_t IDESC = C::IDESC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -223,10 +233,9 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                     cp_async16(dst_hi + ((c ^ swz) << 4), src_hi[h] + ((c & 3) << 4), okh[h]);
                     cp_async16(dst_lo + ((c ^ swz) << 4), src_lo[h] + ((c & 3) << 4), okh[h]);
                 }
-                cp_async_commit();
-                cp_async_wait<0>();
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(&bars->full[stage]);
+                // arrive on the stage barrier when this thread's copies have landed; the thread itself moves on
+                // (the pattern of CUTLASS's sm100 cp.async mainloop), so every free stage is refilled immediately
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bars->full[stage])) : "memory");
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -255,9 +264,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                const uint32_t d_lo = SPLIT ? d_tmem + BN : d_tmem;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async (generic proxy) data -> UMMA (async proxy)
                     tc_fence_after();
                     const uint8_t* st = stage_base + stage * STAGE_BYTES;
                     const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
@@ -265,15 +276,16 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
 #pragma unroll
                     for (uint32_t ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per 16 bf16, in 16-byte units
-                        tc_mma(d_tmem, a_hi + adv, w_hi + adv, IDESC, (kb | (int)ks) ? 1u : 0u);
-                        tc_mma(d_tmem, a_lo + adv, w_hi + adv, IDESC, 1u);
-                        tc_mma(d_tmem, a_hi + adv, w_lo + adv, IDESC, 1u);
+                        const uint32_t first = (kb | (int)ks) ? 1u : 0u;
+                        tc_mma(d_tmem, a_hi + adv, w_hi + adv, IDESC, first);
+                        tc_mma(d_lo, a_lo + adv, w_hi + adv, IDESC, SPLIT ? first : 1u);
+                        tc_mma(d_lo, a_hi + adv, w_lo + adv, IDESC, 1u);
                     }
                     tc_commit(&bars->empty[stage]);            // stage reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&bars->tmem_full[acc]);              // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -294,16 +306,23 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             }
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
             const size_t orow = (size_t)(ok ? row : 0) * p.Cout + n0;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 32; ++cc) {
                 uint32_t v[32];
                 tmem_ld32(t_addr + cc * 32, v);     // .sync.aligned: executed by the whole warp, rows past the end included
-                if (ok) {
                 float f[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + ep_bias[n0 + cc * 32 + i];
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if constexpr (SPLIT) {
+                    tmem_ld32(t_addr + BN + cc * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
+                }
+                if (ok && n0 + cc * 32 < p.n_valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] += ep_bias[n0 + cc * 32 + i];
                 if (rres) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             }
             tc_fence_before();
             mbar_arrive(&bars->tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -395,7 +414,7 @@ inline float bf2f(unsigned short h) {
 // UMMA K-major SWIZZLE_128B image (row r at r*128 bytes, 16-byte chunk j stored at position j ^ (r & 7)).
 // K axis = tap-major, channel-minor, zero-padded to a multiple of 64 (only Cin = 32 needs padding: 416 -> 448).
 static int tc_tile_n(const GLayer& L) {
-    if (L.taps != YT) return 0;
+    if (L.taps != YT && !L.tc_dense) return 0;
     if (!(L.cin == 32 || L.cin % BK == 0)) return 0;
     if (L.cout % 256 == 0) return 256;
     if (L.cout == 32) return 32;
@@ -445,17 +464,17 @@ int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n
     return YOHO_OK;
 }
 
-template <int BN>
+template <int BN, bool SPLIT>
 static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES));
+        YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, SPLIT>::SMEM_BYTES));
         attr_done = true;
     }
     p.n_tiles = p.Cout / BN;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    gconv_tc_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(p);
+    gconv_tc_kernel<BN, SPLIT><<<grid, THREADS, Cfg<BN, SPLIT>::SMEM_BYTES, st>>>(p);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
@@ -474,5 +493,8 @@ int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStr
     p.out_raw = a.out_raw; p.out_act = a.out_act;
     p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
     p.scale = a.scale; p.shift = a.shift;
-    return tc_tile_n(L) == 256 ? tc_launch<256>(ctx, p, st) : tc_launch<32>(ctx, p, st);
+    p.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
+    const bool split = ctx->gconv_impl == 2;
+    if (tc_tile_n(L) == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
+    return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);
 }

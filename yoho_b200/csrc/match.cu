@@ -211,12 +211,19 @@ __global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict
     const int a = t & 63, q = t >> 6;   // rotation a, channel quarter q
     float acc = 0.f;
     if (a < YG) {
-        for (int f = q * 8; f < q * 8 + 8; ++f) {
-            const float* p1 = s1 + f * YG;
-            const float* p2 = s2 + f * YG;
-#pragma unroll 4
-            for (int g = 0; g < YG; ++g) acc = fmaf(p1[pt[g * 64 + a]], p2[g], acc);
+        // per channel the sum runs over g ascending, channels ascending: the permutation index is loaded once per g
+        float accf[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) accf[f] = 0.f;
+        const float* p1 = s1 + q * 8 * YG;
+        const float* p2 = s2 + q * 8 * YG;
+        for (int g = 0; g < YG; ++g) {
+            const int src = pt[g * 64 + a];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) accf[f] = fmaf(p1[f * YG + src], p2[f * YG + g], accf[f]);
         }
+#pragma unroll
+        for (int f = 0; f < 8; ++f) acc += accf[f];
     }
     part[q][a] = acc;
     __syncthreads();

@@ -49,8 +49,12 @@ __device__ __forceinline__ float numpy_mean60(const float* a, int stride) {
     return __fdiv_rn(res, 60.0f);
 }
 
-// One CTA (64 threads) per keypoint.  y4 [B][60][32] (bias included), x [B][32][60].
-__global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restrict__ y4, const float* __restrict__ x,
+// One CTA (64 threads) per keypoint.  x [B][32][60].  Layer-4 result either as y4 [B][60][32] (bias included) or, on
+// the tensor-core path, as Z [B][60][512] = a3 . W_cat with the 13-tap gather still to do:
+//     y4[g][c] = bias[c] + sum_k Z[N[g][k]][k*32 + c]      (taps in ascending order)
+__global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restrict__ y4, const float* __restrict__ z,
+                                                           const int* __restrict__ nei, const float* __restrict__ bias4,
+                                                           const float* __restrict__ x,
                                                            float* __restrict__ eqv, float* __restrict__ inv,
                                                            float* __restrict__ desc, int B) {
     __shared__ float e[YF][YG + 1];
@@ -59,11 +63,22 @@ __global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restr
     const int b = blockIdx.x;
     const int t = threadIdx.x;
     const float* xs = x + (size_t)b * YF * YG;
-    const float* ys = y4 + (size_t)b * YG * YF;
-    // e[c][g] = y4[g][c] + x[c][g]
-    for (int i = t; i < YF * YG; i += 64) {
-        const int g = i / YF, c = i % YF;
-        e[c][g] = ys[i];
+    if (z) {
+        const float* zs = z + (size_t)b * YG * 512;
+        for (int i = t; i < YF * YG; i += 64) {
+            const int g = i / YF, c = i % YF;
+            float acc = bias4[c];
+#pragma unroll
+            for (int k = 0; k < YT; ++k) acc += zs[(size_t)nei[g * YT + k] * 512 + k * 32 + c];
+            e[c][g] = acc;
+        }
+    } else {
+        const float* ys = y4 + (size_t)b * YG * YF;
+        // e[c][g] = y4[g][c] + x[c][g]
+        for (int i = t; i < YF * YG; i += 64) {
+            const int g = i / YF, c = i % YF;
+            e[c][g] = ys[i];
+        }
     }
     __syncthreads();
     for (int i = t; i < YF * YG; i += 64) {
@@ -124,9 +139,9 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
     }
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
-    const bool tc_on = ctx->gconv_impl == 1 && ctx->p1_in.w_hi && ctx->p1_a.w_hi && ctx->p1_b.w_hi && ctx->p1_out.w_hi;
+    const bool tc_on = ctx->gconv_impl >= 1 && ctx->p1_in.w_hi && ctx->p1_a.w_hi && ctx->p1_b.w_hi && ctx->p1_out.w_hi;
     // per keypoint: xt 32, y1 256, a1 256 (fp32, or bf16 hi+lo = same bytes), a2 512 (same), a3 256, y4 32 floats x 60
-    const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 32) * sizeof(float);
+    const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 512) * sizeof(float);
     const int chunk = B < P1_CHUNK ? B : P1_CHUNK;
     if (int rc = yoho_ws_reserve(ctx, per_kp * (size_t)chunk)) return rc;
     for (int s = 0; s < B; s += chunk) {
@@ -167,11 +182,19 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         a.scale = ctx->p1_bn_out.scale; a.shift = ctx->p1_bn_out.shift;
         if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; a.out_hi = a3_hi; a.out_lo = a3_lo; } else { a.act = a2; a.out_act = a3; }
         if (int rc = gconv_forward(ctx, ctx->p1_b, a, st)) return rc;
-        // layer 4: y4 = GC_out(a3)
+        // layer 4: y4 = GC_out(a3).  Tensor-core path: one dense GEMM Z = a3 . W_cat [256 x 13*32] (a3 is read once, not
+        // 13 times); the 13-tap gather-add happens on the 100 KB Z tile of each keypoint inside the finalize kernel.
         a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.out_hi = a.out_lo = nullptr; a.scale = a.shift = nullptr;
-        if (tc) { a.act_hi = a3_hi; a.act_lo = a3_lo; } else { a.act = a3; }
-        if (int rc = gconv_forward(ctx, ctx->p1_out, a, st)) return rc;
-        part1_finalize_kernel<<<n, 64, 0, st>>>(y4, xs, eqv + (size_t)s * YF * YG, inv ? inv + (size_t)s * YF : nullptr,
+        const bool dense4 = tc && ctx->p1_out_cat.w_hi;
+        if (dense4) {
+            a.act_hi = a3_hi; a.act_lo = a3_lo; a.idx = ctx->d_idx_ident; a.n_valid = YT * 32;
+            if (int rc = gconv_forward(ctx, ctx->p1_out_cat, a, st)) return rc;
+        } else {
+            if (tc) { a.act_hi = a3_hi; a.act_lo = a3_lo; } else { a.act = a3; }
+            if (int rc = gconv_forward(ctx, ctx->p1_out, a, st)) return rc;
+        }
+        part1_finalize_kernel<<<n, 64, 0, st>>>(dense4 ? nullptr : y4, dense4 ? y4 : nullptr, ctx->d_idx_full, ctx->p1_out.bias, xs,
+                                                eqv + (size_t)s * YF * YG, inv ? inv + (size_t)s * YF : nullptr,
                                                 desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
         ctx->launches++;
     }

@@ -151,7 +151,7 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
         // without a match list the inputs are already per-match rows: advance them with the chunk
         const size_t adv = pairs ? 0 : (size_t)s * YF * YG;
         // tensor-core path (>= 128 rows in the smallest layer): the activation regions hold bf16 hi|lo halves
-        const bool tc = ctx->gconv_impl == 1 && ctx->p2_init.w_hi && ctx->p2_a.w_hi && ctx->p2_b.w_hi && n >= 128;
+        const bool tc = ctx->gconv_impl >= 1 && ctx->p2_init.w_hi && ctx->p2_a.w_hi && ctx->p2_b.w_hi && n >= 128;
         unsigned short* z0_hi = (unsigned short*)z0a;
         unsigned short* z0_lo = z0_hi + (size_t)n * YG * 128;
         unsigned short* a1_hi = (unsigned short*)a1;

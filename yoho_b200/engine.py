@@ -4,6 +4,7 @@ libyoho_b200.so).  All methods enqueue on the current torch stream and do not sy
 return host values.
 """
 import ctypes
+import os
 import threading
 import numpy as np
 import torch
@@ -36,6 +37,9 @@ class Engine:
         self.h = h
         self.has_part1 = False
         self.has_part2 = False
+        self.impl_name = None
+        # group-convolution implementation: tensor cores by default; YOHO_B200_GCONV=simt selects the FP32 SIMT kernel
+        self.set_gconv_impl(os.environ.get("YOHO_B200_GCONV", "tcgen05"))
 
     def close(self):
         if getattr(self, "h", None):
@@ -60,7 +64,8 @@ class Engine:
         self.has_part2 = True
 
     def set_gconv_impl(self, impl):
-        _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1}.get(impl, impl)))
+        self.impl_name = impl
+        _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2}.get(impl, impl)))
 
     def launch_count(self):
         return int(self.lib.yoho_launch_count(self.h))
@@ -70,7 +75,7 @@ class Engine:
         act = self._f32(act)
         B = act.shape[0]
         out = self._empty((B, 60, cout), torch.float32)
-        _lib.check(self.lib.yoho_debug_layer(self.h, layer, {"simt": 0, "tcgen05": 1}[impl], _ptr(act), B, _ptr(out), _stream()))
+        _lib.check(self.lib.yoho_debug_layer(self.h, layer, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2}[impl], _ptr(act), B, _ptr(out), _stream()))
         return out
 
     def profile(self, enable):
