@@ -100,6 +100,9 @@ int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w);
  * 2 = tcgen05 split-BF16 with the small (lo) products in a separate TMEM accumulator (shorter rounding chain). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
+/* Tuning knobs of the tensor-core kernel (experiments; defaults are the measured best).  key 0 = producer flags. */
+int yoho_set_tuning(yoho_ctx* ctx, int key, int value);
+
 /* A1-A6 — PartI_test.forward (utils/network.py:86-105,140-147) on B keypoints.
  * x [B,32,60] -> eqv [B,32,60] (unit norm over channels per (b,g)), inv [B,32] (may be NULL),
  * desc_mean [B,32] = mean_g eqv, the matcher's descriptor (tests/matcher.py:35-36; may be NULL). */

@@ -45,7 +45,7 @@ def test_layer_tc_vs_simt(engine, layer, cin, cout, B, impl):
         key = ["PartI_net.Conv_in.0", "PartI_net.SO3_Conv_layers.0.comb_layer_in.2", "PartI_net.SO3_Conv_layers.0.comb_layer_out.2",
                "PartI_net.Conv_out.comb_layer.2"][layer]
         _, _, N = O.load_tables()
-        x = torch.from_numpy(np.ascontiguousarray(act.transpose(0, 2, 1)))          # [B,C,60]
+        x = torch.from_numpy(np.ascontiguousarray(act.transpose(0, 2, 1))).double()     # [B,C,60]
         ref64 = O.gconv(x, t, key, N, torch.float64).numpy().transpose(0, 2, 1)
         _report(f"layer{layer} B={B} {impl} vs f64", got, ref64)
         _report(f"layer{layer} B={B} simt vs f64", ref, ref64)

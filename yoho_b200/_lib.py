@@ -44,6 +44,7 @@ SYMBOLS = {
     "yoho_part1_load": (_i, [_vp, ctypes.POINTER(yoho_part1_weights)]),
     "yoho_part2_load": (_i, [_vp, ctypes.POINTER(yoho_part2_weights)]),
     "yoho_set_gconv_impl": (_i, [_vp, _i]),
+    "yoho_set_tuning": (_i, [_vp, _i, _i]),
     "yoho_part1_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "yoho_group_mean": (_i, [_vp, _vp, _i, _vp, _vp]),
     "yoho_nn1": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

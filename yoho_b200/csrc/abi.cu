@@ -228,6 +228,12 @@ extern "C" int yoho_set_gconv_impl(yoho_ctx* ctx, int impl) {
     return YOHO_OK;
 }
 
+extern "C" int yoho_set_tuning(yoho_ctx* ctx, int key, int value) {
+    YARG(ctx && key == 0);
+    ctx->tc_flags = value;
+    return YOHO_OK;
+}
+
 extern "C" int64_t yoho_launch_count(const yoho_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int gconv_simt_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);

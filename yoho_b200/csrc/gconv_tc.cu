@@ -68,6 +68,7 @@ struct TcArgs {
     const float* scale;
     const float* shift;
     int n_valid;                 // columns >= n_valid are not written
+    int flags;                   // bit0: non-blocking producer completion, bit1: line-per-8-lanes producer mapping
 };
 
 struct __align__(8) Barriers {
@@ -192,50 +193,62 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
 
     if (warp < 4) {
         // ================= A producers =================
-        const int r = threadIdx.x;                 // tile row 0..127
-        const uint32_t swz = (uint32_t)(r & 7);
+        // Two lane mappings (p.flags bit 1):
+        //   line map : 8 consecutive lanes copy the 8 16-byte chunks of ONE 128-byte row segment, so a warp-wide cp.async
+        //              touches 4 cache lines; warp w owns tile rows [32w, 32w+32), lane (rsub = lane/8, c = lane%8) copies
+        //              chunk c of rows 32w + 4i + rsub, i = 0..7.
+        //   row map  : one tile row per thread, all 8 chunks (32 cache lines per warp-wide cp.async).
+        // Two completion protocols (p.flags bit 0):
+        //   noinc    : cp.async.mbarrier.arrive.noinc — the barrier arrival fires when this thread's copies land and the
+        //              thread moves on (CUTLASS sm100 cp.async mainloop); the MMA thread fences the proxy.
+        //   blocking : wait_group 0, fence.proxy.async, arrive.
+        const bool linemap = (p.flags & 2) != 0;
+        const bool noinc = (p.flags & 1) != 0;
+        const uint32_t c = (uint32_t)(lane & 7);
+        const int rsub = lane >> 3;
         uint32_t stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.n_tiles;
-            const int row = m_tile * BM + r;
-            const bool ok = row < p.m_total;
-            const int rr = ok ? row : 0;
-            const int b = rr / p.Jout;
-            const int j = rr - b * p.Jout;
-            const size_t rowbase = (size_t)b * p.Jin;
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                // K axis = tap-major, channel-minor.  Cin >= 64: one tap per K block.  Cin == 32: two taps per block
-                // (chunks 0-3 from tap 2kb, chunks 4-7 from tap 2kb+1; the 14th half-block is zero padding).
-                const uint8_t *src_hi[2], *src_lo[2];
-                bool okh[2];
-                if (p.Cin >= BK) {
-                    const int k = kb / cblocks;
-                    const int c0 = (kb - k * cblocks) * BK;
-                    const size_t off = ((rowbase + idx_s[j * p.taps + k]) * p.Cin + c0);
-                    src_hi[0] = (const uint8_t*)(p.a_hi + off); src_lo[0] = (const uint8_t*)(p.a_lo + off);
-                    src_hi[1] = src_hi[0] + 64; src_lo[1] = src_lo[0] + 64;
-                    okh[0] = okh[1] = ok;
-                } else {
+            int rowbase[8], rowj[8];
+            uint32_t okmask = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int k = 2 * kb + h;
-                        okh[h] = ok && k < p.taps;
-                        const size_t off = (rowbase + idx_s[j * p.taps + (k < p.taps ? k : 0)]) * p.Cin;
-                        src_hi[h] = (const uint8_t*)(p.a_hi + off); src_lo[h] = (const uint8_t*)(p.a_lo + off);
-                    }
-                }
-                uint8_t* dst_hi = stage_base + stage * STAGE_BYTES + r * 128;
-                uint8_t* dst_lo = dst_hi + A_TILE;
+            for (int i = 0; i < 8; ++i) {
+                const int r = linemap ? warp * 32 + 4 * i + rsub : (int)threadIdx.x;
+                const int row = m_tile * BM + r;
+                const bool ok = row < p.m_total;
+                const int rr = ok ? row : 0;
+                const int b = rr / p.Jout;
+                rowj[i] = (rr - b * p.Jout) * p.taps;
+                rowbase[i] = b * p.Jin;
+                okmask |= (ok ? 1u : 0u) << i;
+            }
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                uint8_t* st_hi = stage_base + stage * STAGE_BYTES;
                 mbar_wait(&bars->empty[stage], phase ^ 1);
 #pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) {
-                    const int h = c >> 2;
-                    cp_async16(dst_hi + ((c ^ swz) << 4), src_hi[h] + ((c & 3) << 4), okh[h]);
-                    cp_async16(dst_lo + ((c ^ swz) << 4), src_lo[h] + ((c & 3) << 4), okh[h]);
+                for (int i = 0; i < 8; ++i) {
+                    // K axis = tap-major, channel-minor, 8-channel chunks never straddle a tap (Cin % 8 == 0); with
+                    // Cin == 32 a 64-wide block spans two taps and the 14th half-block is zero padding.
+                    const uint32_t ch = linemap ? c : (uint32_t)i;
+                    const int kk0 = kb * BK + (int)ch * 8;
+                    const int k = kk0 / p.Cin;
+                    const int coff = kk0 - k * p.Cin;
+                    const bool tap_ok = k < p.taps;
+                    const int r = linemap ? warp * 32 + 4 * i + rsub : (int)threadIdx.x;
+                    const size_t off = ((size_t)(rowbase[i] + idx_s[rowj[i] + (tap_ok ? k : 0)])) * p.Cin + coff;
+                    uint8_t* dst = st_hi + r * 128 + ((ch ^ (uint32_t)(r & 7)) << 4);
+                    const bool ok = tap_ok && ((okmask >> i) & 1u);
+                    cp_async16(dst, p.a_hi + off, ok);
+                    cp_async16(dst + A_TILE, p.a_lo + off, ok);
                 }
-                // arrive on the stage barrier when this thread's copies have landed; the thread itself moves on
-                // (the pattern of CUTLASS's sm100 cp.async mainloop), so every free stage is refilled immediately
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bars->full[stage])) : "memory");
+                if (noinc) {
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bars->full[stage])) : "memory");
+                } else {
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+                    mbar_arrive(&bars->full[stage]);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                 const uint32_t d_lo = SPLIT ? d_tmem + BN : d_tmem;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async (generic proxy) data -> UMMA (async proxy)
+                    if (p.flags & 1) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
                     tc_fence_after();
                     const uint8_t* st = stage_base + stage * STAGE_BYTES;
                     const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
@@ -494,6 +507,7 @@ int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStr
     p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
     p.scale = a.scale; p.shift = a.shift;
     p.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
+    p.flags = ctx->tc_flags;
     const bool split = ctx->gconv_impl == 2;
     if (tc_tile_n(L) == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
     return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);

@@ -67,6 +67,9 @@ class Engine:
         self.impl_name = impl
         _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2}.get(impl, impl)))
 
+    def set_tuning(self, key, value):
+        _lib.check(self.lib.yoho_set_tuning(self.h, int(key), int(value)))
+
     def launch_count(self):
         return int(self.lib.yoho_launch_count(self.h))
 
