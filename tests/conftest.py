@@ -66,4 +66,4 @@ def engine(request, _engine_session):
     _engine_session.set_gconv_impl(request.param)
     _engine_session.impl_name = request.param
     yield _engine_session
-    _engine_session.set_gconv_impl("tcgen05")
+    _engine_session.set_gconv_impl("tcgen05_split")

@@ -232,10 +232,15 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
     __shared__ int off[YG + 1];
     __shared__ double cdf[YG];
     __shared__ int ok_s;
+    __shared__ uint8_t bins[16384];            // rotation bin of every match (M <= 16384 staged; larger M reads global)
     const int t = threadIdx.x;
     if (t < YG) cnt[t] = 0;
     __syncthreads();
-    for (int m = t; m < M; m += 1024) atomicAdd(&cnt[(int)dr_index[m]], 1);
+    for (int m = t; m < M; m += 1024) {
+        const int b = (int)dr_index[m];
+        if (m < 16384) bins[m] = (uint8_t)b;
+        atomicAdd(&cnt[b], 1);
+    }
     __syncthreads();
     if (t == 0) {
         double tot = 0.0, w[YG];
@@ -266,7 +271,10 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
     // stable bucket fill: thread b owns bin b and scans the matches in order (M is a few thousand at most)
     if (t < YG) {
         int o = off[t];
-        for (int m = 0; m < M; ++m)
+        const int ms = M < 16384 ? M : 16384;
+        for (int m = 0; m < ms; ++m)
+            if (bins[m] == t) members_ws[o++] = m;
+        for (int m = ms; m < M; ++m)
             if ((int)dr_index[m] == t) members_ws[o++] = m;
     }
     __syncthreads();

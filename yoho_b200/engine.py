@@ -38,8 +38,9 @@ class Engine:
         self.has_part1 = False
         self.has_part2 = False
         self.impl_name = None
-        # group-convolution implementation: tensor cores by default; YOHO_B200_GCONV=simt selects the FP32 SIMT kernel
-        self.set_gconv_impl(os.environ.get("YOHO_B200_GCONV", "tcgen05"))
+        # group-convolution implementation: tensor cores (split accumulators) by default;
+        # YOHO_B200_GCONV=simt|tcgen05|tcgen05_split selects another kernel
+        self.set_gconv_impl(os.environ.get("YOHO_B200_GCONV", "tcgen05_split"))
 
     def close(self):
         if getattr(self, "h", None):
