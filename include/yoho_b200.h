@@ -174,6 +174,14 @@ int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, int M, const
                  const int32_t* order, int H, double inlier_dist, double* T, int32_t* best_iter,
                  int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream);
 
+/* "Next" row — the tail of the group-feature lift, YOHO_testset.py:153-166: for every group rotation g,
+ * rotate the keypoints (Keys @ R_g^T, float64), 1-NN of each into that rotation's down-sampled cloud (float64 distances
+ * against float32 points, first minimal index), gather the 32-d backbone feature: out[k,:,g] = feats[offsets[g] + nn, :].
+ * kps float64 [K,3]; pts float32 [sum n_g,3] and feats float32 [sum n_g,32] concatenated over g; offsets DEVICE int32[61];
+ * out float32 [K,32,60]; nn_out int64 [60,K] (may be NULL). */
+int yoho_lift_group_features(yoho_ctx* ctx, const double* kps, int K, const float* pts, const float* feats,
+                             const int32_t* offsets, float* out, int64_t* nn_out, void* stream);
+
 /* Launch accounting for bench.py's "gpu_launches": kernels launched by this context since creation. */
 int64_t yoho_launch_count(const yoho_ctx* ctx);
 

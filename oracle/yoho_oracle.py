@@ -279,3 +279,25 @@ def draw_yohoc_hypotheses(members, prob, max_iter, rng=np.random):
         it += 1
         hyp.append(rng.choice(np.array(members[r]), 3))
     return np.array(hyp, dtype=np.int32).reshape(-1, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row: group-feature lift tail
+# ---------------------------------------------------------------------------------------------
+def lift_group_features(kps, pts_list, feats_list, Rgroup):
+    """YOHO_testset.py:153-166: per rotation g, Keys @ R_g^T (float64), KNN(1) of the float64 keypoints into the float32
+    down-sampled cloud (float64 distances by type promotion, utils/knn_search.py:17-24), gather the backbone feature,
+    stack to [K,32,60] in g order.  Returns (features f32, nn int64 [60,K])."""
+    out, nns = [], []
+    for g in range(G):
+        keys = np.asarray(kps, np.float64) @ Rgroup[g].T
+        src = torch.from_numpy(keys)                                # float64 [K,3]
+        tgt = torch.from_numpy(np.asarray(pts_list[g], np.float32)) # float32 [n,3]
+        ids = []
+        for i in range(0, src.shape[0], 500):
+            d2 = torch.sum((src[i:i + 500].unsqueeze(1) - tgt.unsqueeze(0)).pow(2), 2)
+            ids.append(torch.sqrt(d2 + 1e-7).min(dim=1)[1])
+        nn = torch.cat(ids).numpy()
+        nns.append(nn)
+        out.append(np.asarray(feats_list[g], np.float32)[nn][:, :, None])
+    return np.concatenate(out, axis=-1), np.stack(nns)

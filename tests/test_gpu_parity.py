@@ -364,3 +364,25 @@ def test_device_order_is_permutation(engine):
     for M in (1, 87, 2500):
         o = _np(engine.o_order(M, seed=3))
         assert np.array_equal(np.sort(o), np.arange(M))
+
+
+# ------------------------------------------------------------------------------------------------ next row: feature lift
+def test_lift_group_features_vs_oracle(_engine_session, tables):
+    """SURVEY.md §8f-1 (YOHO_testset.py:153-166): 60 rotated 3-D 1-NN searches + feature gather, exact."""
+    R, _, _ = tables
+    rs = np.random.RandomState(7)
+    K = 333
+    kps = rs.uniform(-1.5, 1.5, (K, 3))
+    base = rs.uniform(-1.6, 1.6, (2500, 3))
+    pts, feats = [], []
+    for g in range(60):
+        n = int(rs.randint(1200, 2500))
+        p = (base[rs.permutation(2500)[:n]] @ R[g].T).astype(np.float32)
+        if g == 3:
+            p[10] = p[5]                       # duplicate point: the first index must win
+        pts.append(p)
+        feats.append(rs.standard_normal((n, 32)).astype(np.float32))
+    out, nn = _engine_session.lift_group_features(kps, pts, feats, want_nn=True)
+    want, want_nn = O.lift_group_features(kps, pts, feats, R)
+    assert np.array_equal(_np(nn), want_nn)
+    assert out.shape == (K, 32, 60) and np.array_equal(_np(out), want)

@@ -25,6 +25,7 @@ SOURCES = {
     "part1.cu": [],
     "part2.cu": [],
     "match.cu": [],
+    "lift.cu": [],
     "estimator.cu": ["-fmad=false"],
 }
 

@@ -202,6 +202,24 @@ class Engine:
                                                _ptr(k0), _ptr(k1), _ptr(quat), _ptr(trans), _stream()))
         return quat, trans
 
+    # ---- next row: group-feature lift tail ----------------------------------------------------------------
+    def lift_group_features(self, kps, pts_list, feats_list, want_nn=False):
+        """kps [K,3] f64; pts_list[g] [n_g,3] f32 (the rotation-g down-sampled cloud), feats_list[g] [n_g,32] f32
+        -> group feature [K,32,60] f32 (YOHO_testset.py:153-166)."""
+        assert len(pts_list) == 60 and len(feats_list) == 60
+        k = self._f64(kps)
+        K = k.shape[0]
+        offs = np.zeros(61, np.int32)
+        offs[1:] = np.cumsum([int(p.shape[0]) for p in pts_list])
+        pts = torch.cat([self._f32(p).reshape(-1, 3) for p in pts_list])
+        feats = torch.cat([self._f32(f).reshape(-1, 32) for f in feats_list])
+        od = torch.from_numpy(offs).to(self.device)
+        out = torch.zeros((K, 32, 60), device=self.device, dtype=torch.float32)
+        nn = self._empty((60, K), torch.int64) if want_nn else None
+        _lib.check(self.lib.yoho_lift_group_features(self.h, _ptr(k), K, _ptr(pts), _ptr(feats), _ptr(od), _ptr(out), _ptr(nn),
+                                                     _stream()))
+        return (out, nn) if want_nn else out
+
     # ---- E: estimators -----------------------------------------------------------------------------
     def gather_kps(self, kps0, kps1, pairs):
         k0, k1, pr = self._f64(kps0), self._f64(kps1), self._i64(pairs)
