@@ -185,11 +185,12 @@ def run_ours(args):
     eng.load_part2(synth.synth_state_dict("PartII", 0))
     dev = eng.device
     K = args.kpts
-    sets_h, sets_d = [], []
+    sets_h, sets_d, sets_p = [], [], []
     for s in range(N_SETS):
         p = synth.make_fragment_pair(K, seed=1000 * rank + s, overlap=0.5, sigma=0.05)
         sets_h.append(p)
         sets_d.append(tuple(torch.from_numpy(p[k]).to(dev) for k in ("feat_A", "feat_B", "kps_A", "kps_B")))
+        sets_p.append(PairPipeline.pin(p["feat_A"], p["feat_B"], p["kps_A"], p["kps_B"]))      # pinned host copies (e2e inputs)
     pipe = PairPipeline(eng, seed=rank)
 
     def barrier():
@@ -207,7 +208,7 @@ def run_ours(args):
     results = []
     for i in range(args.warmup):
         results.append(pipe.register(*sets_d[i % N_SETS]))
-        pipe.register_host(*(sets_h[i % N_SETS][k] for k in ("feat_A", "feat_B", "kps_A", "kps_B")))
+        pipe.register_pinned(*sets_p[i % N_SETS])
     # ---- device-resident timed region -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     eng.profile(True)
@@ -232,8 +233,7 @@ def run_ours(args):
     barrier()
     ev0.record()
     for i in range(args.steps):
-        p = sets_h[i % N_SETS]
-        out = pipe.register_host(p["feat_A"], p["feat_B"], p["kps_A"], p["kps_B"])
+        out = pipe.register_pinned(*sets_p[i % N_SETS])      # H2D from pinned memory, pipeline, D2H of the transforms
     ev1.record()
     barrier()
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
@@ -267,7 +267,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N=1 only
             sec, cores, sample, _ = cpu_pair_seconds(K)
             cpu = {"value": K / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                    "seconds_per_cold_pair": sec}

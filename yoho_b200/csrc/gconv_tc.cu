@@ -7,15 +7,15 @@
 // SURVEY.md §7 hard part 1); three BF16 products per MAC measure 8e-6, at one third of the dense
 // BF16 peak by construction.
 //
-// Kernel (persistent, one CTA per SM, 320 threads, warp-specialised):
+// Kernel (persistent, one CTA per SM, 448 threads, warp-specialised):
 //   warps 0-3   A producers: each thread owns one of the 128 tile rows and gathers its 64-channel slice (hi and
 //               lo) for the current tap straight from L2 with 16-byte cp.async into the 128B-swizzled K-major
 //               layout UMMA expects — the group gather idx[j][k] is pure address arithmetic here.
-//   warp  8     W producer: the weights are pre-packed on the host as ready-made swizzled 32 KB tiles, so one
+//   warp  12    W producer: the weights are pre-packed on the host as ready-made swizzled 32 KB tiles, so one
 //               cp.async.bulk (TMA, 1-D) per tile lands them in shared memory and signals the stage mbarrier.
-//   warp  9     MMA issuer: one thread issues 12 tcgen05.mma (M128 x N256 x K16, kind::f16) per 64-wide K block,
+//   warp  13    MMA issuer: one thread issues 12 tcgen05.mma (M128 x N256 x K16, kind::f16) per 64-wide K block,
 //               accumulating all 13 taps x Cin channels of a tile in TMEM; tcgen05.commit releases the stage.
-//   warps 4-7   epilogue: tcgen05.ld the 128x256 FP32 accumulator (double-buffered in the 512 TMEM columns, so the
+//   warps 4-11  epilogue (two warps per TMEM lane quadrant, splitting the columns): tcgen05.ld the 128x256 FP32 accumulator (double-buffered in the 512 TMEM columns, so the
 //               next tile's MMAs overlap), add bias / residual, apply the NEXT layer's folded BN + ReLU, and write
 //               the activation as a bf16 hi/lo pair (the next layer's A operand) and/or FP32.
 #include <vector>
@@ -27,7 +27,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                       // bf16 elements per K block = one 128-byte swizzle row
 constexpr int A_TILE = BM * BK * 2;          // 16 KB (hi or lo)
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;               // 4 A-producer warps, 8 epilogue warps, W producer, MMA issuer
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_STAGES = 4;
 
 // Tile width BN = 256 for the wide layers (2 stages of 96 KB, two 256-column accumulators = all of TMEM) and
@@ -174,11 +175,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);    // tcgen05.commit
-            mbar_init(&bars->tmem_empty[a], 128); // epilogue threads
+            mbar_init(&bars->tmem_empty[a], EPI_THREADS); // epilogue threads
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == 13) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ================= W producer (one thread) =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -302,8 +303,10 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             }
         }
     } else {
-        // ================= epilogue warps 4..7 =================
-        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        // ================= epilogue warps 4..11 =================
+        // warp % 4 selects the TMEM lane quadrant the warp may access; the two warps of a quadrant split the columns
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.n_tiles;
@@ -321,8 +324,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
             const size_t orow = (size_t)(ok ? row : 0) * p.Cout + n0;
+            constexpr int NCH = BN / 32;                           // 32-column chunks of the tile
+            constexpr int CH0 = NCH >= 2 ? NCH / 2 : 0;           // chunks [0,CH0) -> half 0, [CH0,NCH) -> half 1
+            const int cc_lo = half == 0 ? 0 : CH0, cc_hi = half == 0 ? (NCH >= 2 ? CH0 : 0) : NCH;
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
+            for (int cc = cc_lo; cc < cc_hi; ++cc) {
                 uint32_t v[32];
                 tmem_ld32(t_addr + cc * 32, v);     // .sync.aligned: executed by the whole warp, rows past the end included
                 float f[32];
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }

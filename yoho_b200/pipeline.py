@@ -23,7 +23,7 @@ class PairPipeline:
         self.c_iters, self.o_iters = int(c_iters), int(o_iters)
         self.c_dist, self.o_dist = float(c_dist), float(o_dist)
         self.seed = int(seed)
-        self._pinned = {}
+        self._copy_stream = None
 
     # ---- device-resident pair ------------------------------------------------------------------------
     def register(self, featA, featB, kpsA, kpsB, eqvA=None, eqvB=None, descA=None, descB=None):
@@ -57,25 +57,45 @@ class PairPipeline:
                    o_best=ro["best_iter"], o_inl=ro["n_inl"], o_mask=ro["mask"])
         return out
 
-    # ---- host-facing call (the e2e path: host buffers in, host transforms out) -----------------------------
-    def _stage(self, name, arr, dtype):
-        t = self._pinned.get(name)
-        if t is None or t.shape != arr.shape or t.dtype != dtype:
-            t = torch.empty(arr.shape, dtype=dtype, pin_memory=True)
-            self._pinned[name] = t
-        t.copy_(torch.from_numpy(arr))
-        return t
+    # ---- host-facing calls (the e2e path: host buffers in, host transforms out) -----------------------------
+    @staticmethod
+    def pin(featA, featB, kpsA, kpsB):
+        """numpy -> pinned host tensors (do this once per pair, outside any timed region)."""
+        def p(a, dt):
+            t = torch.empty(a.shape, dtype=dt, pin_memory=True)
+            t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            return t
+        return (p(featA, torch.float32), p(featB, torch.float32), p(kpsA, torch.float64), p(kpsB, torch.float64))
+
+    def register_pinned(self, fa_pin, fb_pin, ka_pin, kb_pin):
+        """Pinned host tensors in -> numpy transforms out.  The four H2D copies run on a side stream; PartI of fragment A
+        starts as soon as A has landed, so the copy of fragment B hides behind it."""
+        dev = self.eng.device
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            fa = fa_pin.to(dev, non_blocking=True)
+            evA = torch.cuda.Event(); evA.record(cs)
+            fb = fb_pin.to(dev, non_blocking=True)
+            ka = ka_pin.to(dev, non_blocking=True)
+            kb = kb_pin.to(dev, non_blocking=True)
+            evB = torch.cuda.Event(); evB.record(cs)
+        for t in (fa, fb, ka, kb):
+            t.record_stream(main)
+        main.wait_event(evA)
+        oa = self.eng.part1(fa, want_inv=False, want_desc=True)
+        main.wait_event(evB)
+        ob = self.eng.part1(fb, want_inv=False, want_desc=True)
+        r = self.register(fa, fb, ka, kb, eqvA=oa["eqv"], eqvB=ob["eqv"], descA=oa["desc"], descB=ob["desc"])
+        res = torch.stack([r["T_c"], r["T_o"]]).cpu().numpy()          # D2H of the result (synchronises)
+        return dict(T_c=res[0], T_o=res[1], M=r["M"])
 
     def register_host(self, featA, featB, kpsA, kpsB):
-        """numpy in (feat [K,32,60] f32, kps [K,3] f64) -> numpy transforms out; H2D/D2H inside."""
-        dev = self.eng.device
-        fa = self._stage("fa", featA, torch.float32).to(dev, non_blocking=True)
-        fb = self._stage("fb", featB, torch.float32).to(dev, non_blocking=True)
-        ka = self._stage("ka", kpsA, torch.float64).to(dev, non_blocking=True)
-        kb = self._stage("kb", kpsB, torch.float64).to(dev, non_blocking=True)
-        r = self.register(fa, fb, ka, kb)
-        res = torch.stack([r["T_c"], r["T_o"]]).cpu().numpy()
-        return dict(T_c=res[0], T_o=res[1], M=r["M"])
+        """numpy in (feat [K,32,60] f32, kps [K,3] f64) -> numpy transforms out; staging + H2D + D2H inside."""
+        return self.register_pinned(*self.pin(featA, featB, kpsA, kpsB))
 
     @staticmethod
     def h2d_bytes(K):
