@@ -229,11 +229,8 @@ __global__ void __launch_bounds__(THREADS, 2) gconv_f32_kernel(const KArgs p) {
 template <int BN>
 int launch(yoho_ctx* ctx, KArgs& k, cudaStream_t st) {
     using L = SmemLayout<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        YCHECK(cudaFuncSetAttribute(gconv_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        attr_done = true;
-    }
+    // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
+    YCHECK(cudaFuncSetAttribute(gconv_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
     k.n_tiles = k.Cout / BN;
     const int m_tiles = (k.m_total + BM - 1) / BM;
     gconv_f32_kernel<BN><<<m_tiles * k.n_tiles, THREADS, L::BYTES, st>>>(k);

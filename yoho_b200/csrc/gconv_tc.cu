@@ -485,11 +485,8 @@ int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n
 
 template <int BN, bool SPLIT>
 static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, SPLIT>::SMEM_BYTES));
-        attr_done = true;
-    }
+    // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
+    YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, SPLIT>::SMEM_BYTES));
     p.n_tiles = p.Cout / BN;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
