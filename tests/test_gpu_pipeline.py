@@ -162,3 +162,25 @@ def test_pair_pipeline_recovers_planted_transform(engine, K, overlap):
     # host-facing call returns the same kind of answer
     h = pipe.register_host(pair['feat_A'], pair['feat_B'], pair['kps_A'], pair['kps_B'])
     assert h['M'] == M and _rot_err_deg(h['T_c'][:, :3], pair['R_gt']) < 2.0
+
+
+def test_scene_driver_matches_per_pair_pipeline(engine):
+    """configs 3-4 shape on one rank: PartI once per fragment, pairs from the cache == cold per-pair registration."""
+    from yoho_b200.pipeline import PairPipeline
+    from yoho_b200.batch import register_scene
+    engine.load_part1(synth.synth_state_dict('PartI', 0))
+    engine.load_part2(synth.synth_state_dict('PartII', 0))
+    a = synth.make_fragment_pair(400, seed=11, overlap=0.6)
+    b = synth.make_fragment_pair(400, seed=12, overlap=0.5)
+    frs = {0: (a['feat_A'], a['kps_A']), 1: (a['feat_B'], a['kps_B']), 2: (b['feat_A'], b['kps_A']), 3: (b['feat_B'], b['kps_B'])}
+    pair_ids = [(0, 1), (2, 3), (0, 3)]
+    res = register_scene(PairPipeline(engine, seed=3), frs, pair_ids)
+    assert tuple(res.shape) == (3, 2, 3, 4)
+    pipe = PairPipeline(engine, seed=3)                       # draws are seeded by pair position
+    dev = engine.device
+    for i, (x, y) in enumerate(pair_ids):
+        t = lambda v: torch.from_numpy(v).to(dev)
+        r = pipe.register(t(frs[x][0]), t(frs[y][0]), t(frs[x][1]), t(frs[y][1]), seed=3 + 1 + i)
+        assert torch.equal(res[i, 0], r['T_c']) and torch.equal(res[i, 1], r['T_o'])
+    Tc = res[0, 0].cpu().numpy()
+    assert _rot_err_deg(Tc[:, :3], a['R_gt']) < 3.0

@@ -29,6 +29,8 @@ constexpr int BK = 64;                       // bf16 elements per K block = one 
 constexpr int A_TILE = BM * BK * 2;          // 16 KB (hi or lo)
 constexpr int THREADS = 448;               // 4 A-producer warps, 8 epilogue warps, W producer, MMA issuer
 constexpr int EPI_THREADS = 256;
+constexpr int EPI_ROW = 80;                 // bytes per staged row: 64 payload + 16 pad (16-byte aligned, conflict-free)
+constexpr int EPI_WBUF = 32 * EPI_ROW;      // per-epilogue-warp staging buffer (2.5 KB)
 constexpr int MAX_STAGES = 4;
 
 // Tile width BN = 256 for the wide layers (2 stages of 96 KB, two 256-column accumulators = all of TMEM) and
@@ -48,7 +50,7 @@ struct Cfg {
     // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=128 (cute::UMMA::InstrDescriptor)
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     static constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + 3 * 512 * sizeof(float) +
-                                         64 * 13 * sizeof(int) + 256;
+                                         64 * 13 * sizeof(int) + 256 + 8 * EPI_WBUF;
 };
 
 struct TcArgs {
@@ -139,6 +141,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// Epilogue store of a [32 rows x NB bytes] block held one row per lane (NB/16 uint4 registers per lane): staged through a
+// per-warp shared-memory buffer so that each warp-wide store instruction writes NB contiguous bytes of 512/NB rows instead of
+// 16 bytes of 32 different rows (the L1TEX tag stage serialises on cache lines touched per instruction).
+template <int NB>
+__device__ __forceinline__ void coalesced_store(uint8_t* wbuf, const uint4* regs, uint8_t* gbase, size_t row_stride,
+                                                int lane, uint32_t okmask) {
+    constexpr int Q = NB / 16;                       // 16-byte pieces per row
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < Q; ++i) *reinterpret_cast<uint4*>(wbuf + lane * EPI_ROW + i * 16) = regs[i];
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < Q; ++it) {
+        const int item = it * 32 + lane;
+        const int row = item / Q, q = item % Q;
+        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + row * EPI_ROW + q * 16);
+        if ((okmask >> row) & 1u) *reinterpret_cast<uint4*>(gbase + (size_t)row * row_stride + q * 16) = v;
+    }
+}
+
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     using C = Cfg<BN, SPLIT>;
@@ -158,6 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     float* ep_shift = ep_scale + 512;
     int* idx_s = (int*)(ep_shift + 512);
     Barriers* bars = (Barriers*)(idx_s + 64 * 13);
+    uint8_t* epi_stage = (uint8_t*)bars + 256;          // 8 x EPI_WBUF, 16-byte aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -190,7 +213,6 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const int total_tiles = p.m_tiles * p.n_tiles;
-    const int cblocks = p.Cin >= BK ? p.Cin / BK : 1;
 
     if (warp < 4) {
         // ================= A producers =================
@@ -323,7 +345,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
-            const size_t orow = (size_t)(ok ? row : 0) * p.Cout + n0;
+            const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+            uint8_t* wbuf = epi_stage + (warp - 4) * EPI_WBUF;
             constexpr int NCH = BN / 32;                           // 32-column chunks of the tile
             constexpr int CH0 = NCH >= 2 ? NCH / 2 : 0;           // chunks [0,CH0) -> half 0, [CH0,NCH) -> half 1
             const int cc_lo = half == 0 ? 0 : CH0, cc_hi = half == 0 ? (NCH >= 2 ? CH0 : 0) : NCH;
@@ -339,49 +362,63 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
                 }
-                if (ok && n0 + cc * 32 < p.n_valid) {
+                if (n0 + cc * 32 < p.n_valid) {       // warp-uniform
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] += ep_bias[n0 + cc * 32 + i];
-                if (rres) {
+                    for (int i = 0; i < 32; ++i) f[i] += ep_bias[n0 + cc * 32 + i];
+                    if (rres) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 rv = *reinterpret_cast<const float4*>(rres + cc * 32 + i);
-                        f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
-                    }
-                }
-                if (p.out_raw) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(p.out_raw + orow + cc * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                }
-                if (p.out_act || p.out_hi) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        f[i] = fmaxf(fmaf(f[i], ep_scale[n0 + cc * 32 + i], ep_shift[n0 + cc * 32 + i]), 0.f);
-                    if (p.out_act) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(p.out_act + orow + cc * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                    }
-                    if (p.out_hi) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
-                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
-                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + orow + cc * 32);
-                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + orow + cc * 32);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                            dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 rv = *reinterpret_cast<const float4*>(rres + cc * 32 + i);
+                            f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
                         }
                     }
-                }
+                    // first row of this warp's 32-row block, column offset of this chunk
+                    const size_t blk = ((size_t)m_tile * BM + q * 32) * p.Cout + n0 + cc * 32;
+                    if (p.out_raw) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 r4[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                r4[i] = make_uint4(__float_as_uint(f[16 * h + 4 * i]), __float_as_uint(f[16 * h + 4 * i + 1]),
+                                                   __float_as_uint(f[16 * h + 4 * i + 2]), __float_as_uint(f[16 * h + 4 * i + 3]));
+                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_raw + blk + 16 * h), (size_t)p.Cout * 4, lane, okmask);
+                        }
+                    }
+                    if (p.out_act || p.out_hi) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            f[i] = fmaxf(fmaf(f[i], ep_scale[n0 + cc * 32 + i], ep_shift[n0 + cc * 32 + i]), 0.f);
+                        if (p.out_act) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint4 r4[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    r4[i] = make_uint4(__float_as_uint(f[16 * h + 4 * i]), __float_as_uint(f[16 * h + 4 * i + 1]),
+                                                       __float_as_uint(f[16 * h + 4 * i + 2]), __float_as_uint(f[16 * h + 4 * i + 3]));
+                                coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_act + blk + 16 * h), (size_t)p.Cout * 4, lane, okmask);
+                            }
+                        }
+                        if (p.out_hi) {
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
+                                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
+                                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
+                                hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            }
+                            uint4 r4[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) r4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_hi + blk), (size_t)p.Cout * 2, lane, okmask);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) r4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_lo + blk), (size_t)p.Cout * 2, lane, okmask);
+                        }
+                    }
                 }
                 __syncwarp();
             }

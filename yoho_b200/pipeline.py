@@ -26,7 +26,7 @@ class PairPipeline:
         self._copy_stream = None
 
     # ---- device-resident pair ------------------------------------------------------------------------
-    def register(self, featA, featB, kpsA, kpsB, eqvA=None, eqvB=None, descA=None, descB=None):
+    def register(self, featA, featB, kpsA, kpsB, eqvA=None, eqvB=None, descA=None, descB=None, seed=None):
         """All inputs CUDA tensors: feat [K,32,60] f32, kps [K,3] f64.  Pass precomputed eqv/desc to skip PartI
         (the amortised regime: one PartI pass per fragment per dataset, tests/extractor.py:46-47)."""
         e = self.eng
@@ -46,11 +46,13 @@ class PairPipeline:
             return out
         dr = e.rot_argmax(eqvB, eqvA, pairs=pairs)          # Batch_Des2R_torch(feats1[m1], feats0[m0])
         k0, k1 = e.gather_kps(kpsA, kpsB, pairs)
-        self.seed += 1
-        hyp, status = e.c_draw(dr, self.c_iters, self.seed)
+        if seed is None:
+            self.seed += 1
+            seed = self.seed
+        hyp, status = e.c_draw(dr, self.c_iters, seed)
         rc = e.c_ransac(k0, k1, hyp, self.c_dist)
         quat, trans = e.part2(featA, featB, eqvA, eqvB, dr, pairs=pairs, kps0=kpsA, kps1=kpsB)
-        order = e.o_order(M, self.seed)
+        order = e.o_order(M, seed)
         ro = e.o_score(k0, k1, trans, self.o_dist, order=order, max_hyp=self.o_iters)
         out.update(dr_index=dr, k0=k0, k1=k1, hyp=hyp, c_status=status, T_c=rc["T"], c_best=rc["best_iter"],
                    c_inl=rc["n_inl"], c_mask=rc["mask"], quat=quat, trans_pre=trans, T_o=ro["T"],
