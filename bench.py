@@ -100,8 +100,12 @@ def cpu_pair_seconds(kpts, sample_kp=900, sample_matches=256, threads=None):
     import yoho_oracle as O
     import estimator_oracle as E
     from yoho_b200 import synth
-    if threads:
-        torch.set_num_threads(threads)
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would starve the CPU arm)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     cores = torch.get_num_threads()
     R, P, N = O.load_tables()
     sdI, sdII = synth.synth_state_dict("PartI", 0), synth.synth_state_dict("PartII", 0)
