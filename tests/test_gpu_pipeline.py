@@ -128,7 +128,7 @@ def test_network_modules_and_knn_api(engine):
     assert np.array_equal(idx[0, 0].numpy(), g['knn_a01'])
 
 
-@pytest.mark.parametrize("K,overlap", [(2000, 0.5), (5000, 0.5), (5000, 0.15)])
+@pytest.mark.parametrize("K,overlap", [(2000, 0.5), (5000, 0.5), (5000, 0.15), (10000, 0.5)])
 def test_pair_pipeline_recovers_planted_transform(engine, K, overlap):
     """Full-size property test (BASELINE.json configs 2-4 shapes): encode a transform in a synthetic pair,
     run PartI -> ... -> YOHO-C / YOHO-O, decode it."""
@@ -184,3 +184,28 @@ def test_scene_driver_matches_per_pair_pipeline(engine):
         assert torch.equal(res[i, 0], r['T_c']) and torch.equal(res[i, 1], r['T_o'])
     Tc = res[0, 0].cpu().numpy()
     assert _rot_err_deg(Tc[:, :3], a['R_gt']) < 3.0
+
+
+def test_pipeline_degenerate_statistics_gives_identity(engine):
+    """Fewer than three matches per rotation bin: DR_statictic returns None and the reference writes the identity
+    (tests/estimator.py:41-51,107-108)."""
+    from yoho_b200.pipeline import PairPipeline
+    engine.load_part1(synth.synth_state_dict('PartI', 0))
+    engine.load_part2(synth.synth_state_dict('PartII', 0))
+    a, ka = synth.make_fragment(40, 1)
+    b, kb = synth.make_fragment(40, 2)            # unrelated fragments: a handful of accidental matches, spread over the bins
+    dev = engine.device
+    t = lambda v: torch.from_numpy(v).to(dev)
+    r = PairPipeline(engine, seed=0).register(t(a), t(b), t(ka), t(kb))
+    dr = r['dr_index'].cpu().numpy()
+    counts = np.bincount(dr, minlength=60)
+    if (counts >= 3).sum() == 0 or sum((c / 100.0) * (c / 100.0 - 0.01) * (c / 100.0 - 0.02) for c in counts if c >= 2) < 1e-4:
+        assert int(r['c_status'].item()) == 1
+        assert np.array_equal(r['T_c'].cpu().numpy(), np.eye(4)[:3]) and int(r['c_best'].item()) == -1
+
+
+def test_part2_empty(engine):
+    engine.load_part2(synth.synth_state_dict('PartII', 0))
+    z = np.zeros((0, 32, 60), np.float32)
+    q, tr = engine.part2(z, z, z, z, np.zeros((0,), np.int64), kps0=np.zeros((0, 3)), kps1=np.zeros((0, 3)))
+    assert tuple(q.shape) == (0, 4) and tuple(tr.shape) == (0, 3, 4)

@@ -51,6 +51,11 @@ class PairPipeline:
             seed = self.seed
         hyp, status = e.c_draw(dr, self.c_iters, seed)
         rc = e.c_ransac(k0, k1, hyp, self.c_dist)
+        # degenerate rotation statistics: the reference skips RANSAC and returns the identity (tests/estimator.py:107-108)
+        eye = torch.eye(4, dtype=torch.float64, device=e.device)[:3]
+        degenerate = status.to(torch.bool)
+        rc["T"] = torch.where(degenerate, eye, rc["T"])
+        rc["best_iter"] = torch.where(degenerate, torch.full_like(rc["best_iter"], -1), rc["best_iter"])
         quat, trans = e.part2(featA, featB, eqvA, eqvB, dr, pairs=pairs, kps0=kpsA, kps1=kpsB)
         order = e.o_order(M, seed)
         ro = e.o_score(k0, k1, trans, self.o_dist, order=order, max_hyp=self.o_iters)
