@@ -548,7 +548,9 @@ int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStr
     p.scale = a.scale; p.shift = a.shift;
     p.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
     p.flags = ctx->tc_flags;
-    const bool split = ctx->gconv_impl == 2;
+    // split accumulators only where the accumulation chain is long; short-K layers (PartI layers 1 and 4) keep two
+    // accumulator buffers in flight so that their (relatively heavy) epilogue overlaps the next tile's MMAs
+    const bool split = ctx->gconv_impl == 2 && p.nkb >= 16;
     if (tc_tile_n(L) == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
     return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);
 }
