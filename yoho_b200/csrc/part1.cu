@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(64) group_mean_kernel(const float* __restrict_
     if (threadIdx.x < YF) desc[(size_t)b * YF + threadIdx.x] = numpy_mean60(&e[threadIdx.x][0], 1);
 }
 
-constexpr int P1_CHUNK = 2048;  // keypoints per pass: bounds the workspace at ~0.63 GB
+constexpr int P1_CHUNK = 8192;  // keypoints per pass (3.6 GB of intermediates); a 5000-keypoint fragment is one pass, which keeps
+                                // the persistent tensor-core kernels at 16-32 full waves of tiles instead of 6-7
 
 }  // namespace
 
@@ -142,7 +143,8 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
     const bool tc_on = ctx->gconv_impl >= 1 && ctx->p1_in.w_hi && ctx->p1_a.w_hi && ctx->p1_b.w_hi && ctx->p1_out.w_hi;
     // per keypoint: xt 32, y1 256, a1 256 (fp32, or bf16 hi+lo = same bytes), a2 512 (same), a3 256, y4 32 floats x 60
     const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 512) * sizeof(float);
-    const int chunk = B < P1_CHUNK ? B : P1_CHUNK;
+    const int n_chunks = (B + P1_CHUNK - 1) / P1_CHUNK;
+    const int chunk = n_chunks > 0 ? (B + n_chunks - 1) / n_chunks : 0;      // balanced passes
     if (int rc = yoho_ws_reserve(ctx, per_kp * (size_t)chunk)) return rc;
     for (int s = 0; s < B; s += chunk) {
         const int n = (B - s) < chunk ? (B - s) : chunk;
