@@ -251,10 +251,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: the 256<->512 group convolutions of PartI ---------------------------
     pk = peaks()
-    dom = [p for p in prof if p["name"] in ("p1_L2_256x512", "p1_L3_512x256")]
+    fourier = eng.impl_name == "tcgen05_fourier"
+    dom = [p for p in prof if p["name"] in ("p1_L2_256x512", "p1_L3_512x256") or (fourier and p["name"] == "p1_fourier_transforms")]
     dms = sum(p["ms"] for p in dom)
     dfl = sum(p["flops"] for p in dom)
     dln = sum(p["launches"] for p in dom)
+    if fourier:     # algorithmic FLOPs of the two layers (13 taps x 60 group elements), whatever formulation executes them
+        dfl = args.steps * 2 * K * 60 * 13 * 256 * 512 * 2 * 2.0
     achieved = dfl / (dms / 1000.0) / 1e12 if dms > 0 else 0.0
     peak = pk["bf16_sustained"]
     traffic = None
@@ -265,7 +268,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     gconv_ms = sum(p["ms"] for p in prof)
-    roofline = {"bound": "tensor", "kernel": "gather-GEMM group convolution, PartI layers 2+3 (256->512->256, 13 taps)",
+    roofline = {"bound": "tensor", "kernel": "gather-GEMM group convolution, PartI layers 2+3 (256->512->256, 13 taps)" + (" in the group-Fourier domain: per-irrep GEMMs + transforms" if fourier else ""),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches": dln, "avg_launch_ms": dms / dln if dln else None,
@@ -310,7 +313,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kpts", type=int, default=5000)
-    ap.add_argument("--gconv", default=None, choices=[None, "simt", "tcgen05", "tcgen05_split"])
+    ap.add_argument("--gconv", default=None, choices=[None, "simt", "tcgen05", "tcgen05_split", "tcgen05_fourier"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

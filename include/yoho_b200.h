@@ -96,8 +96,22 @@ int yoho_ctx_destroy(yoho_ctx* ctx);
 int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w);
 int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w);
 
+/* Group-Fourier form of the two wide PartI layers (implementation 3).  F_host: orthogonal 60x60 transform, row m = Fourier
+ * coefficient (irrep, l, j), column g = group element (yoho_b200/fourier.py).  Per real irrep (dims 1,3,3,4,5): the weights of
+ * PartI layer 2 (w_a_host [d][256][d*512]) and layer 3 (w_b_host [d][512][d*256]) as d-tap gather-GEMM weights with column
+ * n = i*O + o, the input-row table idx_host[j*d + l] and the output-row table omap_host[j*d + i]. */
+typedef struct {
+    int d, off;
+    const float* w_a_host;
+    const float* w_b_host;
+    const int32_t* idx_host;
+    const int32_t* omap_host;
+} yoho_fourier_irrep;
+int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n_irreps, const yoho_fourier_irrep* irreps);
+
 /* Implementation of the group-convolution layers: 0 = FP32 SIMT (default), 1 = tcgen05 split-BF16,
- * 2 = tcgen05 split-BF16 with the small (lo) products in a separate TMEM accumulator (shorter rounding chain). */
+ * 2 = tcgen05 split-BF16 with the small (lo) products in a separate TMEM accumulator (shorter rounding chain),
+ * 3 = as 2, with PartI layers 2 and 3 evaluated in the group-Fourier domain (needs yoho_part1_load_fourier). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
 /* Tuning knobs of the tensor-core kernel (experiments; defaults are the measured best).  key 0 = producer flags. */
@@ -189,13 +203,14 @@ int64_t yoho_launch_count(const yoho_ctx* ctx);
  * roofline object).  enable=1 starts/clears recording, enable=0 stops.  yoho_profile_read synchronises the
  * device and returns, for layer class c in [0, YOHO_PROF_CLASSES): total milliseconds, launches and algorithmic
  * FLOPs (2 * rows * taps * Cin * Cout per launch).  Classes: 0..3 = PartI layers 1..4, 4..6 = PartII group
- * convolutions (init, a, b), 7 = PartII 1x1 head layers. */
+ * convolutions (init, a, b), 7 = PartII 1x1 head layers, 8 = group-Fourier transforms (implementation 3; classes 1 and 2 then
+ * hold the Fourier-domain GEMMs and their FLOPs are the executed ones). */
 /* Test hook: one PartI/PartII group-convolution layer in isolation on FP32 activations act [B,60,Cin]
  * (full 60-element index table), raw output [B,60,Cout] = conv + bias.  layer: 0..3 = PartI layers 1..4,
  * 4..6 = PartII init/a/b.  impl as in yoho_set_gconv_impl. */
 int yoho_debug_layer(yoho_ctx* ctx, int layer, int impl, const float* act, int B, float* out_raw, void* stream);
 
-#define YOHO_PROF_CLASSES 8
+#define YOHO_PROF_CLASSES 9
 int yoho_profile_enable(yoho_ctx* ctx, int enable);
 int yoho_profile_read(yoho_ctx* ctx, double* ms_host, int64_t* launches_host, double* flops_host);
 

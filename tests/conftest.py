@@ -57,12 +57,13 @@ def _engine_session():
     return get_engine()
 
 
-GCONV_IMPLS = ["simt", "tcgen05", "tcgen05_split"]
+GCONV_IMPLS = ["simt", "tcgen05", "tcgen05_split", "tcgen05_fourier"]
 
 
 @pytest.fixture(params=GCONV_IMPLS)
 def engine(request, _engine_session):
-    """Every GPU test runs once per group-convolution implementation (FP32 SIMT, tcgen05, tcgen05 split-accumulator)."""
+    """Every GPU test runs once per group-convolution implementation (FP32 SIMT, tcgen05, tcgen05 split-accumulator,
+    tcgen05 with PartI layers 2+3 in the group-Fourier domain)."""
     _engine_session.set_gconv_impl(request.param)
     _engine_session.impl_name = request.param
     yield _engine_session

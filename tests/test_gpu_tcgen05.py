@@ -59,7 +59,7 @@ def test_layer_tc_vs_simt(engine, layer, cin, cout, B, impl):
     assert err <= 6e-5 * max(scale, 1.0)
 
 
-@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_split"])
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_split", "tcgen05_fourier"])
 @pytest.mark.parametrize("K", [3, 130, 2100])
 def test_part1_tc_vs_oracle(engine, tables, K, impl):
     _, _, N = tables
@@ -82,7 +82,7 @@ def test_part1_tc_vs_oracle(engine, tables, K, impl):
     assert torch.equal(o["eqv"], o2["eqv"])                      # deterministic
 
 
-@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_split"])
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_split", "tcgen05_fourier"])
 def test_part1_tc_realckpt(engine, tables, impl):
     sd = real_ckpt("PartI")
     if sd is None:

@@ -45,3 +45,15 @@ for l, (cin, cout) in layers.items():
         ms = pr["ms"] / max(pr["launches"], 1)
         print(f"{l} {impl} flags={flags} {ms:.4f} ms  {flops / ms / 1e9:.1f} TFLOP/s(alg)  err={err:.3e}", flush=True)
 eng.set_tuning(0, 2)
+
+# ---- whole PartI forward per implementation (5000 keypoints) ------------------------------------------------------
+x = torch.from_numpy(synth.make_fragment(5000, 3)[0]).cuda()
+for impl in ["tcgen05_split", "tcgen05_fourier"]:
+    eng.set_gconv_impl(impl)
+    ms = time_it(lambda: eng.part1(x, want_inv=False))
+    eng.profile(True)
+    eng.part1(x, want_inv=False)
+    pr = eng.profile_read()
+    eng.profile(False)
+    print(f"part1 5000 kpts {impl}: {ms:.3f} ms; " + ", ".join(f"{q['name']}={q['ms']:.3f}" for q in pr if q['launches']), flush=True)
+eng.set_gconv_impl("tcgen05_split")

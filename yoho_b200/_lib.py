@@ -33,6 +33,11 @@ class yoho_part2_weights(ctypes.Structure):
                 ("fc3", yoho_conv_host)]
 
 
+class yoho_fourier_irrep(ctypes.Structure):
+    _fields_ = [("d", ctypes.c_int), ("off", ctypes.c_int), ("w_a_host", _c_f), ("w_b_host", _c_f),
+                ("idx_host", ctypes.POINTER(ctypes.c_int32)), ("omap_host", ctypes.POINTER(ctypes.c_int32))]
+
+
 # name -> (restype, argtypes); every symbol declared in include/yoho_b200.h
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -43,6 +48,7 @@ SYMBOLS = {
     "yoho_ctx_destroy": (_i, [_vp]),
     "yoho_part1_load": (_i, [_vp, ctypes.POINTER(yoho_part1_weights)]),
     "yoho_part2_load": (_i, [_vp, ctypes.POINTER(yoho_part2_weights)]),
+    "yoho_part1_load_fourier": (_i, [_vp, _vp, _i, _vp]),
     "yoho_set_gconv_impl": (_i, [_vp, _i]),
     "yoho_set_tuning": (_i, [_vp, _i, _i]),
     "yoho_part1_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
@@ -62,9 +68,9 @@ SYMBOLS = {
     "yoho_profile_enable": (_i, [_vp, _i]),
     "yoho_profile_read": (_i, [_vp, _vp, _vp, _vp]),
 }
-PROF_CLASSES = 8
+PROF_CLASSES = 9
 PROF_NAMES = ["p1_L1_32x256", "p1_L2_256x512", "p1_L3_512x256", "p1_L4_256x32",
-              "p2_init_128x256", "p2_a_256x512", "p2_b_512x256", "p2_head_1x1"]
+              "p2_init_128x256", "p2_a_256x512", "p2_b_512x256", "p2_head_1x1", "p1_fourier_transforms"]
 
 _lib = None
 

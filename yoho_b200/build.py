@@ -26,6 +26,7 @@ SOURCES = {
     "part2.cu": [],
     "match.cu": [],
     "lift.cu": [],
+    "fourier.cu": [],
     "estimator.cu": ["-fmad=false"],
 }
 

@@ -134,6 +134,8 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     for (GBn* b : bns) free_bn(*b);
     cudaFree(c->d_rot); cudaFree(c->d_rot32); cudaFree(c->d_perm); cudaFree(c->d_perm_t);
     cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one); cudaFree(c->d_idx_ident);
+    for (int r = 0; r < 8; ++r) { free_layer(c->p1f_a[r]); free_layer(c->p1f_b[r]); cudaFree(c->d_fidx[r]); cudaFree(c->d_fomap[r]); }
+    cudaFree(c->d_Fg2m); cudaFree(c->d_Fm2g);
     cudaFree(c->ws);
     delete c;
     return YOHO_OK;
@@ -200,6 +202,49 @@ extern "C" int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w) {
     return YOHO_OK;
 }
 
+extern "C" int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n_irreps, const yoho_fourier_irrep* irreps) {
+    YARG(ctx && F_host && irreps && n_irreps >= 1 && n_irreps <= 8);
+    YCHECK(cudaSetDevice(ctx->device));
+    ctx->has_p1f = false;
+    for (int r = 0; r < 8; ++r) {
+        free_layer(ctx->p1f_a[r]); free_layer(ctx->p1f_b[r]);
+        cudaFree(ctx->d_fidx[r]); cudaFree(ctx->d_fomap[r]);
+        ctx->d_fidx[r] = ctx->d_fomap[r] = nullptr;
+    }
+    cudaFree(ctx->d_Fg2m); cudaFree(ctx->d_Fm2g);
+    ctx->d_Fg2m = ctx->d_Fm2g = nullptr;
+    std::vector<float> g2m(YG * 64, 0.f), m2g(YG * 64, 0.f);
+    for (int m = 0; m < YG; ++m)
+        for (int g = 0; g < YG; ++g) { g2m[g * 64 + m] = F_host[m * YG + g]; m2g[m * 64 + g] = F_host[m * YG + g]; }
+    int rc = 0;
+    if ((rc = upload(&ctx->d_Fg2m, g2m))) return rc;
+    if ((rc = upload(&ctx->d_Fm2g, m2g))) return rc;
+    int total = 0;
+    for (int r = 0; r < n_irreps; ++r) {
+        const yoho_fourier_irrep& ir = irreps[r];
+        YARG(ir.d >= 1 && ir.d <= 5 && ir.w_a_host && ir.w_b_host && ir.idx_host && ir.omap_host);
+        total += ir.d * ir.d;
+        ctx->fd[r] = ir.d;
+        std::vector<int> idx(ir.idx_host, ir.idx_host + ir.d * ir.d), om(ir.omap_host, ir.omap_host + ir.d * ir.d);
+        if ((rc = upload(&ctx->d_fidx[r], idx))) return rc;
+        if ((rc = upload(&ctx->d_fomap[r], om))) return rc;
+        struct { GLayer* L; const float* w; int cin, o; int cls; } two[2] = {{&ctx->p1f_a[r], ir.w_a_host, 256, 512, 1},
+                                                                              {&ctx->p1f_b[r], ir.w_b_host, 512, 256, 2}};
+        for (auto& e : two) {
+            GLayer& L = *e.L;
+            L.cin = e.cin; L.cout = ir.d * e.o; L.taps = ir.d; L.tc_dense = 1; L.prof_class = e.cls;
+            std::vector<float> w(e.w, e.w + (size_t)ir.d * e.cin * L.cout), zb(L.cout, 0.f);
+            if ((rc = upload(&L.bias, zb))) return rc;
+            if ((rc = gconv_tc_pack(ctx, L, w))) return rc;
+            YARG(L.w_hi && L.w_lo);
+        }
+    }
+    YARG(total == YG);
+    ctx->nf = n_irreps;
+    ctx->has_p1f = true;
+    return YOHO_OK;
+}
+
 extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
     YARG(ctx && w);
     YCHECK(cudaSetDevice(ctx->device));
@@ -223,7 +268,7 @@ extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
 }
 
 extern "C" int yoho_set_gconv_impl(yoho_ctx* ctx, int impl) {
-    YARG(ctx && impl >= 0 && impl <= 2);
+    YARG(ctx && impl >= 0 && impl <= 3);
     ctx->gconv_impl = impl;
     return YOHO_OK;
 }
@@ -245,6 +290,18 @@ static cudaEvent_t prof_event(yoho_ctx* ctx) {
     if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
     else cudaEventCreate(&e);
     return e;
+}
+
+void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st) {
+    if (!ctx->prof_on) return;
+    yoho_ctx::ProfRec rec{};
+    rec.a = prof_event(ctx); rec.b = prof_event(ctx); rec.cls = cls; rec.flops = flops;
+    cudaEventRecord(rec.a, st);
+    ctx->prof.push_back(rec);
+}
+void yoho_prof_end(yoho_ctx* ctx, cudaStream_t st) {
+    if (!ctx->prof_on || ctx->prof.empty()) return;
+    cudaEventRecord(ctx->prof.back().b, st);
 }
 
 int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {

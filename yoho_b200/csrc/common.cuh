@@ -72,6 +72,15 @@ struct yoho_ctx {
     GLayer p1_out_cat;              // PartI layer 4 as one dense GEMM: W_cat[c][k*32+o] = W_k[c][o], 416 -> 512 columns
     int* d_idx_ident = nullptr;     // [60][1] identity
     GBn p1_bn_a, p1_bn_b, p1_bn_out;
+    // PartI layers 2+3 in the group-Fourier domain (implementation 3)
+    bool has_p1f = false;
+    int nf = 0;
+    int fd[8] = {0};
+    GLayer p1f_a[8], p1f_b[8];
+    int* d_fidx[8] = {nullptr};
+    int* d_fomap[8] = {nullptr};
+    float* d_Fg2m = nullptr;        // [60][64]: Fg2m[g][m] = F[m][g]   (forward transform as M1[k=g][m])
+    float* d_Fm2g = nullptr;        // [60][64]: Fm2g[m][g] = F[m][g]   (inverse transform as M1[k=m][g])
     // PartII
     bool has_p2 = false;
     GLayer p2_init, p2_a, p2_b, p2_fc1, p2_fc2, p2_fc3;
@@ -105,6 +114,9 @@ struct GConvArgs {
     void* out_hi;            // nullable [B][Jout][Cout] bf16: hi/lo of relu(out_raw*scale + shift)
     void* out_lo;
     int n_valid;             // tensor-core path: only columns < n_valid are written (0 = all)
+    // tensor-core path, group-Fourier layers: remapped output rows (see gconv_tc.cu TcArgs)
+    const int* omap;
+    int ogroup, out_J;
 };
 int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st);
 

@@ -72,6 +72,10 @@ struct TcArgs {
     const float* shift;
     int n_valid;                 // columns >= n_valid are not written
     int flags;                   // bit0: non-blocking producer completion, bit1: line-per-8-lanes producer mapping
+    // remapped output rows (group-Fourier layers): columns are groups of `ogroup`; group i of GEMM row (b,j) is written to
+    // row b*out_J + omap[j*n_groups + i] of an [.., ogroup]-wide output.  omap == nullptr: plain [rows][Cout] output.
+    const int* omap;
+    int ogroup, out_J;
 };
 
 struct __align__(8) Barriers {
@@ -145,9 +149,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // per-warp shared-memory buffer so that each warp-wide store instruction writes NB contiguous bytes of 512/NB rows instead of
 // 16 bytes of 32 different rows (the L1TEX tag stage serialises on cache lines touched per instruction).
 template <int NB>
-__device__ __forceinline__ void coalesced_store(uint8_t* wbuf, const uint4* regs, uint8_t* gbase, size_t row_stride,
-                                                int lane, uint32_t okmask) {
+__device__ __forceinline__ void coalesced_store(uint8_t* wbuf, const uint4* regs, uint8_t* my_row, int lane, uint32_t okmask) {
+    // my_row: global address of THIS lane's row (column offset applied); rows need not be equally spaced (remapped outputs)
     constexpr int Q = NB / 16;                       // 16-byte pieces per row
+    const unsigned long long addr = (unsigned long long)my_row;
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < Q; ++i) *reinterpret_cast<uint4*>(wbuf + lane * EPI_ROW + i * 16) = regs[i];
@@ -157,7 +162,8 @@ __device__ __forceinline__ void coalesced_store(uint8_t* wbuf, const uint4* regs
         const int item = it * 32 + lane;
         const int row = item / Q, q = item % Q;
         const uint4 v = *reinterpret_cast<const uint4*>(wbuf + row * EPI_ROW + q * 16);
-        if ((okmask >> row) & 1u) *reinterpret_cast<uint4*>(gbase + (size_t)row * row_stride + q * 16) = v;
+        const unsigned long long ra = __shfl_sync(0xffffffffu, addr, row);
+        if ((okmask >> row) & 1u) *reinterpret_cast<uint4*>((uint8_t*)ra + q * 16) = v;
     }
 }
 
@@ -186,6 +192,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     const int lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < p.Jout * p.taps; i += THREADS) idx_s[i] = p.idx[i];
+    int* omap_s = idx_s + 800;                            // <= 25 entries; Fourier layers use <= 25 idx entries as well
+    if (p.omap) for (int i = threadIdx.x; i < p.Jout * (p.Cout / p.ogroup); i += THREADS) omap_s[i] = p.omap[i];
     for (int i = threadIdx.x; i < p.Cout; i += THREADS) {
         ep_bias[i] = p.bias[i];
         ep_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -372,8 +380,16 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                             f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
                         }
                     }
-                    // first row of this warp's 32-row block, column offset of this chunk
-                    const size_t blk = ((size_t)m_tile * BM + q * 32) * p.Cout + n0 + cc * 32;
+                    // element offset of this lane's row at this chunk's first column
+                    size_t blk;
+                    if (p.omap) {
+                        const int n = n0 + cc * 32, grp = n / p.ogroup;
+                        const int rr = ok ? row : 0;
+                        const int b = rr / p.Jout, j = rr - b * p.Jout;
+                        blk = ((size_t)b * p.out_J + omap_s[j * (p.Cout / p.ogroup) + grp]) * p.ogroup + (n - grp * p.ogroup);
+                    } else {
+                        blk = (size_t)(ok ? row : 0) * p.Cout + n0 + cc * 32;
+                    }
                     if (p.out_raw) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -382,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                             for (int i = 0; i < 4; ++i)
                                 r4[i] = make_uint4(__float_as_uint(f[16 * h + 4 * i]), __float_as_uint(f[16 * h + 4 * i + 1]),
                                                    __float_as_uint(f[16 * h + 4 * i + 2]), __float_as_uint(f[16 * h + 4 * i + 3]));
-                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_raw + blk + 16 * h), (size_t)p.Cout * 4, lane, okmask);
+                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_raw + blk + 16 * h), lane, okmask);
                         }
                     }
                     if (p.out_act || p.out_hi) {
@@ -397,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                                 for (int i = 0; i < 4; ++i)
                                     r4[i] = make_uint4(__float_as_uint(f[16 * h + 4 * i]), __float_as_uint(f[16 * h + 4 * i + 1]),
                                                        __float_as_uint(f[16 * h + 4 * i + 2]), __float_as_uint(f[16 * h + 4 * i + 3]));
-                                coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_act + blk + 16 * h), (size_t)p.Cout * 4, lane, okmask);
+                                coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_act + blk + 16 * h), lane, okmask);
                             }
                         }
                         if (p.out_hi) {
@@ -413,10 +429,10 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                             uint4 r4[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) r4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_hi + blk), (size_t)p.Cout * 2, lane, okmask);
+                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_hi + blk), lane, okmask);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) r4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_lo + blk), (size_t)p.Cout * 2, lane, okmask);
+                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_lo + blk), lane, okmask);
                         }
                     }
                 }
@@ -548,9 +564,10 @@ int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStr
     p.scale = a.scale; p.shift = a.shift;
     p.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
     p.flags = ctx->tc_flags;
+    p.omap = a.omap; p.ogroup = a.omap ? a.ogroup : L.cout; p.out_J = a.out_J;
     // split accumulators only where the accumulation chain is long; short-K layers (PartI layers 1 and 4) keep two
     // accumulator buffers in flight so that their (relatively heavy) epilogue overlaps the next tile's MMAs
-    const bool split = ctx->gconv_impl == 2 && p.nkb >= 16;
+    const bool split = ctx->gconv_impl >= 2 && p.nkb >= 16 && !a.omap;     // Fourier layers: chains are short, keep overlap
     if (tc_tile_n(L) == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
     return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);
 }

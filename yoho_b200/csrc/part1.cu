@@ -9,6 +9,13 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
+// fourier.cu / abi.cu
+int group_transform(yoho_ctx* ctx, const float* in, int B, int C, const float* m1, const float* m2, const float* bias,
+                    const float* resid, const float* scale, const float* shift, void* out_hi, void* out_lo, float* out_f32,
+                    cudaStream_t st);
+void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st);
+void yoho_prof_end(yoho_ctx* ctx, cudaStream_t st);
+
 namespace {
 
 // [B][32][60] -> [B][60][32]; one CTA per keypoint.
@@ -142,7 +149,9 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
     YCHECK(cudaSetDevice(ctx->device));
     const bool tc_on = ctx->gconv_impl >= 1 && ctx->p1_in.w_hi && ctx->p1_a.w_hi && ctx->p1_b.w_hi && ctx->p1_out.w_hi;
     // per keypoint: xt 32, y1 256, a1 256 (fp32, or bf16 hi+lo = same bytes), a2 512 (same), a3 256, y4 32 floats x 60
-    const size_t per_kp = (size_t)YG * (32 + 256 + 256 + 512 + 256 + 512) * sizeof(float);
+    const bool fourier_on = tc_on && ctx->gconv_impl == 3 && ctx->has_p1f;
+    // group-Fourier path adds: a1 fp32 (256), X1 hi|lo (256), Y2 fp32 (512), X2 hi|lo (512), Y3 fp32 (256)
+    const size_t per_kp = (size_t)YG * ((32 + 256 + 256 + 512 + 256 + 512) + (fourier_on ? (256 + 256 + 512 + 512 + 256) : 0)) * sizeof(float);
     const int n_chunks = (B + P1_CHUNK - 1) / P1_CHUNK;
     const int chunk = n_chunks > 0 ? (B + n_chunks - 1) / n_chunks : 0;      // balanced passes
     if (int rc = yoho_ws_reserve(ctx, per_kp * (size_t)chunk)) return rc;
@@ -173,7 +182,43 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         a.resid = nullptr; a.out_raw = y1;
         a.scale = ctx->p1_bn_a.scale; a.shift = ctx->p1_bn_a.shift;
         if (tc) { a.act_hi = xt_hi; a.act_lo = xt_lo; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.act = xt; a.out_act = a1; }
+        if (fourier_on && n >= 128) { a.out_hi = a.out_lo = nullptr; a.out_act = y4 + (size_t)n * YG * 512; }   // FP32 a1 for the transform
         if (int rc = gconv_forward(ctx, ctx->p1_in, a, st)) return rc;
+        a.out_act = nullptr;
+        const bool fourier = fourier_on && n >= 128;
+        if (fourier) {
+            // ---- layers 2 and 3 in the group-Fourier domain (yoho_b200/fourier.py) ----
+            float* fa1 = y4 + (size_t)n * YG * 512;                 // a1 as FP32 (input of the forward transform)
+            unsigned short* X1h = (unsigned short*)(fa1 + (size_t)n * YG * 256);
+            unsigned short* X1l = X1h + (size_t)n * YG * 256;
+            float* Y2 = (float*)(X1l + (size_t)n * YG * 256);
+            unsigned short* X2h = (unsigned short*)(Y2 + (size_t)n * YG * 512);
+            unsigned short* X2l = X2h + (size_t)n * YG * 512;
+            float* Y3 = (float*)(X2l + (size_t)n * YG * 512);
+            yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
+            if (int rc = group_transform(ctx, fa1, n, 256, ctx->d_Fg2m, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, nullptr, st)) return rc;
+            yoho_prof_end(ctx, st);
+            GConvArgs f{};
+            f.B = n; f.Jin = YG; f.out_J = YG;
+            for (int r = 0; r < ctx->nf; ++r) {
+                f.act_hi = X1h; f.act_lo = X1l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
+                f.out_raw = Y2; f.omap = ctx->d_fomap[r]; f.ogroup = 512;
+                if (int rc = gconv_forward(ctx, ctx->p1f_a[r], f, st)) return rc;
+            }
+            yoho_prof_begin(ctx, 8, 2.0 * n * 512 * 7200.0, st);
+            if (int rc = group_transform(ctx, Y2, n, 512, ctx->d_Fm2g, ctx->d_Fg2m, ctx->p1_a.bias, nullptr, ctx->p1_bn_b.scale,
+                                         ctx->p1_bn_b.shift, X2h, X2l, nullptr, st)) return rc;
+            yoho_prof_end(ctx, st);
+            for (int r = 0; r < ctx->nf; ++r) {
+                f.act_hi = X2h; f.act_lo = X2l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
+                f.out_raw = Y3; f.omap = ctx->d_fomap[r]; f.ogroup = 256;
+                if (int rc = gconv_forward(ctx, ctx->p1f_b[r], f, st)) return rc;
+            }
+            yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
+            if (int rc = group_transform(ctx, Y3, n, 256, ctx->d_Fm2g, nullptr, ctx->p1_b.bias, y1, ctx->p1_bn_out.scale,
+                                         ctx->p1_bn_out.shift, a3_hi, a3_lo, nullptr, st)) return rc;
+            yoho_prof_end(ctx, st);
+        } else {
         // layer 2: a2 = relu(BN_b(GC_a(a1)))
         a.out_raw = nullptr;
         a.scale = ctx->p1_bn_b.scale; a.shift = ctx->p1_bn_b.shift;
@@ -184,6 +229,7 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         a.scale = ctx->p1_bn_out.scale; a.shift = ctx->p1_bn_out.shift;
         if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; a.out_hi = a3_hi; a.out_lo = a3_lo; } else { a.act = a2; a.out_act = a3; }
         if (int rc = gconv_forward(ctx, ctx->p1_b, a, st)) return rc;
+        }
         // layer 4: y4 = GC_out(a3).  Tensor-core path: one dense GEMM Z = a3 . W_cat [256 x 13*32] (a3 is read once, not
         // 13 times); the 13-tap gather-add happens on the 100 KB Z tile of each keypoint inside the finalize kernel.
         a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.out_hi = a.out_lo = nullptr; a.scale = a.shift = nullptr;

@@ -54,10 +54,34 @@ class Engine:
             pass
 
     # ---- weights -----------------------------------------------------------------------------------
-    def load_part1(self, state_dict):
+    def load_part1(self, state_dict, fourier=True):
         w, keep = _lib.part1_struct(state_dict)
         _lib.check(self.lib.yoho_part1_load(self.h, ctypes.byref(w)))
         self.has_part1 = True
+        if fourier:
+            self._load_part1_fourier(_lib._to_numpy_sd(state_dict))
+
+    def _load_part1_fourier(self, sd):
+        """Group-Fourier weights of PartI layers 2 and 3 (yoho_b200/fourier.py) for implementation 'tcgen05_fourier'."""
+        from . import fourier
+        T = fourier.build(self.tables.dir if self.tables.dir != _group._PKG_DIR else None)
+        blk = "PartI_net.SO3_Conv_layers.0."
+        pa = fourier.pack_layer(sd[blk + "comb_layer_in.2.weight"], T)
+        pb = fourier.pack_layer(sd[blk + "comb_layer_out.2.weight"], T)
+        n = len(pa)
+        arr = (_lib.yoho_fourier_irrep * n)()
+        keep = []
+        for r in range(n):
+            wa, wb = np.ascontiguousarray(pa[r]["w"]), np.ascontiguousarray(pb[r]["w"])
+            idx, om = np.ascontiguousarray(pa[r]["idx"], np.int32), np.ascontiguousarray(pa[r]["omap"], np.int32)
+            keep += [wa, wb, idx, om]
+            arr[r].d, arr[r].off = pa[r]["d"], pa[r]["off"]
+            arr[r].w_a_host = wa.ctypes.data_as(_lib._c_f)
+            arr[r].w_b_host = wb.ctypes.data_as(_lib._c_f)
+            arr[r].idx_host = idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+            arr[r].omap_host = om.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        F = np.ascontiguousarray(T["F"], np.float32)
+        _lib.check(self.lib.yoho_part1_load_fourier(self.h, F.ctypes.data, n, ctypes.cast(arr, ctypes.c_void_p)))
 
     def load_part2(self, state_dict):
         w, keep = _lib.part2_struct(state_dict)
@@ -66,7 +90,7 @@ class Engine:
 
     def set_gconv_impl(self, impl):
         self.impl_name = impl
-        _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2}.get(impl, impl)))
+        _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2, "tcgen05_fourier": 3}.get(impl, impl)))
 
     def set_tuning(self, key, value):
         _lib.check(self.lib.yoho_set_tuning(self.h, int(key), int(value)))
@@ -79,7 +103,7 @@ class Engine:
         act = self._f32(act)
         B = act.shape[0]
         out = self._empty((B, 60, cout), torch.float32)
-        _lib.check(self.lib.yoho_debug_layer(self.h, layer, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2}[impl], _ptr(act), B, _ptr(out), _stream()))
+        _lib.check(self.lib.yoho_debug_layer(self.h, layer, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2, "tcgen05_fourier": 3}[impl], _ptr(act), B, _ptr(out), _stream()))
         return out
 
     def profile(self, enable):
