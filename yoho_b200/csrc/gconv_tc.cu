@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     for (int i = threadIdx.x; i < p.Jout * p.taps; i += THREADS) idx_s[i] = p.idx[i];
     int* omap_s = idx_s + 800;                            // <= 25 entries; Fourier layers use <= 25 idx entries as well
     if (p.omap) for (int i = threadIdx.x; i < p.Jout * (p.Cout / p.ogroup); i += THREADS) omap_s[i] = p.omap[i];
-    for (int i = threadIdx.x; i < p.Cout; i += THREADS) {
+    // bias / next-BN tables of all Cout (<= 512) channels; the group-Fourier layers (Cout up to 2560) carry no bias or
+    // activation here (both are applied in the group domain by the transform kernel)
+    const bool has_ep = p.omap == nullptr;
+    for (int i = threadIdx.x; has_ep && i < p.Cout; i += THREADS) {
         ep_bias[i] = p.bias[i];
         ep_scale[i] = p.scale ? p.scale[i] : 1.f;
         ep_shift[i] = p.shift ? p.shift[i] : 0.f;
@@ -371,8 +374,10 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                     for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
                 }
                 if (n0 + cc * 32 < p.n_valid) {       // warp-uniform
+                    if (has_ep) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] += ep_bias[n0 + cc * 32 + i];
+                        for (int i = 0; i < 32; ++i) f[i] += ep_bias[n0 + cc * 32 + i];
+                    }
                     if (rres) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
@@ -551,6 +556,7 @@ static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
 
 int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
     YARG(gconv_tc_eligible(L, a));
+    YARG(a.omap ? (!a.out_act && !a.out_hi && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0) : L.cout <= 512);
     TcArgs p;
     p.a_hi = (const __nv_bfloat16*)a.act_hi; p.a_lo = (const __nv_bfloat16*)a.act_lo;
     p.w_hi = (const uint8_t*)L.w_hi; p.w_lo = (const uint8_t*)L.w_lo;
