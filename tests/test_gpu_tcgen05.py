@@ -148,3 +148,26 @@ def test_part2_tc_realckpt(engine, tables, impl):
     want = O.part2_forward(fA, fB, yA, yB, pre, sd, P, N)
     err, _ = _report(f"part2 real ckpt {impl} vs oracle", _np(q), want.numpy())
     assert err <= DESC_TOL
+
+
+def test_fourier_transform_kernels_agree(engine, tables):
+    """The warp-MMA transform kernel (default) against its FP32 SIMT twin (tuning flag 4), through the whole PartI."""
+    _, _, N = tables
+    sd = synth.synth_state_dict("PartI", 2)
+    engine.load_part1(sd)
+    x, _ = synth.make_fragment(300, 41)
+    engine.set_gconv_impl("tcgen05_fourier")
+    try:
+        engine.set_tuning(0, 3)
+        a = engine.part1(x)
+        engine.set_tuning(0, 3 | 4)
+        b = engine.part1(x)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_tuning(0, 3)
+        engine.set_gconv_impl("simt")
+    ref = O.part1_forward(x, sd, N)
+    _report("fourier mma-xf vs simt-xf", _np(a["eqv"]), _np(b["eqv"]))
+    e1, _ = _report("fourier mma-xf vs oracle", _np(a["eqv"]), ref["eqv"].numpy())
+    e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
+    assert e1 <= DESC_TOL and e2 <= DESC_TOL

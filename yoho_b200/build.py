@@ -27,6 +27,7 @@ SOURCES = {
     "match.cu": [],
     "lift.cu": [],
     "fourier.cu": [],
+    "fourier_mma.cu": [],
     "estimator.cu": ["-fmad=false"],
 }
 

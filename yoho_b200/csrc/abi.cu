@@ -136,6 +136,7 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one); cudaFree(c->d_idx_ident);
     for (int r = 0; r < 8; ++r) { free_layer(c->p1f_a[r]); free_layer(c->p1f_b[r]); cudaFree(c->d_fidx[r]); cudaFree(c->d_fomap[r]); }
     cudaFree(c->d_Fg2m); cudaFree(c->d_Fm2g);
+    cudaFree(c->d_fwd_hi); cudaFree(c->d_fwd_lo); cudaFree(c->d_inv_hi); cudaFree(c->d_inv_lo);
     cudaFree(c->ws);
     delete c;
     return YOHO_OK;
@@ -219,6 +220,23 @@ extern "C" int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n
     int rc = 0;
     if ((rc = upload(&ctx->d_Fg2m, g2m))) return rc;
     if ((rc = upload(&ctx->d_Fm2g, m2g))) return rc;
+    {   // bf16 hi/lo copies with the OUTPUT index as the row: forward[m][g] = F[m][g], inverse[g][m] = F[m][g]
+        auto f2bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7FFFu + ((u >> 16) & 1u); return (unsigned short)(u >> 16); };
+        auto bf2f = [](unsigned short h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; };
+        std::vector<unsigned short> fh(64 * 64, 0), fl(64 * 64, 0), ih(64 * 64, 0), il(64 * 64, 0);
+        for (int m = 0; m < YG; ++m)
+            for (int g = 0; g < YG; ++g) {
+                const float v = F_host[m * YG + g];
+                const unsigned short h = f2bf(v), l = f2bf(v - bf2f(h));
+                fh[m * 64 + g] = h; fl[m * 64 + g] = l;
+                ih[g * 64 + m] = h; il[g * 64 + m] = l;
+            }
+        cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_lo);
+        if ((rc = upload((unsigned short**)&ctx->d_fwd_hi, fh))) return rc;
+        if ((rc = upload((unsigned short**)&ctx->d_fwd_lo, fl))) return rc;
+        if ((rc = upload((unsigned short**)&ctx->d_inv_hi, ih))) return rc;
+        if ((rc = upload((unsigned short**)&ctx->d_inv_lo, il))) return rc;
+    }
     int total = 0;
     for (int r = 0; r < n_irreps; ++r) {
         const yoho_fourier_irrep& ir = irreps[r];

@@ -81,6 +81,9 @@ struct yoho_ctx {
     int* d_fomap[8] = {nullptr};
     float* d_Fg2m = nullptr;        // [60][64]: Fg2m[g][m] = F[m][g]   (forward transform as M1[k=g][m])
     float* d_Fm2g = nullptr;        // [60][64]: Fm2g[m][g] = F[m][g]   (inverse transform as M1[k=m][g])
+    // the same two matrices for the mma.sync transform kernel: [64 out][64 in] bf16 hi/lo (row = OUTPUT index)
+    void* d_fwd_hi = nullptr; void* d_fwd_lo = nullptr;     // forward: rows m (coefficient), cols g
+    void* d_inv_hi = nullptr; void* d_inv_lo = nullptr;     // inverse: rows g, cols m
     // PartII
     bool has_p2 = false;
     GLayer p2_init, p2_a, p2_b, p2_fc1, p2_fc2, p2_fc3;

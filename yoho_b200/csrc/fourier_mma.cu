@@ -1,0 +1,193 @@
+// Group-Fourier transforms on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x3 split, FP32 accumulate).
+// Same contract as group_transform_kernel in fourier.cu (which stays as the FP32 SIMT reference of this kernel):
+//     mid[m][c] = sum_k M1[k][m] in[k][c] ;  pointwise (bias / shortcut / BN+ReLU) ;  out[m][c] = sum_k M2[k][m] mid[k][c]
+// One CTA = one keypoint x 128 channels, 8 warps = 4 (16 output rows each) x 2 (64 channels each).
+// The transform is memory-bound (60x60 per channel), so the legacy warp MMA is enough here; the big GEMMs use tcgen05.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int XC = 128;               // channels per CTA
+constexpr int MP = 72;                // padded row length (bf16) of the 64x64 transform matrices: 144 B, conflict-free ldmatrix
+constexpr int XP = 136;               // padded row length (bf16) of the 64 x 128 data tiles: 272 B
+
+struct XmArgs {
+    const float* in;                  // [B][60][C] fp32
+    const __nv_bfloat16* m1_hi;       // [64 m][64 k] bf16: M1^T (row = output index m, col = input index k), zero padded
+    const __nv_bfloat16* m1_lo;
+    const __nv_bfloat16* m2_hi;       // nullable
+    const __nv_bfloat16* m2_lo;
+    const float* bias;
+    const float* resid;
+    const float* scale;
+    const float* shift;
+    unsigned short* out_hi;           // [B][60][C]
+    unsigned short* out_lo;
+    int B, C;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[nt][4] (8 n-tiles of 8 channels) += M^T (rows m0..m0+15) x data (64 k x channels n_base..n_base+63), 3 split products
+__device__ __forceinline__ void warp_product(const __nv_bfloat16* mh, const __nv_bfloat16* ml, const __nv_bfloat16* xh,
+                                             const __nv_bfloat16* xl, int m0, int n_base, int lane, float (&acc)[8][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const int arow = m0 + (lane & 15), acol = (lane >> 4) * 8;            // ldmatrix.x4 address pattern of a 16x16 A tile
+    const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;   // .trans: 16 k-rows x 16 channels
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[4], al[4];
+        ldsm_x4(ah, mh + arow * MP + ks * 16 + acol);
+        ldsm_x4(al, ml + arow * MP + ks * 16 + acol);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {                                   // pairs of n-tiles (16 channels)
+            uint32_t bh[4], bl[4];
+            const int off = (ks * 16 + brow) * XP + n_base + np * 16 + bcol;
+            ldsm_x4_t(bh, xh + off);
+            ldsm_x4_t(bl, xl + off);
+            mma16816(acc[2 * np], ah, bh[0], bh[1]);
+            mma16816(acc[2 * np], al, bh[0], bh[1]);
+            mma16816(acc[2 * np], ah, bl[0], bl[1]);
+            mma16816(acc[2 * np + 1], ah, bh[2], bh[3]);
+            mma16816(acc[2 * np + 1], al, bh[2], bh[3]);
+            mma16816(acc[2 * np + 1], ah, bl[2], bl[3]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+}
+
+__global__ void __launch_bounds__(256, 2) group_transform_mma_kernel(const XmArgs p) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    __nv_bfloat16* m1h = (__nv_bfloat16*)smraw;          // [64][MP]
+    __nv_bfloat16* m1l = m1h + 64 * MP;
+    __nv_bfloat16* m2h = m1l + 64 * MP;
+    __nv_bfloat16* m2l = m2h + 64 * MP;
+    __nv_bfloat16* xh = m2l + 64 * MP;                   // [64][XP]   input tile, later the output staging tile
+    __nv_bfloat16* xl = xh + 64 * XP;
+    __nv_bfloat16* yh = xl + 64 * XP;                    // [64][XP]   intermediate tile (two-stage transforms)
+    __nv_bfloat16* yl = yh + 64 * XP;
+    const int b = blockIdx.x, cb = blockIdx.y * XC, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    // transform matrices: 64 x 64 bf16, global row stride 64 -> smem row stride MP
+    for (int i = t; i < 64 * 8; i += 256) {
+        const int r = i >> 3, q = i & 7;
+        *reinterpret_cast<uint4*>(m1h + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_hi)[i];
+        *reinterpret_cast<uint4*>(m1l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_lo)[i];
+        if (p.m2_hi) {
+            *reinterpret_cast<uint4*>(m2h + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m2_hi)[i];
+            *reinterpret_cast<uint4*>(m2l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m2_lo)[i];
+        }
+    }
+    // input tile: fp32 -> bf16 hi/lo, rows 60..63 zero
+    const float* src = p.in + (size_t)b * YG * p.C + cb;
+    for (int i = t; i < 64 * (XC / 4); i += 256) {
+        const int k = i / (XC / 4), c4 = i % (XC / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < YG) v = *reinterpret_cast<const float4*>(src + (size_t)k * p.C + c4 * 4);
+        uint32_t l0, l1;
+        const uint32_t h0 = pack_hi_lo(v.x, v.y, l0), h1 = pack_hi_lo(v.z, v.w, l1);
+        *reinterpret_cast<uint2*>(xh + k * XP + c4 * 4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(xl + k * XP + c4 * 4) = make_uint2(l0, l1);
+    }
+    __syncthreads();
+
+    const int m0 = (warp & 3) * 16, n_base = (warp >> 2) * 64;
+    float acc[8][4];
+    warp_product(m1h, m1l, xh, xl, m0, n_base, lane, acc);
+
+    // pointwise stage on the accumulator fragments: thread holds rows m0 + lane/4 (+8), channels n + 2*(lane%4) + {0,1}
+    const int r0 = m0 + (lane >> 2), cq = 2 * (lane & 3);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = cb + n_base + nt * 8 + cq;
+        float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
+        if (p.bias) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
+        if (p.scale) { s0 = p.scale[c]; s1 = p.scale[c + 1]; h0 = p.shift[c]; h1 = p.shift[c + 1]; }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int m = r0 + 8 * hf;
+            float v0 = acc[nt][2 * hf] + b0, v1 = acc[nt][2 * hf + 1] + b1;
+            if (p.resid && m < YG) {
+                const float2 rr = *reinterpret_cast<const float2*>(p.resid + ((size_t)b * YG + m) * p.C + c);
+                v0 += rr.x; v1 += rr.y;
+            }
+            if (p.scale) { v0 = fmaxf(fmaf(v0, s0, h0), 0.f); v1 = fmaxf(fmaf(v1, s1, h1), 0.f); }
+            if (m >= YG) { v0 = 0.f; v1 = 0.f; }            // padded rows feed the second product as zeros
+            acc[nt][2 * hf] = v0; acc[nt][2 * hf + 1] = v1;
+        }
+    }
+    __nv_bfloat16* oh = xh;      // staging tile of the final result
+    __nv_bfloat16* ol = xl;
+    if (p.m2_hi) {
+        // intermediate -> shared as bf16 hi/lo [k = m][channel], then the second product
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t lo;
+                const uint32_t hi = pack_hi_lo(acc[nt][2 * hf], acc[nt][2 * hf + 1], lo);
+                const int o = (r0 + 8 * hf) * XP + n_base + nt * 8 + cq;
+                *reinterpret_cast<uint32_t*>(yh + o) = hi;
+                *reinterpret_cast<uint32_t*>(yl + o) = lo;
+            }
+        __syncthreads();
+        warp_product(m2h, m2l, yh, yl, m0, n_base, lane, acc);
+    } else {
+        __syncthreads();         // everybody is done reading xh/xl before they become the staging tile
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t lo;
+            const uint32_t hi = pack_hi_lo(acc[nt][2 * hf], acc[nt][2 * hf + 1], lo);
+            const int o = (r0 + 8 * hf) * XP + n_base + nt * 8 + cq;
+            *reinterpret_cast<uint32_t*>(oh + o) = hi;
+            *reinterpret_cast<uint32_t*>(ol + o) = lo;
+        }
+    __syncthreads();
+    // coalesced write of the [60][128] bf16 tiles
+    for (int i = t; i < YG * (XC / 8); i += 256) {
+        const int m = i / (XC / 8), q = i % (XC / 8);
+        const size_t o = ((size_t)b * YG + m) * p.C + cb + q * 8;
+        *reinterpret_cast<uint4*>(p.out_hi + o) = *reinterpret_cast<const uint4*>(oh + m * XP + q * 8);
+        *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(ol + m * XP + q * 8);
+    }
+}
+
+constexpr size_t XM_SMEM = (size_t)(4 * 64 * MP + 4 * 64 * XP) * sizeof(__nv_bfloat16);
+
+}  // namespace
+
+int group_transform_mma(yoho_ctx* ctx, const float* in, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
+                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
+                        void* out_hi, void* out_lo, cudaStream_t st) {
+    YARG(C % XC == 0 && B > 0 && in && m1_hi && m1_lo && out_hi && out_lo);
+    YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XM_SMEM));
+    XmArgs p{in, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
+             bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
+    group_transform_mma_kernel<<<dim3(B, C / XC), 256, XM_SMEM, st>>>(p);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}

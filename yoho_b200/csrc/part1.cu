@@ -13,6 +13,9 @@
 int group_transform(yoho_ctx* ctx, const float* in, int B, int C, const float* m1, const float* m2, const float* bias,
                     const float* resid, const float* scale, const float* shift, void* out_hi, void* out_lo, float* out_f32,
                     cudaStream_t st);
+int group_transform_mma(yoho_ctx* ctx, const float* in, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
+                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
+                        void* out_hi, void* out_lo, cudaStream_t st);
 void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st);
 void yoho_prof_end(yoho_ctx* ctx, cudaStream_t st);
 
@@ -196,7 +199,9 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             unsigned short* X2l = X2h + (size_t)n * YG * 512;
             float* Y3 = (float*)(X2l + (size_t)n * YG * 512);
             yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
-            if (int rc = group_transform(ctx, fa1, n, 256, ctx->d_Fg2m, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, nullptr, st)) return rc;
+            const bool xmma = (ctx->tc_flags & 4) == 0;     // warp-MMA transform kernel (default) vs the FP32 SIMT one
+            if (int rc = xmma ? group_transform_mma(ctx, fa1, n, 256, ctx->d_fwd_hi, ctx->d_fwd_lo, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, st)
+                              : group_transform(ctx, fa1, n, 256, ctx->d_Fg2m, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, nullptr, st)) return rc;
             yoho_prof_end(ctx, st);
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
@@ -206,8 +211,10 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
                 if (int rc = gconv_forward(ctx, ctx->p1f_a[r], f, st)) return rc;
             }
             yoho_prof_begin(ctx, 8, 2.0 * n * 512 * 7200.0, st);
-            if (int rc = group_transform(ctx, Y2, n, 512, ctx->d_Fm2g, ctx->d_Fg2m, ctx->p1_a.bias, nullptr, ctx->p1_bn_b.scale,
-                                         ctx->p1_bn_b.shift, X2h, X2l, nullptr, st)) return rc;
+            if (int rc = xmma ? group_transform_mma(ctx, Y2, n, 512, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_a.bias, nullptr,
+                                                    ctx->p1_bn_b.scale, ctx->p1_bn_b.shift, X2h, X2l, st)
+                              : group_transform(ctx, Y2, n, 512, ctx->d_Fm2g, ctx->d_Fg2m, ctx->p1_a.bias, nullptr, ctx->p1_bn_b.scale,
+                                                ctx->p1_bn_b.shift, X2h, X2l, nullptr, st)) return rc;
             yoho_prof_end(ctx, st);
             for (int r = 0; r < ctx->nf; ++r) {
                 f.act_hi = X2h; f.act_lo = X2l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
@@ -215,8 +222,10 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
                 if (int rc = gconv_forward(ctx, ctx->p1f_b[r], f, st)) return rc;
             }
             yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
-            if (int rc = group_transform(ctx, Y3, n, 256, ctx->d_Fm2g, nullptr, ctx->p1_b.bias, y1, ctx->p1_bn_out.scale,
-                                         ctx->p1_bn_out.shift, a3_hi, a3_lo, nullptr, st)) return rc;
+            if (int rc = xmma ? group_transform_mma(ctx, Y3, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, nullptr, nullptr, ctx->p1_b.bias, y1,
+                                                    ctx->p1_bn_out.scale, ctx->p1_bn_out.shift, a3_hi, a3_lo, st)
+                              : group_transform(ctx, Y3, n, 256, ctx->d_Fm2g, nullptr, ctx->p1_b.bias, y1, ctx->p1_bn_out.scale,
+                                                ctx->p1_bn_out.shift, a3_hi, a3_lo, nullptr, st)) return rc;
             yoho_prof_end(ctx, st);
         } else {
         // layer 2: a2 = relu(BN_b(GC_a(a1)))
