@@ -1,7 +1,7 @@
 // Group-Fourier transforms on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x3 split, FP32 accumulate).
 // Same contract as group_transform_kernel in fourier.cu (which stays as the FP32 SIMT reference of this kernel):
 //     mid[m][c] = sum_k M1[k][m] in[k][c] ;  pointwise (bias / shortcut / BN+ReLU) ;  out[m][c] = sum_k M2[k][m] mid[k][c]
-// One CTA = one keypoint x 128 channels, 8 warps = 4 (16 output rows each) x 2 (64 channels each).
+// One tile = one keypoint x 128 channels; 16 warps = 4 (16 output rows each) x 4 (32 channels each); persistent CTAs.
 // The transform is memory-bound (60x60 per channel), so the legacy warp MMA is enough here; the big GEMMs use tcgen05.
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -39,22 +39,42 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// acc[nt][4] (8 n-tiles of 8 channels) += M^T (rows m0..m0+15) x data (64 k x channels n_base..n_base+63), 3 split products
-__device__ __forceinline__ void warp_product(const __nv_bfloat16* mh, const __nv_bfloat16* ml, const __nv_bfloat16* xh,
-                                             const __nv_bfloat16* xl, int m0, int n_base, int lane, float (&acc)[8][4]) {
+__device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+}
+
+// Persistent: one CTA per SM loops over (keypoint, 128-channel) tiles.  The FP32 input tile (and the shortcut tile, if any) of
+// the NEXT tile streams into a staging buffer with cp.async while the current tile is converted, multiplied and written
+// back, so global loads are always in flight (the kernel is memory-bound: ~2 x 30 KB in, 30 KB out per tile).
+constexpr int XT = 512;                       // threads: 16 warps = 4 (16 rows) x 4 (32 channels)
+constexpr int STG = YG * XC;                  // floats of one staged [60][128] tile
+
+__device__ __forceinline__ void stage_tile(float* dst, const float* src, int C, int t) {
+    for (int i = t; i < YG * (XC / 4); i += XT) {
+        const int k = i / (XC / 4), c4 = i % (XC / 4);
+        cp_async16(dst + k * XC + c4 * 4, src + (size_t)k * C + c4 * 4, true);
+    }
+}
+
+// acc[nt][4] (4 n-tiles of 8 channels) = M^T (rows m0..m0+15) x data (64 k x channels n_base..n_base+31), 3 split products
+__device__ __forceinline__ void warp_product32(const __nv_bfloat16* mh, const __nv_bfloat16* ml, const __nv_bfloat16* xh,
+                                               const __nv_bfloat16* xl, int m0, int n_base, int lane, float (&acc)[4][4]) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-    const int arow = m0 + (lane & 15), acol = (lane >> 4) * 8;            // ldmatrix.x4 address pattern of a 16x16 A tile
-    const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;   // .trans: 16 k-rows x 16 channels
+    const int arow = m0 + (lane & 15), acol = (lane >> 4) * 8;
+    const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         uint32_t ah[4], al[4];
         ldsm_x4(ah, mh + arow * MP + ks * 16 + acol);
         ldsm_x4(al, ml + arow * MP + ks * 16 + acol);
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {                                   // pairs of n-tiles (16 channels)
+        for (int np = 0; np < 2; ++np) {
             uint32_t bh[4], bl[4];
             const int off = (ks * 16 + brow) * XP + n_base + np * 16 + bcol;
             ldsm_x4_t(bh, xh + off);
@@ -69,14 +89,7 @@ __device__ __forceinline__ void warp_product(const __nv_bfloat16* mh, const __nv
     }
 }
 
-__device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-}
-
-__global__ void __launch_bounds__(256, 2) group_transform_mma_kernel(const XmArgs p) {
+__global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs p) {
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* m1h = (__nv_bfloat16*)smraw;          // [64][MP]
     __nv_bfloat16* m1l = m1h + 64 * MP;
@@ -86,10 +99,13 @@ __global__ void __launch_bounds__(256, 2) group_transform_mma_kernel(const XmArg
     __nv_bfloat16* xl = xh + 64 * XP;
     __nv_bfloat16* yh = xl + 64 * XP;                    // [64][XP]   intermediate tile (two-stage transforms)
     __nv_bfloat16* yl = yh + 64 * XP;
-    const int b = blockIdx.x, cb = blockIdx.y * XC, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float* stage = (float*)(yl + 64 * XP);               // 2 x [60][128] fp32 input staging
+    float* rstage = stage + 2 * STG;                     // [60][128] fp32 shortcut staging
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cblocks = p.C / XC;
+    const int tiles = p.B * cblocks;
 
-    // transform matrices: 64 x 64 bf16, global row stride 64 -> smem row stride MP
-    for (int i = t; i < 64 * 8; i += 256) {
+    for (int i = t; i < 64 * 8; i += XT) {
         const int r = i >> 3, q = i & 7;
         *reinterpret_cast<uint4*>(m1h + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_hi)[i];
         *reinterpret_cast<uint4*>(m1l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_lo)[i];
@@ -98,84 +114,105 @@ __global__ void __launch_bounds__(256, 2) group_transform_mma_kernel(const XmArg
             *reinterpret_cast<uint4*>(m2l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m2_lo)[i];
         }
     }
-    // input tile: fp32 -> bf16 hi/lo, rows 60..63 zero
-    const float* src = p.in + (size_t)b * YG * p.C + cb;
-    for (int i = t; i < 64 * (XC / 4); i += 256) {
-        const int k = i / (XC / 4), c4 = i % (XC / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < YG) v = *reinterpret_cast<const float4*>(src + (size_t)k * p.C + c4 * 4);
-        uint32_t l0, l1;
-        const uint32_t h0 = pack_hi_lo(v.x, v.y, l0), h1 = pack_hi_lo(v.z, v.w, l1);
-        *reinterpret_cast<uint2*>(xh + k * XP + c4 * 4) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(xl + k * XP + c4 * 4) = make_uint2(l0, l1);
+    for (int i = t; i < 4 * XP; i += XT) {               // rows 60..63 of the data tiles stay zero
+        xh[YG * XP + i] = __float2bfloat16_rn(0.f); xl[YG * XP + i] = __float2bfloat16_rn(0.f);
+        yh[YG * XP + i] = __float2bfloat16_rn(0.f); yl[YG * XP + i] = __float2bfloat16_rn(0.f);
     }
-    __syncthreads();
-
-    const int m0 = (warp & 3) * 16, n_base = (warp >> 2) * 64;
-    float acc[8][4];
-    warp_product(m1h, m1l, xh, xl, m0, n_base, lane, acc);
-
-    // pointwise stage on the accumulator fragments: thread holds rows m0 + lane/4 (+8), channels n + 2*(lane%4) + {0,1}
+    int tile = blockIdx.x;
+    if (tile < tiles) {
+        const int b = tile / cblocks, cb = (tile - b * cblocks) * XC;
+        stage_tile(stage, p.in + (size_t)b * YG * p.C + cb, p.C, t);
+    }
+    cp_async_commit();
+    const int m0 = (warp & 3) * 16, n_base = (warp >> 2) * 32;
     const int r0 = m0 + (lane >> 2), cq = 2 * (lane & 3);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const int c = cb + n_base + nt * 8 + cq;
-        float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
-        if (p.bias) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
-        if (p.scale) { s0 = p.scale[c]; s1 = p.scale[c + 1]; h0 = p.shift[c]; h1 = p.shift[c + 1]; }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int m = r0 + 8 * hf;
-            float v0 = acc[nt][2 * hf] + b0, v1 = acc[nt][2 * hf + 1] + b1;
-            if (p.resid && m < YG) {
-                const float2 rr = *reinterpret_cast<const float2*>(p.resid + ((size_t)b * YG + m) * p.C + c);
-                v0 += rr.x; v1 += rr.y;
-            }
-            if (p.scale) { v0 = fmaxf(fmaf(v0, s0, h0), 0.f); v1 = fmaxf(fmaf(v1, s1, h1), 0.f); }
-            if (m >= YG) { v0 = 0.f; v1 = 0.f; }            // padded rows feed the second product as zeros
-            acc[nt][2 * hf] = v0; acc[nt][2 * hf + 1] = v1;
+    int it = 0;
+    for (; tile < tiles; tile += gridDim.x, ++it) {
+        const int b = tile / cblocks, cb = (tile - b * cblocks) * XC;
+        const float* cur = stage + (it & 1) * STG;
+        // group A: this tile's shortcut; group B: the next tile's input
+        if (p.resid) stage_tile(rstage, p.resid + (size_t)b * YG * p.C + cb, p.C, t);
+        cp_async_commit();
+        const int nxt = tile + gridDim.x;
+        if (nxt < tiles) {
+            const int nb = nxt / cblocks, ncb = (nxt - nb * cblocks) * XC;
+            stage_tile(stage + ((it + 1) & 1) * STG, p.in + (size_t)nb * YG * p.C + ncb, p.C, t);
         }
-    }
-    __nv_bfloat16* oh = xh;      // staging tile of the final result
-    __nv_bfloat16* ol = xl;
-    if (p.m2_hi) {
-        // intermediate -> shared as bf16 hi/lo [k = m][channel], then the second product
+        cp_async_commit();
+        cp_async_wait<2>();                                // this tile's input has landed (two younger groups may be in flight)
+        __syncthreads();
+        for (int i = t; i < YG * (XC / 4); i += XT) {      // fp32 -> bf16 hi/lo
+            const int k = i / (XC / 4), c4 = i % (XC / 4);
+            const float4 v = *reinterpret_cast<const float4*>(cur + k * XC + c4 * 4);
+            uint32_t l0, l1;
+            const uint32_t h0 = pack_hi_lo(v.x, v.y, l0), h1 = pack_hi_lo(v.z, v.w, l1);
+            *reinterpret_cast<uint2*>(xh + k * XP + c4 * 4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(xl + k * XP + c4 * 4) = make_uint2(l0, l1);
+        }
+        __syncthreads();
+        float acc[4][4];
+        warp_product32(m1h, m1l, xh, xl, m0, n_base, lane, acc);
+        if (p.resid) { cp_async_wait<1>(); }               // shortcut tile landed (the next input may still be in flight)
+        __syncthreads();                                   // ... and every warp is done reading xh/xl
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < 4; ++nt) {
+            const int cl = n_base + nt * 8 + cq, c = cb + cl;
+            float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
+            if (p.bias) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
+            if (p.scale) { s0 = p.scale[c]; s1 = p.scale[c + 1]; h0 = p.shift[c]; h1 = p.shift[c + 1]; }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
+                const int m = r0 + 8 * hf;
+                float v0 = acc[nt][2 * hf] + b0, v1 = acc[nt][2 * hf + 1] + b1;
+                if (p.resid && m < YG) {
+                    const float2 rr = *reinterpret_cast<const float2*>(rstage + m * XC + cl);
+                    v0 += rr.x; v1 += rr.y;
+                }
+                if (p.scale) { v0 = fmaxf(fmaf(v0, s0, h0), 0.f); v1 = fmaxf(fmaf(v1, s1, h1), 0.f); }
+                if (m >= YG) { v0 = 0.f; v1 = 0.f; }
+                acc[nt][2 * hf] = v0; acc[nt][2 * hf + 1] = v1;
+            }
+        }
+        if (p.m2_hi) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t lo;
+                    const uint32_t hi = pack_hi_lo(acc[nt][2 * hf], acc[nt][2 * hf + 1], lo);
+                    const int o = (r0 + 8 * hf) * XP + n_base + nt * 8 + cq;
+                    *reinterpret_cast<uint32_t*>(yh + o) = hi;
+                    *reinterpret_cast<uint32_t*>(yl + o) = lo;
+                }
+            __syncthreads();
+            warp_product32(m2h, m2l, yh, yl, m0, n_base, lane, acc);
+        }
+        // result -> staging tile (xh/xl are free: product 1 finished before the barrier above)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int m = r0 + 8 * hf;
+                if (m >= YG) continue;
                 uint32_t lo;
                 const uint32_t hi = pack_hi_lo(acc[nt][2 * hf], acc[nt][2 * hf + 1], lo);
-                const int o = (r0 + 8 * hf) * XP + n_base + nt * 8 + cq;
-                *reinterpret_cast<uint32_t*>(yh + o) = hi;
-                *reinterpret_cast<uint32_t*>(yl + o) = lo;
+                const int o = m * XP + n_base + nt * 8 + cq;
+                *reinterpret_cast<uint32_t*>(xh + o) = hi;
+                *reinterpret_cast<uint32_t*>(xl + o) = lo;
             }
         __syncthreads();
-        warp_product(m2h, m2l, yh, yl, m0, n_base, lane, acc);
-    } else {
-        __syncthreads();         // everybody is done reading xh/xl before they become the staging tile
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            uint32_t lo;
-            const uint32_t hi = pack_hi_lo(acc[nt][2 * hf], acc[nt][2 * hf + 1], lo);
-            const int o = (r0 + 8 * hf) * XP + n_base + nt * 8 + cq;
-            *reinterpret_cast<uint32_t*>(oh + o) = hi;
-            *reinterpret_cast<uint32_t*>(ol + o) = lo;
+        for (int i = t; i < YG * (XC / 8); i += XT) {      // coalesced write of the [60][128] bf16 tiles
+            const int m = i / (XC / 8), q = i % (XC / 8);
+            const size_t o = ((size_t)b * YG + m) * p.C + cb + q * 8;
+            *reinterpret_cast<uint4*>(p.out_hi + o) = *reinterpret_cast<const uint4*>(xh + m * XP + q * 8);
+            *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(xl + m * XP + q * 8);
         }
-    __syncthreads();
-    // coalesced write of the [60][128] bf16 tiles
-    for (int i = t; i < YG * (XC / 8); i += 256) {
-        const int m = i / (XC / 8), q = i % (XC / 8);
-        const size_t o = ((size_t)b * YG + m) * p.C + cb + q * 8;
-        *reinterpret_cast<uint4*>(p.out_hi + o) = *reinterpret_cast<const uint4*>(oh + m * XP + q * 8);
-        *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(ol + m * XP + q * 8);
+        __syncthreads();                                   // before the next conversion overwrites xh/xl and rstage is refilled
     }
+    cp_async_wait<0>();
 }
 
-constexpr size_t XM_SMEM = (size_t)(4 * 64 * MP + 4 * 64 * XP) * sizeof(__nv_bfloat16);
+constexpr size_t XM_SMEM = (size_t)(4 * 64 * MP + 4 * 64 * XP) * sizeof(__nv_bfloat16) + (size_t)3 * STG * sizeof(float);
 
 }  // namespace
 
@@ -186,7 +223,9 @@ int group_transform_mma(yoho_ctx* ctx, const float* in, int B, int C, const void
     YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XM_SMEM));
     XmArgs p{in, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
              bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
-    group_transform_mma_kernel<<<dim3(B, C / XC), 256, XM_SMEM, st>>>(p);
+    const int tiles = B * (C / XC);
+    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    group_transform_mma_kernel<<<grid, XT, XM_SMEM, st>>>(p);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
