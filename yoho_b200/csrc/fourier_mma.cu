@@ -13,7 +13,8 @@ constexpr int MP = 72;                // padded row length (bf16) of the 64x64 t
 constexpr int XP = 136;               // padded row length (bf16) of the 64 x 128 data tiles: 272 B
 
 struct XmArgs {
-    const float* in;                  // [B][60][C] fp32
+    const unsigned short* in_hi;      // [B][60][C] bf16 hi/lo split of the input
+    const unsigned short* in_lo;
     const __nv_bfloat16* m1_hi;       // [64 m][64 k] bf16: M1^T (row = output index m, col = input index k), zero padded
     const __nv_bfloat16* m1_lo;
     const __nv_bfloat16* m2_hi;       // nullable
@@ -50,12 +51,20 @@ __device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo) {
 // the NEXT tile streams into a staging buffer with cp.async while the current tile is converted, multiplied and written
 // back, so global loads are always in flight (the kernel is memory-bound: ~2 x 30 KB in, 30 KB out per tile).
 constexpr int XT = 512;                       // threads: 16 warps = 4 (16 rows) x 4 (32 channels)
-constexpr int STG = YG * XC;                  // floats of one staged [60][128] tile
+constexpr int STG = YG * XC;                  // floats of one staged [60][128] shortcut tile
 
+// [60][128] fp32 tile -> shared (row stride 128 floats)
 __device__ __forceinline__ void stage_tile(float* dst, const float* src, int C, int t) {
     for (int i = t; i < YG * (XC / 4); i += XT) {
         const int k = i / (XC / 4), c4 = i % (XC / 4);
         cp_async16(dst + k * XC + c4 * 4, src + (size_t)k * C + c4 * 4, true);
+    }
+}
+// [60][128] bf16 tile -> shared operand tile (row stride XP)
+__device__ __forceinline__ void stage_bf16(__nv_bfloat16* dst, const unsigned short* src, int C, int t) {
+    for (int i = t; i < YG * (XC / 8); i += XT) {
+        const int k = i / (XC / 8), q = i % (XC / 8);
+        cp_async16(dst + k * XP + q * 8, src + (size_t)k * C + q * 8, true);
     }
 }
 
@@ -95,12 +104,10 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
     __nv_bfloat16* m1l = m1h + 64 * MP;
     __nv_bfloat16* m2h = m1l + 64 * MP;
     __nv_bfloat16* m2l = m2h + 64 * MP;
-    __nv_bfloat16* xh = m2l + 64 * MP;                   // [64][XP]   input tile, later the output staging tile
-    __nv_bfloat16* xl = xh + 64 * XP;
-    __nv_bfloat16* yh = xl + 64 * XP;                    // [64][XP]   intermediate tile (two-stage transforms)
+    __nv_bfloat16* xbuf = m2l + 64 * MP;                 // 2 x {hi,lo} x [64][XP]: input tiles (double-buffered), reused as output staging
+    __nv_bfloat16* yh = xbuf + 4 * 64 * XP;              // [64][XP]   intermediate tile (two-stage transforms)
     __nv_bfloat16* yl = yh + 64 * XP;
-    float* stage = (float*)(yl + 64 * XP);               // 2 x [60][128] fp32 input staging
-    float* rstage = stage + 2 * STG;                     // [60][128] fp32 shortcut staging
+    float* rstage = (float*)(yl + 64 * XP);              // [60][128] fp32 shortcut staging
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int cblocks = p.C / XC;
     const int tiles = p.B * cblocks;
@@ -115,13 +122,16 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
         }
     }
     for (int i = t; i < 4 * XP; i += XT) {               // rows 60..63 of the data tiles stay zero
-        xh[YG * XP + i] = __float2bfloat16_rn(0.f); xl[YG * XP + i] = __float2bfloat16_rn(0.f);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) xbuf[s4 * 64 * XP + YG * XP + i] = __float2bfloat16_rn(0.f);
         yh[YG * XP + i] = __float2bfloat16_rn(0.f); yl[YG * XP + i] = __float2bfloat16_rn(0.f);
     }
     int tile = blockIdx.x;
     if (tile < tiles) {
         const int b = tile / cblocks, cb = (tile - b * cblocks) * XC;
-        stage_tile(stage, p.in + (size_t)b * YG * p.C + cb, p.C, t);
+        const size_t o = (size_t)b * YG * p.C + cb;
+        stage_bf16(xbuf, p.in_hi + o, p.C, t);
+        stage_bf16(xbuf + 64 * XP, p.in_lo + o, p.C, t);
     }
     cp_async_commit();
     const int m0 = (warp & 3) * 16, n_base = (warp >> 2) * 32;
@@ -129,26 +139,21 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
     int it = 0;
     for (; tile < tiles; tile += gridDim.x, ++it) {
         const int b = tile / cblocks, cb = (tile - b * cblocks) * XC;
-        const float* cur = stage + (it & 1) * STG;
+        __nv_bfloat16* xh = xbuf + (it & 1) * 2 * 64 * XP;
+        __nv_bfloat16* xl = xh + 64 * XP;
         // group A: this tile's shortcut; group B: the next tile's input
         if (p.resid) stage_tile(rstage, p.resid + (size_t)b * YG * p.C + cb, p.C, t);
         cp_async_commit();
         const int nxt = tile + gridDim.x;
         if (nxt < tiles) {
             const int nb = nxt / cblocks, ncb = (nxt - nb * cblocks) * XC;
-            stage_tile(stage + ((it + 1) & 1) * STG, p.in + (size_t)nb * YG * p.C + ncb, p.C, t);
+            const size_t o = (size_t)nb * YG * p.C + ncb;
+            __nv_bfloat16* nx = xbuf + ((it + 1) & 1) * 2 * 64 * XP;
+            stage_bf16(nx, p.in_hi + o, p.C, t);
+            stage_bf16(nx + 64 * XP, p.in_lo + o, p.C, t);
         }
         cp_async_commit();
         cp_async_wait<2>();                                // this tile's input has landed (two younger groups may be in flight)
-        __syncthreads();
-        for (int i = t; i < YG * (XC / 4); i += XT) {      // fp32 -> bf16 hi/lo
-            const int k = i / (XC / 4), c4 = i % (XC / 4);
-            const float4 v = *reinterpret_cast<const float4*>(cur + k * XC + c4 * 4);
-            uint32_t l0, l1;
-            const uint32_t h0 = pack_hi_lo(v.x, v.y, l0), h1 = pack_hi_lo(v.z, v.w, l1);
-            *reinterpret_cast<uint2*>(xh + k * XP + c4 * 4) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(xl + k * XP + c4 * 4) = make_uint2(l0, l1);
-        }
         __syncthreads();
         float acc[4][4];
         warp_product32(m1h, m1l, xh, xl, m0, n_base, lane, acc);
@@ -207,21 +212,21 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
             *reinterpret_cast<uint4*>(p.out_hi + o) = *reinterpret_cast<const uint4*>(xh + m * XP + q * 8);
             *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(xl + m * XP + q * 8);
         }
-        __syncthreads();                                   // before the next conversion overwrites xh/xl and rstage is refilled
+        __syncthreads();                                   // before this x buffer is refilled (two tiles ahead) and rstage is reused
     }
     cp_async_wait<0>();
 }
 
-constexpr size_t XM_SMEM = (size_t)(4 * 64 * MP + 4 * 64 * XP) * sizeof(__nv_bfloat16) + (size_t)3 * STG * sizeof(float);
+constexpr size_t XM_SMEM = (size_t)(4 * 64 * MP + 6 * 64 * XP) * sizeof(__nv_bfloat16) + (size_t)STG * sizeof(float);
 
 }  // namespace
 
-int group_transform_mma(yoho_ctx* ctx, const float* in, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
+int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                         const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                         void* out_hi, void* out_lo, cudaStream_t st) {
-    YARG(C % XC == 0 && B > 0 && in && m1_hi && m1_lo && out_hi && out_lo);
+    YARG(C % XC == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
     YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XM_SMEM));
-    XmArgs p{in, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
+    XmArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
              bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
     const int tiles = B * (C / XC);
     const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;

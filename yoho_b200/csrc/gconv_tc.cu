@@ -407,9 +407,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                         }
                     }
                     if (p.out_act || p.out_hi) {
+                        if (has_ep) {      // next layer's BN + ReLU; group-Fourier layers emit the raw value (hi/lo split only)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            f[i] = fmaxf(fmaf(f[i], ep_scale[n0 + cc * 32 + i], ep_shift[n0 + cc * 32 + i]), 0.f);
+                            for (int i = 0; i < 32; ++i)
+                                f[i] = fmaxf(fmaf(f[i], ep_scale[n0 + cc * 32 + i], ep_shift[n0 + cc * 32 + i]), 0.f);
+                        }
                         if (p.out_act) {
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
@@ -556,7 +558,7 @@ static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
 
 int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
     YARG(gconv_tc_eligible(L, a));
-    YARG(a.omap ? (!a.out_act && !a.out_hi && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0) : L.cout <= 512);
+    YARG(a.omap ? (!a.out_act && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0) : L.cout <= 512);
     TcArgs p;
     p.a_hi = (const __nv_bfloat16*)a.act_hi; p.a_lo = (const __nv_bfloat16*)a.act_lo;
     p.w_hi = (const uint8_t*)L.w_hi; p.w_lo = (const uint8_t*)L.w_lo;

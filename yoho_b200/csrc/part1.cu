@@ -13,7 +13,7 @@
 int group_transform(yoho_ctx* ctx, const float* in, int B, int C, const float* m1, const float* m2, const float* bias,
                     const float* resid, const float* scale, const float* shift, void* out_hi, void* out_lo, float* out_f32,
                     cudaStream_t st);
-int group_transform_mma(yoho_ctx* ctx, const float* in, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
+int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                         const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                         void* out_hi, void* out_lo, cudaStream_t st);
 void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st);
@@ -185,44 +185,53 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         a.resid = nullptr; a.out_raw = y1;
         a.scale = ctx->p1_bn_a.scale; a.shift = ctx->p1_bn_a.shift;
         if (tc) { a.act_hi = xt_hi; a.act_lo = xt_lo; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.act = xt; a.out_act = a1; }
-        if (fourier_on && n >= 128) { a.out_hi = a.out_lo = nullptr; a.out_act = y4 + (size_t)n * YG * 512; }   // FP32 a1 for the transform
+        if (fourier_on && n >= 128 && (ctx->tc_flags & 4)) { a.out_hi = a.out_lo = nullptr; a.out_act = y4 + (size_t)n * YG * 512; }   // FP32 a1 for the SIMT transform
         if (int rc = gconv_forward(ctx, ctx->p1_in, a, st)) return rc;
         a.out_act = nullptr;
         const bool fourier = fourier_on && n >= 128;
         if (fourier) {
             // ---- layers 2 and 3 in the group-Fourier domain (yoho_b200/fourier.py) ----
-            float* fa1 = y4 + (size_t)n * YG * 512;                 // a1 as FP32 (input of the forward transform)
+            // Every tensor between the kernels is a bf16 hi/lo pair (same bytes as FP32): the GEMMs consume it directly
+            // and the warp-MMA transform kernel streams it into its operand tiles with cp.async.  The FP32 SIMT transform
+            // kernel (tuning flag 4, kept as the reference twin) takes FP32 instead.
+            const bool xmma = (ctx->tc_flags & 4) == 0;
+            float* fa1 = y4 + (size_t)n * YG * 512;                 // FP32 a1 (SIMT transform path only)
             unsigned short* X1h = (unsigned short*)(fa1 + (size_t)n * YG * 256);
             unsigned short* X1l = X1h + (size_t)n * YG * 256;
             float* Y2 = (float*)(X1l + (size_t)n * YG * 256);
+            unsigned short* Y2h = (unsigned short*)Y2;
+            unsigned short* Y2l = Y2h + (size_t)n * YG * 512;
             unsigned short* X2h = (unsigned short*)(Y2 + (size_t)n * YG * 512);
             unsigned short* X2l = X2h + (size_t)n * YG * 512;
             float* Y3 = (float*)(X2l + (size_t)n * YG * 512);
+            unsigned short* Y3h = (unsigned short*)Y3;
+            unsigned short* Y3l = Y3h + (size_t)n * YG * 256;
             yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
-            const bool xmma = (ctx->tc_flags & 4) == 0;     // warp-MMA transform kernel (default) vs the FP32 SIMT one
-            if (int rc = xmma ? group_transform_mma(ctx, fa1, n, 256, ctx->d_fwd_hi, ctx->d_fwd_lo, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, st)
+            if (int rc = xmma ? group_transform_mma(ctx, a1_hi, a1_lo, n, 256, ctx->d_fwd_hi, ctx->d_fwd_lo, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, st)
                               : group_transform(ctx, fa1, n, 256, ctx->d_Fg2m, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, nullptr, st)) return rc;
             yoho_prof_end(ctx, st);
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
             for (int r = 0; r < ctx->nf; ++r) {
                 f.act_hi = X1h; f.act_lo = X1l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
-                f.out_raw = Y2; f.omap = ctx->d_fomap[r]; f.ogroup = 512;
+                f.omap = ctx->d_fomap[r]; f.ogroup = 512;
+                if (xmma) { f.out_raw = nullptr; f.out_hi = Y2h; f.out_lo = Y2l; } else { f.out_raw = Y2; f.out_hi = f.out_lo = nullptr; }
                 if (int rc = gconv_forward(ctx, ctx->p1f_a[r], f, st)) return rc;
             }
             yoho_prof_begin(ctx, 8, 2.0 * n * 512 * 7200.0, st);
-            if (int rc = xmma ? group_transform_mma(ctx, Y2, n, 512, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_a.bias, nullptr,
+            if (int rc = xmma ? group_transform_mma(ctx, Y2h, Y2l, n, 512, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_a.bias, nullptr,
                                                     ctx->p1_bn_b.scale, ctx->p1_bn_b.shift, X2h, X2l, st)
                               : group_transform(ctx, Y2, n, 512, ctx->d_Fm2g, ctx->d_Fg2m, ctx->p1_a.bias, nullptr, ctx->p1_bn_b.scale,
                                                 ctx->p1_bn_b.shift, X2h, X2l, nullptr, st)) return rc;
             yoho_prof_end(ctx, st);
             for (int r = 0; r < ctx->nf; ++r) {
                 f.act_hi = X2h; f.act_lo = X2l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
-                f.out_raw = Y3; f.omap = ctx->d_fomap[r]; f.ogroup = 256;
+                f.omap = ctx->d_fomap[r]; f.ogroup = 256;
+                if (xmma) { f.out_raw = nullptr; f.out_hi = Y3h; f.out_lo = Y3l; } else { f.out_raw = Y3; f.out_hi = f.out_lo = nullptr; }
                 if (int rc = gconv_forward(ctx, ctx->p1f_b[r], f, st)) return rc;
             }
             yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
-            if (int rc = xmma ? group_transform_mma(ctx, Y3, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, nullptr, nullptr, ctx->p1_b.bias, y1,
+            if (int rc = xmma ? group_transform_mma(ctx, Y3h, Y3l, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, nullptr, nullptr, ctx->p1_b.bias, y1,
                                                     ctx->p1_bn_out.scale, ctx->p1_bn_out.shift, a3_hi, a3_lo, st)
                               : group_transform(ctx, Y3, n, 256, ctx->d_Fm2g, nullptr, ctx->p1_b.bias, y1, ctx->p1_bn_out.scale,
                                                 ctx->p1_bn_out.shift, a3_hi, a3_lo, nullptr, st)) return rc;
