@@ -275,7 +275,9 @@ def run_ours(args):
                 "algorithmic_flops_per_launch": dfl / dln if dln else None,
                 "share_of_step": dms / ms if ms else None, "all_gconv_share_of_step": gconv_ms / ms if ms else None,
                 "impl": eng.impl_name, "traffic": traffic,
-                "note": "FP32 results at 1e-4 parity need >=3 bf16 products per MAC on tensor cores: frac <= 1/3 by construction"}
+                "note": ("FP32 results at 1e-4 parity need >=3 bf16 products per MAC on tensor cores: frac <= 1/3 for the direct "
+                         "formulation; the group-Fourier formulation executes 244/780 of the algorithmic MACs, so frac is counted "
+                         "in algorithmic FLOPs over the time of the per-irrep GEMMs plus the transform kernels")}
 
     line = None
     if rank == 0:
@@ -286,7 +288,7 @@ def run_ours(args):
                    "seconds_per_cold_pair": sec}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if eng.impl_name == "simt" else "f32 via bf16x3 split products, f32 accumulate (tcgen05)",
+                "dtype": "f32" if eng.impl_name == "simt" else "f32 via bf16x3 split products, f32 accumulate (tcgen05" + (", group-Fourier layers 2+3)" if fourier else ")"),
                 "data": "synthetic",
                 "config": {"workload": f"configs[1]: one cold {K}-keypoint 3DMatch-shaped pair per rank per step: PartI x2, "
                                        "mutual 1-NN, rotation argmax, YOHO-C 1000 iters, PartII, YOHO-O",

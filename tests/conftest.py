@@ -67,4 +67,4 @@ def engine(request, _engine_session):
     _engine_session.set_gconv_impl(request.param)
     _engine_session.impl_name = request.param
     yield _engine_session
-    _engine_session.set_gconv_impl("tcgen05_split")
+    _engine_session.set_gconv_impl("tcgen05_fourier")

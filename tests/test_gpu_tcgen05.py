@@ -26,7 +26,7 @@ def _report(name, got, want):
 @pytest.fixture
 def engine(_engine_session):
     yield _engine_session
-    _engine_session.set_gconv_impl("tcgen05_split")
+    _engine_session.set_gconv_impl("tcgen05_fourier")
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_split"])

@@ -38,9 +38,9 @@ class Engine:
         self.has_part1 = False
         self.has_part2 = False
         self.impl_name = None
-        # group-convolution implementation: tensor cores (split accumulators) by default;
-        # YOHO_B200_GCONV=simt|tcgen05|tcgen05_split selects another kernel
-        self.set_gconv_impl(os.environ.get("YOHO_B200_GCONV", "tcgen05_split"))
+        # group-convolution implementation: tensor cores, PartI layers 2+3 in the group-Fourier domain by default;
+        # YOHO_B200_GCONV=simt|tcgen05|tcgen05_split|tcgen05_fourier selects another one
+        self.set_gconv_impl(os.environ.get("YOHO_B200_GCONV", "tcgen05_fourier"))
 
     def close(self):
         if getattr(self, "h", None):
