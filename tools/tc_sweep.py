@@ -30,7 +30,7 @@ def time_it(fn, reps=6):
 
 
 print("layer impl flags ms TFLOPs(alg) maxerr_vs_simt")
-for l, (cin, cout) in layers.items():
+for l, (cin, cout) in (layers.items() if "--layers" in sys.argv else []):
     flops = 2.0 * B * 60 * 13 * cin * cout
     for impl, flags in itertools.product(["tcgen05", "tcgen05_split"], [0, 1, 2, 3]):
         eng.set_tuning(0, flags)
@@ -48,12 +48,14 @@ eng.set_tuning(0, 2)
 
 # ---- whole PartI forward per implementation (5000 keypoints) ------------------------------------------------------
 x = torch.from_numpy(synth.make_fragment(5000, 3)[0]).cuda()
-for impl in ["tcgen05_split", "tcgen05_fourier"]:
+for impl, flags in [("tcgen05_split", 3), ("tcgen05_fourier", 3), ("tcgen05_fourier", 3 | 8), ("tcgen05_fourier", 3 | 4)]:
     eng.set_gconv_impl(impl)
+    eng.set_tuning(0, flags)
     ms = time_it(lambda: eng.part1(x, want_inv=False))
     eng.profile(True)
     eng.part1(x, want_inv=False)
     pr = eng.profile_read()
     eng.profile(False)
-    print(f"part1 5000 kpts {impl}: {ms:.3f} ms; " + ", ".join(f"{q['name']}={q['ms']:.3f}" for q in pr if q['launches']), flush=True)
-eng.set_gconv_impl("tcgen05_split")
+    print(f"part1 5000 kpts {impl} flags={flags}: {ms:.3f} ms; " + ", ".join(f"{q['name']}={q['ms']:.3f}" for q in pr if q['launches']), flush=True)
+eng.set_tuning(0, 3)
+eng.set_gconv_impl("tcgen05_fourier")

@@ -8,9 +8,7 @@
 
 namespace {
 
-constexpr int XC = 128;               // channels per CTA
 constexpr int MP = 72;                // padded row length (bf16) of the 64x64 transform matrices: 144 B, conflict-free ldmatrix
-constexpr int XP = 136;               // padded row length (bf16) of the 64 x 128 data tiles: 272 B
 
 struct XmArgs {
     const unsigned short* in_hi;      // [B][60][C] bf16 hi/lo split of the input
@@ -50,29 +48,32 @@ __device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo) {
 // Persistent: one CTA per SM loops over (keypoint, 128-channel) tiles.  The FP32 input tile (and the shortcut tile, if any) of
 // the NEXT tile streams into a staging buffer with cp.async while the current tile is converted, multiplied and written
 // back, so global loads are always in flight (the kernel is memory-bound: ~2 x 30 KB in, 30 KB out per tile).
-constexpr int XT = 512;                       // threads: 16 warps = 4 (16 rows) x 4 (32 channels)
-constexpr int STG = YG * XC;                  // floats of one staged [60][128] shortcut tile
+constexpr int XT = 512;                       // threads: 16 warps = 4 (16 rows) x 4 (XC/4 channels)
 
-// [60][128] fp32 tile -> shared (row stride 128 floats)
+// [60][XC] fp32 tile -> shared (row stride XC floats)
+template <int XC>
 __device__ __forceinline__ void stage_tile(float* dst, const float* src, int C, int t) {
     for (int i = t; i < YG * (XC / 4); i += XT) {
         const int k = i / (XC / 4), c4 = i % (XC / 4);
         cp_async16(dst + k * XC + c4 * 4, src + (size_t)k * C + c4 * 4, true);
     }
 }
-// [60][128] bf16 tile -> shared operand tile (row stride XP)
+// [60][XC] bf16 tile -> shared operand tile (row stride XP = XC + 8)
+template <int XC>
 __device__ __forceinline__ void stage_bf16(__nv_bfloat16* dst, const unsigned short* src, int C, int t) {
+    constexpr int XP = XC + 8;
     for (int i = t; i < YG * (XC / 8); i += XT) {
         const int k = i / (XC / 8), q = i % (XC / 8);
         cp_async16(dst + k * XP + q * 8, src + (size_t)k * C + q * 8, true);
     }
 }
 
-// acc[nt][4] (4 n-tiles of 8 channels) = M^T (rows m0..m0+15) x data (64 k x channels n_base..n_base+31), 3 split products
+// acc[nt][4] (NT n-tiles of 8 channels) = M^T (rows m0..m0+15) x data (64 k x channels n_base..n_base+8*NT-1), 3 split products
+template <int NT, int XP>
 __device__ __forceinline__ void warp_product32(const __nv_bfloat16* mh, const __nv_bfloat16* ml, const __nv_bfloat16* xh,
-                                               const __nv_bfloat16* xl, int m0, int n_base, int lane, float (&acc)[4][4]) {
+                                               const __nv_bfloat16* xl, int m0, int n_base, int lane, float (&acc)[NT][4]) {
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const int arow = m0 + (lane & 15), acol = (lane >> 4) * 8;
@@ -83,7 +84,7 @@ __device__ __forceinline__ void warp_product32(const __nv_bfloat16* mh, const __
         ldsm_x4(ah, mh + arow * MP + ks * 16 + acol);
         ldsm_x4(al, ml + arow * MP + ks * 16 + acol);
 #pragma unroll
-        for (int np = 0; np < 2; ++np) {
+        for (int np = 0; np < NT / 2; ++np) {
             uint32_t bh[4], bl[4];
             const int off = (ks * 16 + brow) * XP + n_base + np * 16 + bcol;
             ldsm_x4_t(bh, xh + off);
@@ -98,7 +99,11 @@ __device__ __forceinline__ void warp_product32(const __nv_bfloat16* mh, const __
     }
 }
 
-__global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs p) {
+template <int XC>
+__global__ void __launch_bounds__(XT, XC == 128 ? 1 : 2) group_transform_mma_kernel(const XmArgs p) {
+    constexpr int XP = XC + 8;                 // padded row length (bf16) of the data tiles: conflict-free ldmatrix
+    constexpr int NT = XC / 32;                // 8-channel n-tiles per warp
+    constexpr int STG = YG * XC;               // floats of one staged shortcut tile
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* m1h = (__nv_bfloat16*)smraw;          // [64][MP]
     __nv_bfloat16* m1l = m1h + 64 * MP;
@@ -130,11 +135,11 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
     if (tile < tiles) {
         const int b = tile / cblocks, cb = (tile - b * cblocks) * XC;
         const size_t o = (size_t)b * YG * p.C + cb;
-        stage_bf16(xbuf, p.in_hi + o, p.C, t);
-        stage_bf16(xbuf + 64 * XP, p.in_lo + o, p.C, t);
+        stage_bf16<XC>(xbuf, p.in_hi + o, p.C, t);
+        stage_bf16<XC>(xbuf + 64 * XP, p.in_lo + o, p.C, t);
     }
     cp_async_commit();
-    const int m0 = (warp & 3) * 16, n_base = (warp >> 2) * 32;
+    const int m0 = (warp & 3) * 16, n_base = (warp >> 2) * (XC / 4);
     const int r0 = m0 + (lane >> 2), cq = 2 * (lane & 3);
     int it = 0;
     for (; tile < tiles; tile += gridDim.x, ++it) {
@@ -142,25 +147,25 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
         __nv_bfloat16* xh = xbuf + (it & 1) * 2 * 64 * XP;
         __nv_bfloat16* xl = xh + 64 * XP;
         // group A: this tile's shortcut; group B: the next tile's input
-        if (p.resid) stage_tile(rstage, p.resid + (size_t)b * YG * p.C + cb, p.C, t);
+        if (p.resid) stage_tile<XC>(rstage, p.resid + (size_t)b * YG * p.C + cb, p.C, t);
         cp_async_commit();
         const int nxt = tile + gridDim.x;
         if (nxt < tiles) {
             const int nb = nxt / cblocks, ncb = (nxt - nb * cblocks) * XC;
             const size_t o = (size_t)nb * YG * p.C + ncb;
             __nv_bfloat16* nx = xbuf + ((it + 1) & 1) * 2 * 64 * XP;
-            stage_bf16(nx, p.in_hi + o, p.C, t);
-            stage_bf16(nx + 64 * XP, p.in_lo + o, p.C, t);
+            stage_bf16<XC>(nx, p.in_hi + o, p.C, t);
+            stage_bf16<XC>(nx + 64 * XP, p.in_lo + o, p.C, t);
         }
         cp_async_commit();
         cp_async_wait<2>();                                // this tile's input has landed (two younger groups may be in flight)
         __syncthreads();
-        float acc[4][4];
-        warp_product32(m1h, m1l, xh, xl, m0, n_base, lane, acc);
+        float acc[NT][4];
+        warp_product32<NT, XP>(m1h, m1l, xh, xl, m0, n_base, lane, acc);
         if (p.resid) { cp_async_wait<1>(); }               // shortcut tile landed (the next input may still be in flight)
         __syncthreads();                                   // ... and every warp is done reading xh/xl
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             const int cl = n_base + nt * 8 + cq, c = cb + cl;
             float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
             if (p.bias) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
         }
         if (p.m2_hi) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t lo;
@@ -190,11 +195,11 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
                     *reinterpret_cast<uint32_t*>(yl + o) = lo;
                 }
             __syncthreads();
-            warp_product32(m2h, m2l, yh, yl, m0, n_base, lane, acc);
+            warp_product32<NT, XP>(m2h, m2l, yh, yl, m0, n_base, lane, acc);
         }
         // result -> staging tile (xh/xl are free: product 1 finished before the barrier above)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const int m = r0 + 8 * hf;
@@ -217,20 +222,27 @@ __global__ void __launch_bounds__(XT, 1) group_transform_mma_kernel(const XmArgs
     cp_async_wait<0>();
 }
 
-constexpr size_t XM_SMEM = (size_t)(4 * 64 * MP + 6 * 64 * XP) * sizeof(__nv_bfloat16) + (size_t)STG * sizeof(float);
+template <int XC>
+constexpr size_t xm_smem() { return (size_t)(4 * 64 * MP + 6 * 64 * (XC + 8)) * sizeof(__nv_bfloat16) + (size_t)YG * XC * sizeof(float); }
 
 }  // namespace
 
 int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                         const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                         void* out_hi, void* out_lo, cudaStream_t st) {
-    YARG(C % XC == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
-    YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XM_SMEM));
+    YARG(C % 128 == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
     XmArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
              bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
-    const int tiles = B * (C / XC);
-    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    group_transform_mma_kernel<<<grid, XT, XM_SMEM, st>>>(p);
+    if (ctx->tc_flags & 8) {      // 128-channel tiles, one CTA per SM
+        YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem<128>()));
+        const int tiles = B * (C / 128);
+        group_transform_mma_kernel<128><<<tiles < ctx->num_sms ? tiles : ctx->num_sms, XT, xm_smem<128>(), st>>>(p);
+    } else {                      // 64-channel tiles, two CTAs per SM (default): the barriers of one tile hide behind the other
+        YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem<64>()));
+        const int tiles = B * (C / 64);
+        const int cap = 2 * ctx->num_sms;
+        group_transform_mma_kernel<64><<<tiles < cap ? tiles : cap, XT, xm_smem<64>(), st>>>(p);
+    }
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
