@@ -162,6 +162,10 @@ def test_fourier_transform_kernels_agree(engine, tables):
         a = engine.part1(x)
         engine.set_tuning(0, 3 | 4)
         b = engine.part1(x)
+        engine.set_tuning(0, 3 | 8)          # 128-channel transform tiles: same arithmetic, different tiling
+        c = engine.part1(x)
+        engine.set_tuning(0, 3 | 16)         # one launch per irrep instead of the grouped launch
+        d = engine.part1(x)
         torch.cuda.synchronize()
     finally:
         engine.set_tuning(0, 3)
@@ -171,3 +175,4 @@ def test_fourier_transform_kernels_agree(engine, tables):
     e1, _ = _report("fourier mma-xf vs oracle", _np(a["eqv"]), ref["eqv"].numpy())
     e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
     assert e1 <= DESC_TOL and e2 <= DESC_TOL
+    assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], d["eqv"])

@@ -338,6 +338,18 @@ int gconv_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream
     return rc;
 }
 
+int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st);
+
+// All per-irrep GEMMs of a group-Fourier layer in one launch (falls back to one launch per irrep for the SIMT twin).
+int gconv_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st) {
+    double flops = 0;
+    for (int g = 0; g < n; ++g) flops += 2.0 * (double)as[g].B * as[g].Jout * Ls[g]->taps * Ls[g]->cin * Ls[g]->cout;
+    yoho_prof_begin(ctx, Ls[0]->prof_class, flops, st);
+    const int rc = gconv_tc_forward_grouped(ctx, Ls, as, n, st);
+    yoho_prof_end(ctx, st);
+    return rc;
+}
+
 extern "C" int yoho_profile_enable(yoho_ctx* ctx, int enable) {
     YARG(ctx);
     YCHECK(cudaSetDevice(ctx->device));

@@ -53,15 +53,24 @@ struct Cfg {
                                          64 * 13 * sizeof(int) + 256 + 8 * EPI_WBUF;
 };
 
+// One GEMM of a launch.  A launch is a list of up to MAX_GROUPS GEMMs sharing the activation tensor and the output
+// tensor (the per-irrep GEMMs of a group-Fourier layer run as ONE persistent launch, so there is one tail, not five).
+constexpr int MAX_GROUPS = 5;
+struct TcGroup {
+    const uint8_t* w_hi;         // [n_tiles][nkb] swizzled tiles
+    const uint8_t* w_lo;
+    const int* idx;              // [Jout][taps] input-row table
+    const int* omap;             // [Jout][Cout/ogroup] output-row table (nullptr: plain [rows][Cout] output)
+    int Jout, taps, Cout, nkb, m_total, n_tiles, tile_begin, idx_off, omap_off;
+};
+
 struct TcArgs {
     const __nv_bfloat16* a_hi;   // [B][Jin][Cin]
     const __nv_bfloat16* a_lo;
-    const uint8_t* w_hi;         // [n_tiles][nkb] swizzled 32 KB tiles
-    const uint8_t* w_lo;
     const float* bias;
-    const int* idx;
-    int Jin, Jout, Cin, Cout, taps;
-    int m_total, m_tiles, n_tiles, nkb;
+    int Jin, Cin;
+    int ngroups, total_tiles;
+    TcGroup grp[MAX_GROUPS];
     const float* resid;
     int Jres, resid_off, resid_per_j;
     float* out_raw;
@@ -73,10 +82,15 @@ struct TcArgs {
     int n_valid;                 // columns >= n_valid are not written
     int flags;                   // bit0: non-blocking producer completion, bit1: line-per-8-lanes producer mapping
     // remapped output rows (group-Fourier layers): columns are groups of `ogroup`; group i of GEMM row (b,j) is written to
-    // row b*out_J + omap[j*n_groups + i] of an [.., ogroup]-wide output.  omap == nullptr: plain [rows][Cout] output.
-    const int* omap;
+    // row b*out_J + omap[j*n_groups + i] of an [.., ogroup]-wide output.
     int ogroup, out_J;
 };
+
+__device__ __forceinline__ int find_group(const TcArgs& p, int tile) {
+    int g = 0;
+    while (g + 1 < p.ngroups && tile >= p.grp[g + 1].tile_begin) ++g;
+    return g;
+}
 
 struct __align__(8) Barriers {
     unsigned long long full[MAX_STAGES];
@@ -191,13 +205,15 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < p.Jout * p.taps; i += THREADS) idx_s[i] = p.idx[i];
-    int* omap_s = idx_s + 800;                            // <= 25 entries; Fourier layers use <= 25 idx entries as well
-    if (p.omap) for (int i = threadIdx.x; i < p.Jout * (p.Cout / p.ogroup); i += THREADS) omap_s[i] = p.omap[i];
+    for (int g = 0; g < p.ngroups; ++g) {
+        const TcGroup& G = p.grp[g];
+        for (int i = threadIdx.x; i < G.Jout * G.taps; i += THREADS) idx_s[G.idx_off + i] = G.idx[i];
+        if (G.omap) for (int i = threadIdx.x; i < G.Jout * (G.Cout / p.ogroup); i += THREADS) idx_s[G.omap_off + i] = G.omap[i];
+    }
     // bias / next-BN tables of all Cout (<= 512) channels; the group-Fourier layers (Cout up to 2560) carry no bias or
     // activation here (both are applied in the group domain by the transform kernel)
-    const bool has_ep = p.omap == nullptr;
-    for (int i = threadIdx.x; has_ep && i < p.Cout; i += THREADS) {
+    const bool has_ep = p.grp[0].omap == nullptr;
+    for (int i = threadIdx.x; has_ep && i < p.grp[0].Cout; i += THREADS) {
         ep_bias[i] = p.bias[i];
         ep_scale[i] = p.scale ? p.scale[i] : 1.f;
         ep_shift[i] = p.shift ? p.shift[i] : 0.f;
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = p.total_tiles;
 
     if (warp < 4) {
         // ================= A producers =================
@@ -242,21 +258,23 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         const int rsub = lane >> 3;
         uint32_t stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles;
+            const TcGroup& G = p.grp[find_group(p, tile)];
+            const int m_tile = (tile - G.tile_begin) / G.n_tiles;
+            const int* idx_g = idx_s + G.idx_off;
             int rowbase[8], rowj[8];
             uint32_t okmask = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = linemap ? warp * 32 + 4 * i + rsub : (int)threadIdx.x;
                 const int row = m_tile * BM + r;
-                const bool ok = row < p.m_total;
+                const bool ok = row < G.m_total;
                 const int rr = ok ? row : 0;
-                const int b = rr / p.Jout;
-                rowj[i] = (rr - b * p.Jout) * p.taps;
+                const int b = rr / G.Jout;
+                rowj[i] = (rr - b * G.Jout) * G.taps;
                 rowbase[i] = b * p.Jin;
                 okmask |= (ok ? 1u : 0u) << i;
             }
-            for (int kb = 0; kb < p.nkb; ++kb) {
+            for (int kb = 0; kb < G.nkb; ++kb) {
                 uint8_t* st_hi = stage_base + stage * STAGE_BYTES;
                 mbar_wait(&bars->empty[stage], phase ^ 1);
 #pragma unroll
@@ -267,9 +285,9 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                     const int kk0 = kb * BK + (int)ch * 8;
                     const int k = kk0 / p.Cin;
                     const int coff = kk0 - k * p.Cin;
-                    const bool tap_ok = k < p.taps;
+                    const bool tap_ok = k < G.taps;
                     const int r = linemap ? warp * 32 + 4 * i + rsub : (int)threadIdx.x;
-                    const size_t off = ((size_t)(rowbase[i] + idx_s[rowj[i] + (tap_ok ? k : 0)])) * p.Cin + coff;
+                    const size_t off = ((size_t)(rowbase[i] + idx_g[rowj[i] + (tap_ok ? k : 0)])) * p.Cin + coff;
                     uint8_t* dst = st_hi + r * 128 + ((ch ^ (uint32_t)(r & 7)) << 4);
                     const bool ok = tap_ok && ((okmask >> i) & 1u);
                     cp_async16(dst, p.a_hi + off, ok);
@@ -291,10 +309,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.n_tiles;
-                const uint8_t* wh = p.w_hi + (size_t)n_tile * p.nkb * W_TILE;
-                const uint8_t* wl = p.w_lo + (size_t)n_tile * p.nkb * W_TILE;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                const TcGroup& G = p.grp[find_group(p, tile)];
+                const int n_tile = (tile - G.tile_begin) % G.n_tiles;
+                const uint8_t* wh = G.w_hi + (size_t)n_tile * G.nkb * W_TILE;
+                const uint8_t* wl = G.w_lo + (size_t)n_tile * G.nkb * W_TILE;
+                for (int kb = 0; kb < G.nkb; ++kb) {
                     uint8_t* dst = stage_base + stage * STAGE_BYTES + 2 * A_TILE;
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     mbar_expect_tx(&bars->full[stage], 2 * W_TILE);
@@ -313,7 +332,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 const uint32_t d_lo = SPLIT ? d_tmem + BN : d_tmem;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                const int nkb = p.grp[find_group(p, tile)].nkb;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
                     if (p.flags & 1) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
                     tc_fence_after();
@@ -342,16 +362,18 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         const int half = (warp - 4) >> 2;
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles;
-            const int n_tile = tile - m_tile * p.n_tiles;
+            const TcGroup& G = p.grp[find_group(p, tile)];
+            const int m_tile = (tile - G.tile_begin) / G.n_tiles;
+            const int n_tile = (tile - G.tile_begin) - m_tile * G.n_tiles;
+            const int* omap_s = idx_s + G.omap_off;
             const int row = m_tile * BM + q * 32 + lane;
-            const bool ok = row < p.m_total;
+            const bool ok = row < G.m_total;
             const int n0 = n_tile * BN;
             const float* rres = nullptr;
             if (p.resid && ok) {
-                const int b = row / p.Jout;
-                const int j = row - b * p.Jout;
-                rres = p.resid + ((size_t)b * p.Jres + p.resid_off + (p.resid_per_j ? j : 0)) * p.Cout + n0;
+                const int b = row / G.Jout;
+                const int j = row - b * G.Jout;
+                rres = p.resid + ((size_t)b * p.Jres + p.resid_off + (p.resid_per_j ? j : 0)) * G.Cout + n0;
             }
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -387,13 +409,13 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                     }
                     // element offset of this lane's row at this chunk's first column
                     size_t blk;
-                    if (p.omap) {
+                    if (G.omap) {
                         const int n = n0 + cc * 32, grp = n / p.ogroup;
                         const int rr = ok ? row : 0;
-                        const int b = rr / p.Jout, j = rr - b * p.Jout;
-                        blk = ((size_t)b * p.out_J + omap_s[j * (p.Cout / p.ogroup) + grp]) * p.ogroup + (n - grp * p.ogroup);
+                        const int b = rr / G.Jout, j = rr - b * G.Jout;
+                        blk = ((size_t)b * p.out_J + omap_s[j * (G.Cout / p.ogroup) + grp]) * p.ogroup + (n - grp * p.ogroup);
                     } else {
-                        blk = (size_t)(ok ? row : 0) * p.Cout + n0 + cc * 32;
+                        blk = (size_t)(ok ? row : 0) * G.Cout + n0 + cc * 32;
                     }
                     if (p.out_raw) {
 #pragma unroll
@@ -547,35 +569,71 @@ template <int BN, bool SPLIT>
 static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
     // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
     YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, SPLIT>::SMEM_BYTES));
-    p.n_tiles = p.Cout / BN;
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    const int grid = p.total_tiles < ctx->num_sms ? p.total_tiles : ctx->num_sms;
     gconv_tc_kernel<BN, SPLIT><<<grid, THREADS, Cfg<BN, SPLIT>::SMEM_BYTES, st>>>(p);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
 }
 
-int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
-    YARG(gconv_tc_eligible(L, a));
-    YARG(a.omap ? (!a.out_act && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0) : L.cout <= 512);
-    TcArgs p;
+static void tc_fill_common(TcArgs& p, const GLayer& L, const GConvArgs& a, yoho_ctx* ctx) {
     p.a_hi = (const __nv_bfloat16*)a.act_hi; p.a_lo = (const __nv_bfloat16*)a.act_lo;
-    p.w_hi = (const uint8_t*)L.w_hi; p.w_lo = (const uint8_t*)L.w_lo;
-    p.bias = L.bias; p.idx = a.idx;
-    p.Jin = a.Jin; p.Jout = a.Jout; p.Cin = L.cin; p.Cout = L.cout; p.taps = L.taps;
-    p.m_total = a.B * a.Jout; p.m_tiles = (p.m_total + BM - 1) / BM;
-    p.nkb = (L.taps * L.cin + BK - 1) / BK;
+    p.bias = L.bias;
+    p.Jin = a.Jin; p.Cin = L.cin;
     p.resid = a.resid; p.Jres = a.Jres; p.resid_off = a.resid_off; p.resid_per_j = a.resid_per_j;
     p.out_raw = a.out_raw; p.out_act = a.out_act;
     p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
     p.scale = a.scale; p.shift = a.shift;
     p.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
     p.flags = ctx->tc_flags;
-    p.omap = a.omap; p.ogroup = a.omap ? a.ogroup : L.cout; p.out_J = a.out_J;
-    // split accumulators only where the accumulation chain is long; short-K layers (PartI layers 1 and 4) keep two
-    // accumulator buffers in flight so that their (relatively heavy) epilogue overlaps the next tile's MMAs
-    const bool split = ctx->gconv_impl >= 2 && p.nkb >= 16 && !a.omap;     // Fourier layers: chains are short, keep overlap
-    if (tc_tile_n(L) == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
+    p.ogroup = a.omap ? a.ogroup : L.cout; p.out_J = a.out_J;
+}
+
+static void tc_fill_group(TcGroup& G, const GLayer& L, const GConvArgs& a, int bn, int tile_begin, int idx_off, int omap_off) {
+    G.w_hi = (const uint8_t*)L.w_hi; G.w_lo = (const uint8_t*)L.w_lo;
+    G.idx = a.idx; G.omap = a.omap;
+    G.Jout = a.Jout; G.taps = L.taps; G.Cout = L.cout;
+    G.nkb = (L.taps * L.cin + BK - 1) / BK;
+    G.m_total = a.B * a.Jout;
+    G.n_tiles = L.cout / bn;
+    G.tile_begin = tile_begin; G.idx_off = idx_off; G.omap_off = omap_off;
+}
+
+int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
+    YARG(gconv_tc_eligible(L, a));
+    YARG(a.omap ? (!a.out_act && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0) : L.cout <= 512);
+    TcArgs p;
+    tc_fill_common(p, L, a, ctx);
+    const int bn = tc_tile_n(L);
+    p.ngroups = 1;
+    tc_fill_group(p.grp[0], L, a, bn, 0, 0, 800);       // <= 25 omap entries behind the (<= 780-entry) index table
+    p.total_tiles = ((p.grp[0].m_total + BM - 1) / BM) * p.grp[0].n_tiles;
+    // split accumulators only where the accumulation chain is long; short-K layers (PartI layers 1 and 4, the group-Fourier
+    // GEMMs) keep two accumulator buffers in flight so that their (relatively heavy) epilogue overlaps the next tile's MMAs
+    const bool split = ctx->gconv_impl >= 2 && p.grp[0].nkb >= 16 && !a.omap;
+    if (bn == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
     return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);
+}
+
+// The per-irrep GEMMs of one group-Fourier layer as ONE persistent launch: n GEMMs over the same activation tensor
+// (coefficient rows selected by each irrep's idx table) writing disjoint coefficient rows of the same output.
+// Groups are visited in the given order; pass the largest first so the tail of the launch is made of short tiles.
+int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st) {
+    YARG(n >= 1 && n <= MAX_GROUPS);
+    TcArgs p;
+    tc_fill_common(p, *Ls[0], as[0], ctx);
+    p.ngroups = n;
+    p.n_valid = 1 << 30;          // every group writes all of its columns
+    int tiles = 0;
+    for (int g = 0; g < n; ++g) {
+        const GLayer& L = *Ls[g];
+        const GConvArgs& a = as[g];
+        YARG(gconv_tc_eligible(L, a) && tc_tile_n(L) == 256 && a.omap && !a.out_act && !a.resid);
+        YARG(L.cin == Ls[0]->cin && a.ogroup == as[0].ogroup && a.act_hi == as[0].act_hi && a.out_hi == as[0].out_hi &&
+             a.out_raw == as[0].out_raw && a.B == as[0].B && a.Jin == as[0].Jin && L.cout % a.ogroup == 0);
+        tc_fill_group(p.grp[g], L, a, 256, tiles, g * 32, 160 + g * 32);
+        tiles += ((p.grp[g].m_total + BM - 1) / BM) * p.grp[g].n_tiles;
+    }
+    p.total_tiles = tiles;
+    return tc_launch<256, false>(ctx, p, st);
 }

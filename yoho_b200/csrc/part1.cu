@@ -16,6 +16,7 @@ int group_transform(yoho_ctx* ctx, const float* in, int B, int C, const float* m
 int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                         const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                         void* out_hi, void* out_lo, cudaStream_t st);
+int gconv_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st);
 void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st);
 void yoho_prof_end(yoho_ctx* ctx, cudaStream_t st);
 
@@ -212,24 +213,33 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             yoho_prof_end(ctx, st);
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
-            for (int r = 0; r < ctx->nf; ++r) {
+            const bool grouped = (ctx->tc_flags & 16) == 0 && ctx->nf <= 5;   // all irreps of a layer in one persistent launch
+            GConvArgs fs[8];
+            const GLayer* Ls[8];
+            for (int q = 0; q < ctx->nf; ++q) {
+                const int r = ctx->nf - 1 - q;                               // largest irrep first: short tiles make up the tail
                 f.act_hi = X1h; f.act_lo = X1l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
                 f.omap = ctx->d_fomap[r]; f.ogroup = 512;
                 if (xmma) { f.out_raw = nullptr; f.out_hi = Y2h; f.out_lo = Y2l; } else { f.out_raw = Y2; f.out_hi = f.out_lo = nullptr; }
-                if (int rc = gconv_forward(ctx, ctx->p1f_a[r], f, st)) return rc;
+                fs[q] = f; Ls[q] = &ctx->p1f_a[r];
+                if (!grouped) { if (int rc = gconv_forward(ctx, ctx->p1f_a[r], f, st)) return rc; }
             }
+            if (grouped) { if (int rc = gconv_forward_grouped(ctx, Ls, fs, ctx->nf, st)) return rc; }
             yoho_prof_begin(ctx, 8, 2.0 * n * 512 * 7200.0, st);
             if (int rc = xmma ? group_transform_mma(ctx, Y2h, Y2l, n, 512, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_a.bias, nullptr,
                                                     ctx->p1_bn_b.scale, ctx->p1_bn_b.shift, X2h, X2l, st)
                               : group_transform(ctx, Y2, n, 512, ctx->d_Fm2g, ctx->d_Fg2m, ctx->p1_a.bias, nullptr, ctx->p1_bn_b.scale,
                                                 ctx->p1_bn_b.shift, X2h, X2l, nullptr, st)) return rc;
             yoho_prof_end(ctx, st);
-            for (int r = 0; r < ctx->nf; ++r) {
+            for (int q = 0; q < ctx->nf; ++q) {
+                const int r = ctx->nf - 1 - q;
                 f.act_hi = X2h; f.act_lo = X2l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
                 f.omap = ctx->d_fomap[r]; f.ogroup = 256;
                 if (xmma) { f.out_raw = nullptr; f.out_hi = Y3h; f.out_lo = Y3l; } else { f.out_raw = Y3; f.out_hi = f.out_lo = nullptr; }
-                if (int rc = gconv_forward(ctx, ctx->p1f_b[r], f, st)) return rc;
+                fs[q] = f; Ls[q] = &ctx->p1f_b[r];
+                if (!grouped) { if (int rc = gconv_forward(ctx, ctx->p1f_b[r], f, st)) return rc; }
             }
+            if (grouped) { if (int rc = gconv_forward_grouped(ctx, Ls, fs, ctx->nf, st)) return rc; }
             yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
             if (int rc = xmma ? group_transform_mma(ctx, Y3h, Y3l, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, nullptr, nullptr, ctx->p1_b.bias, y1,
                                                     ctx->p1_bn_out.scale, ctx->p1_bn_out.shift, a3_hi, a3_lo, st)
