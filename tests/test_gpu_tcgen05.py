@@ -151,7 +151,8 @@ def test_part2_tc_realckpt(engine, tables, impl):
 
 
 def test_fourier_transform_kernels_agree(engine, tables):
-    """The warp-MMA transform kernel (default) against its FP32 SIMT twin (tuning flag 4), through the whole PartI."""
+    """The warp-autonomous MMA transform kernel (default) against its FP32 SIMT twin (tuning flag 4) and the two block-tiled
+    MMA variants (flags 8, 32), through the whole PartI."""
     _, _, N = tables
     sd = synth.synth_state_dict("PartI", 2)
     engine.load_part1(sd)
@@ -162,8 +163,10 @@ def test_fourier_transform_kernels_agree(engine, tables):
         a = engine.part1(x)
         engine.set_tuning(0, 3 | 4)
         b = engine.part1(x)
-        engine.set_tuning(0, 3 | 8)          # 128-channel transform tiles: same arithmetic, different tiling
+        engine.set_tuning(0, 3 | 8)          # 128-channel block-tiled transform: same arithmetic, different tiling
         c = engine.part1(x)
+        engine.set_tuning(0, 3 | 32)         # 64-channel block-tiled transform
+        c2 = engine.part1(x)
         engine.set_tuning(0, 3 | 16)         # one launch per irrep instead of the grouped launch
         d = engine.part1(x)
         torch.cuda.synchronize()
@@ -175,4 +178,4 @@ def test_fourier_transform_kernels_agree(engine, tables):
     e1, _ = _report("fourier mma-xf vs oracle", _np(a["eqv"]), ref["eqv"].numpy())
     e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
     assert e1 <= DESC_TOL and e2 <= DESC_TOL
-    assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], d["eqv"])
+    assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], c2["eqv"]) and torch.equal(a["eqv"], d["eqv"])

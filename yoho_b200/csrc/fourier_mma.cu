@@ -39,10 +39,13 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 __device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    // two values -> packed bf16x2 hi and lo parts (first value in the low half) with the paired conversion instruction
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hu << 16), hb = __uint_as_float(hu & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+    return hu;
 }
 
 // Persistent: one CTA per SM loops over (keypoint, 128-channel) tiles.  The FP32 input tile (and the shortcut tile, if any) of
@@ -222,6 +225,188 @@ __global__ void __launch_bounds__(XT, XC == 128 ? 1 : 2) group_transform_mma_ker
     cp_async_wait<0>();
 }
 
+
+// ---- warp-autonomous variant (default) ------------------------------------------------------------------------------------
+// Each warp owns a (keypoint, 32-channel) tile end to end: it streams its own [60][32] hi/lo columns with cp.async (double
+// buffered), holds all 64 output rows in registers (4 m-tiles x 4 n-tiles), hands the intermediate tile to its second product
+// through its private shared-memory buffer and writes the result back itself.  No block-wide barrier in the main loop; the
+// transform matrices are the only shared state.  Per k-step a warp issues 12 ldmatrix for 48 mma (the block-tiled kernel
+// above: 16 for 24), which is what the shared-memory pipe needed.  Accumulation order per output element is the same as in
+// the block-tiled kernel, so the two produce identical bits.
+constexpr int WC = 32;                       // channels per warp tile
+constexpr int WP = WC + 8;                   // padded row length (bf16): 80 B, conflict-free ldmatrix / stmatrix
+constexpr int VW = 8;                        // warps per CTA (one CTA per SM)
+constexpr int WBUF = 64 * WP;                // elements of one [64][WP] operand tile
+
+__device__ __forceinline__ void stsm_x4(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};\n" :: "r"(smem_u32(p)), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+__device__ __forceinline__ void warp_stage(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const unsigned short* hi, const unsigned short* lo, int C, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = lane + 32 * j;
+        if (i < YG * 4) {
+            const int k = i >> 2, q = i & 3;
+            cp_async16(dst_hi + k * WP + q * 8, hi + (size_t)k * C + q * 8, true);
+            cp_async16(dst_lo + k * WP + q * 8, lo + (size_t)k * C + q * 8, true);
+        }
+    }
+}
+
+// acc[mt][nt][4] = M^T (64 rows) x data (64 k x 32 channels), 3 split products, same order as warp_product32
+__device__ __forceinline__ void warp_product_full(const __nv_bfloat16* mh, const __nv_bfloat16* ml, const __nv_bfloat16* xh,
+                                                  const __nv_bfloat16* xl, int lane, float (&acc)[4][4][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    const int arow = lane & 15, acol = (lane >> 4) * 8;
+    const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            const int off = (ks * 16 + brow) * WP + np * 16 + bcol;
+            ldsm_x4_t(bh[np], xh + off);
+            ldsm_x4_t(bl[np], xl + off);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            uint32_t ah[4], al[4];
+            ldsm_x4(ah, mh + (mt * 16 + arow) * MP + ks * 16 + acol);
+            ldsm_x4(al, ml + (mt * 16 + arow) * MP + ks * 16 + acol);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                mma16816(acc[mt][2 * np], ah, bh[np][0], bh[np][1]);
+                mma16816(acc[mt][2 * np], al, bh[np][0], bh[np][1]);
+                mma16816(acc[mt][2 * np], ah, bl[np][0], bl[np][1]);
+                mma16816(acc[mt][2 * np + 1], ah, bh[np][2], bh[np][3]);
+                mma16816(acc[mt][2 * np + 1], al, bh[np][2], bh[np][3]);
+                mma16816(acc[mt][2 * np + 1], ah, bl[np][2], bl[np][3]);
+            }
+        }
+    }
+}
+
+// accumulators -> bf16 hi/lo [64][WP] tiles (rows >= 60 are written as zeros by the caller's masking)
+__device__ __forceinline__ void warp_store_tiles(__nv_bfloat16* th, __nv_bfloat16* tl, int lane, const float (&acc)[4][4][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) h[nt] = pack_hi_lo(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1], l[nt]);
+            const int o = (mt * 16 + hf * 8 + (lane & 7)) * WP + (lane >> 3) * 8;   // lane -> row (lane&7) of matrix (lane>>3) = n-tile
+            stsm_x4(th + o, h[0], h[1], h[2], h[3]);
+            stsm_x4(tl + o, l[0], l[1], l[2], l[3]);
+        }
+}
+
+__global__ void __launch_bounds__(VW * 32, 1) group_transform_warp_kernel(const XmArgs p) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    __nv_bfloat16* m1h = (__nv_bfloat16*)smraw;          // [64][MP]
+    __nv_bfloat16* m1l = m1h + 64 * MP;
+    __nv_bfloat16* m2h = m1l + 64 * MP;
+    __nv_bfloat16* m2l = m2h + 64 * MP;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __nv_bfloat16* wbuf = m2l + 64 * MP + (size_t)warp * 4 * WBUF;   // this warp's 2 x {hi, lo} x [64][WP]
+    for (int i = t; i < 64 * 8; i += VW * 32) {
+        const int r = i >> 3, q = i & 7;
+        *reinterpret_cast<uint4*>(m1h + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_hi)[i];
+        *reinterpret_cast<uint4*>(m1l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_lo)[i];
+        if (p.m2_hi) {
+            *reinterpret_cast<uint4*>(m2h + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m2_hi)[i];
+            *reinterpret_cast<uint4*>(m2l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m2_lo)[i];
+        }
+    }
+    for (int i = lane; i < 4 * 4 * WP; i += 32)          // rows 60..63 of the four operand tiles stay zero
+        wbuf[(i / (4 * WP)) * WBUF + YG * WP + i % (4 * WP)] = __float2bfloat16_rn(0.f);
+    __syncthreads();
+    const int cblocks = p.C / WC;
+    const long long tiles = (long long)p.B * cblocks;
+    const long long stride = (long long)gridDim.x * VW;
+    long long tile = (long long)blockIdx.x * VW + warp;
+    if (tile < tiles) {
+        const int b = (int)(tile / cblocks), cb = (int)(tile - (long long)b * cblocks) * WC;
+        const size_t o = (size_t)b * YG * p.C + cb;
+        warp_stage(wbuf, wbuf + WBUF, p.in_hi + o, p.in_lo + o, p.C, lane);
+    }
+    cp_async_commit();
+    const int r0 = lane >> 2, cq = 2 * (lane & 3);
+    for (int it = 0; tile < tiles; tile += stride, ++it) {
+        const int b = (int)(tile / cblocks), cb = (int)(tile - (long long)b * cblocks) * WC;
+        __nv_bfloat16* xh = wbuf + (it & 1) * 2 * WBUF;
+        __nv_bfloat16* xl = xh + WBUF;
+        const long long nxt = tile + stride;
+        if (nxt < tiles) {
+            const int nb = (int)(nxt / cblocks), ncb = (int)(nxt - (long long)nb * cblocks) * WC;
+            const size_t o = (size_t)nb * YG * p.C + ncb;
+            __nv_bfloat16* nx = wbuf + ((it + 1) & 1) * 2 * WBUF;
+            warp_stage(nx, nx + WBUF, p.in_hi + o, p.in_lo + o, p.C, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        float acc[4][4][4];
+        warp_product_full(m1h, m1l, xh, xl, lane, acc);
+        // pointwise stage on the accumulators: row m = mt*16 + r0 + 8*hf, channel cb + nt*8 + cq + {0,1}
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c = cb + nt * 8 + cq;
+            float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
+            if (p.bias) { b0 = __ldg(p.bias + c); b1 = __ldg(p.bias + c + 1); }
+            if (p.scale) { s0 = __ldg(p.scale + c); s1 = __ldg(p.scale + c + 1); h0 = __ldg(p.shift + c); h1 = __ldg(p.shift + c + 1); }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int m = mt * 16 + r0 + 8 * hf;
+                    float v0 = acc[mt][nt][2 * hf] + b0, v1 = acc[mt][nt][2 * hf + 1] + b1;
+                    if (p.resid && m < YG) {
+                        const float2 rr = __ldg(reinterpret_cast<const float2*>(p.resid + ((size_t)b * YG + m) * p.C + c));
+                        v0 += rr.x; v1 += rr.y;
+                    }
+                    if (p.scale) { v0 = fmaxf(fmaf(v0, s0, h0), 0.f); v1 = fmaxf(fmaf(v1, s1, h1), 0.f); }
+                    if (m >= YG) { v0 = 0.f; v1 = 0.f; }
+                    acc[mt][nt][2 * hf] = v0; acc[mt][nt][2 * hf + 1] = v1;
+                }
+        }
+        __syncwarp();                                      // every lane is done reading xh/xl
+        if (p.m2_hi) {
+            warp_store_tiles(xh, xl, lane, acc);           // intermediate tile (rows 60..63 = 0) in place of the input
+            __syncwarp();
+            warp_product_full(m2h, m2l, xh, xl, lane, acc);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+                    if (48 + r0 + 8 * hf >= YG) { acc[3][nt][2 * hf] = 0.f; acc[3][nt][2 * hf + 1] = 0.f; }
+            __syncwarp();
+        }
+        warp_store_tiles(xh, xl, lane, acc);               // result staging (rows 60..63 stay zero)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                      // 8 rows x 64 B per instruction, full sectors
+            const int i = lane + 32 * j;
+            if (i < YG * 4) {
+                const int m = i >> 2, q = i & 3;
+                const size_t o = ((size_t)b * YG + m) * p.C + cb + q * 8;
+                *reinterpret_cast<uint4*>(p.out_hi + o) = *reinterpret_cast<const uint4*>(xh + m * WP + q * 8);
+                *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(xl + m * WP + q * 8);
+            }
+        }
+        __syncwarp();                                      // before this buffer is refilled (next iteration's prefetch goes to the other one)
+    }
+    cp_async_wait<0>();
+}
+
+constexpr size_t xw_smem() { return (size_t)(4 * 64 * MP + VW * 4 * WBUF) * sizeof(__nv_bfloat16); }
+
 template <int XC>
 constexpr size_t xm_smem() { return (size_t)(4 * 64 * MP + 6 * 64 * (XC + 8)) * sizeof(__nv_bfloat16) + (size_t)YG * XC * sizeof(float); }
 
@@ -233,11 +418,16 @@ int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int
     YARG(C % 128 == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
     XmArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
              bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
-    if (ctx->tc_flags & 8) {      // 128-channel tiles, one CTA per SM
+    if ((ctx->tc_flags & (8 | 32)) == 0) {   // default: warp-autonomous 32-channel tiles, one 8-warp CTA per SM
+        YCHECK(cudaFuncSetAttribute(group_transform_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xw_smem()));
+        const long long tiles = (long long)B * (C / WC);
+        const long long ctas = (tiles + VW - 1) / VW;
+        group_transform_warp_kernel<<<(int)(ctas < ctx->num_sms ? ctas : ctx->num_sms), VW * 32, xw_smem(), st>>>(p);
+    } else if (ctx->tc_flags & 8) {      // 128-channel block tiles, one CTA per SM
         YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem<128>()));
         const int tiles = B * (C / 128);
         group_transform_mma_kernel<128><<<tiles < ctx->num_sms ? tiles : ctx->num_sms, XT, xm_smem<128>(), st>>>(p);
-    } else {                      // 64-channel tiles, two CTAs per SM (default): the barriers of one tile hide behind the other
+    } else {                      // flag 32: 64-channel block tiles, two CTAs per SM
         YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem<64>()));
         const int tiles = B * (C / 64);
         const int cap = 2 * ctx->num_sms;
