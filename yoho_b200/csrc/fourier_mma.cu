@@ -33,7 +33,7 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -279,13 +279,21 @@ __device__ __forceinline__ void warp_product_full(const __nv_bfloat16* mh, const
             uint32_t ah[4], al[4];
             ldsm_x4(ah, mh + (mt * 16 + arow) * MP + ks * 16 + acol);
             ldsm_x4(al, ml + (mt * 16 + arow) * MP + ks * 16 + acol);
+            // the three products of one accumulator are issued four MMAs apart (same per-accumulator order: hh, lh, hl), so
+            // consecutive tensor instructions are independent
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
                 mma16816(acc[mt][2 * np], ah, bh[np][0], bh[np][1]);
-                mma16816(acc[mt][2 * np], al, bh[np][0], bh[np][1]);
-                mma16816(acc[mt][2 * np], ah, bl[np][0], bl[np][1]);
                 mma16816(acc[mt][2 * np + 1], ah, bh[np][2], bh[np][3]);
+            }
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                mma16816(acc[mt][2 * np], al, bh[np][0], bh[np][1]);
                 mma16816(acc[mt][2 * np + 1], al, bh[np][2], bh[np][3]);
+            }
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                mma16816(acc[mt][2 * np], ah, bl[np][0], bl[np][1]);
                 mma16816(acc[mt][2 * np + 1], ah, bl[np][2], bl[np][3]);
             }
         }
