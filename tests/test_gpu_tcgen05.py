@@ -169,6 +169,10 @@ def test_fourier_transform_kernels_agree(engine, tables):
         c2 = engine.part1(x)
         engine.set_tuning(0, 3 | 16)         # one launch per irrep instead of the grouped launch
         d = engine.part1(x)
+        engine.set_tuning(0, 3 | 64)         # 16 single-buffered warps per CTA
+        e = engine.part1(x)
+        engine.set_tuning(0, 3 | 128)        # 12 single-buffered warps per CTA
+        f = engine.part1(x)
         torch.cuda.synchronize()
     finally:
         engine.set_tuning(0, 3)
@@ -179,3 +183,4 @@ def test_fourier_transform_kernels_agree(engine, tables):
     e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
     assert e1 <= DESC_TOL and e2 <= DESC_TOL
     assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], c2["eqv"]) and torch.equal(a["eqv"], d["eqv"])
+    assert torch.equal(a["eqv"], e["eqv"]) and torch.equal(a["eqv"], f["eqv"])

@@ -235,7 +235,6 @@ __global__ void __launch_bounds__(XT, XC == 128 ? 1 : 2) group_transform_mma_ker
 // the block-tiled kernel, so the two produce identical bits.
 constexpr int WC = 32;                       // channels per warp tile
 constexpr int WP = WC + 8;                   // padded row length (bf16): 80 B, conflict-free ldmatrix / stmatrix
-constexpr int VW = 8;                        // warps per CTA (one CTA per SM)
 constexpr int WBUF = 64 * WP;                // elements of one [64][WP] operand tile
 
 __device__ __forceinline__ void stsm_x4(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
@@ -315,6 +314,9 @@ __device__ __forceinline__ void warp_store_tiles(__nv_bfloat16* th, __nv_bfloat1
         }
 }
 
+// VW warps per CTA (one CTA per SM), NBUF input buffers per warp: <8,2> prefetches the next tile while computing (248 registers),
+// <16,1> trades the prefetch for twice the warps (128 registers) and lets the other warps of the scheduler hide the load.
+template <int VW, int NBUF>
 __global__ void __launch_bounds__(VW * 32, 1) group_transform_warp_kernel(const XmArgs p) {
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* m1h = (__nv_bfloat16*)smraw;          // [64][MP]
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(VW * 32, 1) group_transform_warp_kernel(const 
     __nv_bfloat16* m2h = m1l + 64 * MP;
     __nv_bfloat16* m2l = m2h + 64 * MP;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    __nv_bfloat16* wbuf = m2l + 64 * MP + (size_t)warp * 4 * WBUF;   // this warp's 2 x {hi, lo} x [64][WP]
+    __nv_bfloat16* wbuf = m2l + 64 * MP + (size_t)warp * NBUF * 2 * WBUF;   // this warp's NBUF x {hi, lo} x [64][WP]
     for (int i = t; i < 64 * 8; i += VW * 32) {
         const int r = i >> 3, q = i & 7;
         *reinterpret_cast<uint4*>(m1h + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m1_hi)[i];
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(VW * 32, 1) group_transform_warp_kernel(const 
             *reinterpret_cast<uint4*>(m2l + r * MP + q * 8) = reinterpret_cast<const uint4*>(p.m2_lo)[i];
         }
     }
-    for (int i = lane; i < 4 * 4 * WP; i += 32)          // rows 60..63 of the four operand tiles stay zero
+    for (int i = lane; i < NBUF * 2 * 4 * WP; i += 32)   // rows 60..63 of the operand tiles stay zero
         wbuf[(i / (4 * WP)) * WBUF + YG * WP + i % (4 * WP)] = __float2bfloat16_rn(0.f);
     __syncthreads();
     const int cblocks = p.C / WC;
@@ -348,17 +350,21 @@ __global__ void __launch_bounds__(VW * 32, 1) group_transform_warp_kernel(const 
     const int r0 = lane >> 2, cq = 2 * (lane & 3);
     for (int it = 0; tile < tiles; tile += stride, ++it) {
         const int b = (int)(tile / cblocks), cb = (int)(tile - (long long)b * cblocks) * WC;
-        __nv_bfloat16* xh = wbuf + (it & 1) * 2 * WBUF;
+        __nv_bfloat16* xh = wbuf + (NBUF == 2 ? (it & 1) : 0) * 2 * WBUF;
         __nv_bfloat16* xl = xh + WBUF;
         const long long nxt = tile + stride;
-        if (nxt < tiles) {
-            const int nb = (int)(nxt / cblocks), ncb = (int)(nxt - (long long)nb * cblocks) * WC;
-            const size_t o = (size_t)nb * YG * p.C + ncb;
-            __nv_bfloat16* nx = wbuf + ((it + 1) & 1) * 2 * WBUF;
-            warp_stage(nx, nx + WBUF, p.in_hi + o, p.in_lo + o, p.C, lane);
+        if (NBUF == 2) {
+            if (nxt < tiles) {
+                const int nb = (int)(nxt / cblocks), ncb = (int)(nxt - (long long)nb * cblocks) * WC;
+                const size_t o = (size_t)nb * YG * p.C + ncb;
+                __nv_bfloat16* nx = wbuf + ((it + 1) & 1) * 2 * WBUF;
+                warp_stage(nx, nx + WBUF, p.in_hi + o, p.in_lo + o, p.C, lane);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        cp_async_commit();
-        cp_async_wait<1>();
         __syncwarp();
         float acc[4][4][4];
         warp_product_full(m1h, m1l, xh, xl, lane, acc);
@@ -408,12 +414,30 @@ __global__ void __launch_bounds__(VW * 32, 1) group_transform_warp_kernel(const 
                 *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(xl + m * WP + q * 8);
             }
         }
-        __syncwarp();                                      // before this buffer is refilled (next iteration's prefetch goes to the other one)
+        __syncwarp();                                      // before this buffer is refilled
+        if (NBUF == 1) {
+            if (nxt < tiles) {
+                const int nb = (int)(nxt / cblocks), ncb = (int)(nxt - (long long)nb * cblocks) * WC;
+                const size_t o = (size_t)nb * YG * p.C + ncb;
+                warp_stage(xh, xl, p.in_hi + o, p.in_lo + o, p.C, lane);
+            }
+            cp_async_commit();
+        }
     }
     cp_async_wait<0>();
 }
 
-constexpr size_t xw_smem() { return (size_t)(4 * 64 * MP + VW * 4 * WBUF) * sizeof(__nv_bfloat16); }
+template <int VW, int NBUF>
+constexpr size_t xw_smem() { return (size_t)(4 * 64 * MP + VW * NBUF * 2 * WBUF) * sizeof(__nv_bfloat16); }
+
+template <int VW, int NBUF>
+int launch_warp_kernel(yoho_ctx* ctx, const XmArgs& p, cudaStream_t st) {
+    YCHECK(cudaFuncSetAttribute(group_transform_warp_kernel<VW, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xw_smem<VW, NBUF>()));
+    const long long tiles = (long long)p.B * (p.C / WC);
+    const long long ctas = (tiles + VW - 1) / VW;
+    group_transform_warp_kernel<VW, NBUF><<<(int)(ctas < ctx->num_sms ? ctas : ctx->num_sms), VW * 32, xw_smem<VW, NBUF>(), st>>>(p);
+    return YOHO_OK;
+}
 
 template <int XC>
 constexpr size_t xm_smem() { return (size_t)(4 * 64 * MP + 6 * 64 * (XC + 8)) * sizeof(__nv_bfloat16) + (size_t)YG * XC * sizeof(float); }
@@ -426,11 +450,9 @@ int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int
     YARG(C % 128 == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
     XmArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
              bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
-    if ((ctx->tc_flags & (8 | 32)) == 0) {   // default: warp-autonomous 32-channel tiles, one 8-warp CTA per SM
-        YCHECK(cudaFuncSetAttribute(group_transform_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xw_smem()));
-        const long long tiles = (long long)B * (C / WC);
-        const long long ctas = (tiles + VW - 1) / VW;
-        group_transform_warp_kernel<<<(int)(ctas < ctx->num_sms ? ctas : ctx->num_sms), VW * 32, xw_smem(), st>>>(p);
+    if ((ctx->tc_flags & (8 | 32)) == 0) {   // default: warp-autonomous 32-channel tiles, one CTA per SM
+        if (int rc = (ctx->tc_flags & 64) ? launch_warp_kernel<16, 1>(ctx, p, st) : (ctx->tc_flags & 128) ? launch_warp_kernel<12, 1>(ctx, p, st)
+                                                                                  : launch_warp_kernel<8, 2>(ctx, p, st)) return rc;
     } else if (ctx->tc_flags & 8) {      // 128-channel block tiles, one CTA per SM
         YCHECK(cudaFuncSetAttribute(group_transform_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem<128>()));
         const int tiles = B * (C / 128);
