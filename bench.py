@@ -264,7 +264,8 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            ent = json.load(open(tp)).get(eng.impl_name)
+            traffic = ent.get("dram_bytes_per_launch") if ent else None
         except Exception:
             traffic = None
     gconv_ms = sum(p["ms"] for p in prof)
