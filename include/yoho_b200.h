@@ -196,6 +196,23 @@ int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, int M, const
 int yoho_lift_group_features(yoho_ctx* ctx, const double* kps, int K, const float* pts, const float* feats,
                              const int32_t* offsets, float* out, int64_t* nn_out, void* stream);
 
+/* "Next" row — evaluation metrics on the device.
+ * yoho_fmr_batch replaces the per-pair body of Evaluator_PartI.Feature_match_Recall (tests/evaluator.py:57-66; also
+ * utils/utils.py:221-228 evaluate_the_match): keys0/keys1 float64 [Mtot,3] are the MATCHED keypoints of all pairs,
+ * concatenated; pair p owns rows offsets[p]..offsets[p+1]-1 (DEVICE int64[n_pairs+1]); gt float64 [n_pairs,4,4] (R|t with
+ * R @ keys1 + t = keys0; pass a 3x4 ground truth with the row 0 0 0 1); counts int32[n_pairs] = number of matches with
+ * ||keys0 - gt(keys1)|| < threshold.  The pair ratio is counts/M and FMR = mean(ratio > fmr_ratio) (host, exact). */
+int yoho_fmr_batch(yoho_ctx* ctx, const double* keys0, const double* keys1, const int64_t* offsets, const double* gt,
+                   int n_pairs, double threshold, int32_t* counts, void* stream);
+
+/* Replaces the numeric body of utils/RR_cal.py evaluate_registration / benchmark for aligned lists of n pairs:
+ * est, gt float64 [n,4,4]; info float64 [n,6,6] (needed only for p).  Outputs (each may be NULL): p[n] = the Redwood error
+ * computeTransformationErr(inv(gt) @ est, info) BEFORE the square root (RR_cal.py:48-65,273,289; nibabel mat2quat's
+ * largest-eigenvector quaternion); rre_deg[n] = rotation_error(gt_R, est_R) in degrees with the reference's float32 pi
+ * (RR_cal.py:13-33); rte[n] = translation_error (RR_cal.py:35-46).  A singular gt gives p = NaN. */
+int yoho_registration_errors(yoho_ctx* ctx, const double* est, const double* gt, const double* info, int n, double* p,
+                             double* rre_deg, double* rte, void* stream);
+
 /* Launch accounting for bench.py's "gpu_launches": kernels launched by this context since creation. */
 int64_t yoho_launch_count(const yoho_ctx* ctx);
 

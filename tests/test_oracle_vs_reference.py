@@ -78,3 +78,34 @@ def test_part2_and_transforms(ref, tables):
         t = kA[i] - kB[i] @ Rm.T
         T = O.part2_transforms(want[i:i + 1], pre[i:i + 1], kA[i:i + 1], kB[i:i + 1], R)[0]
         assert np.array_equal(T[:, :3], Rm) and np.array_equal(T[:, 3], t)
+
+
+def test_metrics_against_reference(ref):
+    """the metrics oracle against the reference's utils/RR_cal.py and utils/utils.py on seeds the golden file
+    does not use (nibabel's mat2quat is supplied by the oracle's restatement: the package is not installed here)."""
+    import sys
+    import importlib
+    import metrics_oracle as MO
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_metrics as G
+    sys.modules["nibabel.quaternions"].mat2quat = MO.mat2quat
+    sys.modules["nibabel"].quaternions = sys.modules["nibabel.quaternions"]
+    RR = importlib.import_module("utils.RR_cal")
+    for seed, noncons in ((101, True), (102, False), (103, True)):
+        n_frag, est, est_pairs, gt_pairs, gt, info = G.make_scene(seed, n_frag=9)
+        want = RR.evaluate_registration(n_frag, est, est_pairs, gt_pairs, gt, info, err2=0.2, nonconsecutive=noncons)
+        got = MO.evaluate_registration(n_frag, est, est_pairs, gt_pairs, gt, info, err2=0.2, nonconsecutive=noncons)
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
+        assert np.array_equal(np.array(got[3]), np.array(want[3]))
+        m = min(len(est), len(gt))
+        re = RR.rotation_error(torch.from_numpy(gt[:m, :3, :3]), torch.from_numpy(est[:m, :3, :3])).numpy()
+        te = RR.translation_error(torch.from_numpy(gt[:m, :3, 3:4]), torch.from_numpy(est[:m, :3, 3:4])).numpy()
+        assert np.allclose(MO.rotation_error(gt[:m, :3, :3], est[:m, :3, :3]), re, rtol=1e-12, atol=1e-10)
+        assert np.allclose(MO.translation_error(gt[:m, :3, 3:4], est[:m, :3, 3:4]), te, rtol=1e-13, atol=0)
+    rs = np.random.RandomState(9)
+    k0, k1 = rs.uniform(0, 3, (200, 3)), rs.uniform(0, 3, (210, 3))
+    mt = np.stack([rs.randint(0, 200, 120), rs.randint(0, 210, 120)], 1)
+    T = G.rand_rigid(rs)
+    k0[mt[:40, 0]] = k1[mt[:40, 1]] @ T[:3, :3].T + T[:3, 3] + rs.standard_normal((40, 3)) * 0.05
+    for gtm in (T, T[:3]):
+        assert MO.pair_fmr(k0[mt[:, 0]], k1[mt[:, 1]], gtm, 0.1) == ref.utils.evaluate_the_match(k0, k1, mt, gtm, 0.1)

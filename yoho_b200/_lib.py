@@ -63,6 +63,8 @@ SYMBOLS = {
     "yoho_o_order": (_i, [_vp, _i, ctypes.c_uint64, _vp, _vp]),
     "yoho_o_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_lift_group_features": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yoho_fmr_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_double, _vp, _vp]),
+    "yoho_registration_errors": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "yoho_launch_count": (ctypes.c_int64, [_vp]),
     "yoho_debug_layer": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "yoho_profile_enable": (_i, [_vp, _i]),

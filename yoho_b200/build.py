@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libyoho_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-# estimator.cu: FP64 operations must round exactly as written (bit-parity with oracle/estimator_oracle.c)
+# estimator.cu, metrics.cu: FP64 operations must round exactly as written (bit-parity with oracle/estimator_oracle.c)
 SOURCES = {
     "abi.cu": [],
     "gconv_simt.cu": [],
@@ -29,6 +29,7 @@ SOURCES = {
     "fourier.cu": [],
     "fourier_mma.cu": [],
     "estimator.cu": ["-fmad=false"],
+    "metrics.cu": ["-fmad=false"],
 }
 
 

@@ -244,6 +244,37 @@ class Engine:
                                                      _stream()))
         return (out, nn) if want_nn else out
 
+    # ---- evaluation metrics ---------------------------------------------------------
+    def fmr_counts(self, keys0, keys1, offsets, gt, threshold):
+        """Matched keypoints of n pairs concatenated ([Mtot,3] f64 each), offsets [n+1], gt [n,4,4] (or [n,3,4]) ->
+        int32[n] matches closer than `threshold` under the ground truth (tests/evaluator.py:57-66)."""
+        k0, k1 = self._f64(keys0).reshape(-1, 3), self._f64(keys1).reshape(-1, 3)
+        off = self._i64(offsets)
+        n = off.shape[0] - 1
+        g = self._f64(gt)
+        if g.dim() == 3 and g.shape[1] == 3:
+            pad = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=self.device).expand(g.shape[0], 1, 4)
+            g = torch.cat([g, pad], 1).contiguous()
+        assert g.shape == (n, 4, 4) and k0.shape == k1.shape
+        counts = torch.zeros((max(n, 0),), device=self.device, dtype=torch.int32)
+        if n > 0:
+            _lib.check(self.lib.yoho_fmr_batch(self.h, _ptr(k0), _ptr(k1), _ptr(off), _ptr(g), n, ctypes.c_double(threshold),
+                                               _ptr(counts), _stream()))
+        return counts
+
+    def registration_errors(self, est, gt, info=None):
+        """est, gt [n,4,4] f64, info [n,6,6] f64 or None -> (p or None, rre_deg, rte), utils/RR_cal.py:13-65."""
+        e, g = self._f64(est), self._f64(gt)
+        n = e.shape[0]
+        assert e.shape == (n, 4, 4) and g.shape == (n, 4, 4)
+        inf = self._f64(info) if info is not None else None
+        p = self._empty((n,), torch.float64) if inf is not None else None
+        re = self._empty((n,), torch.float64)
+        te = self._empty((n,), torch.float64)
+        if n > 0:
+            _lib.check(self.lib.yoho_registration_errors(self.h, _ptr(e), _ptr(g), _ptr(inf), n, _ptr(p), _ptr(re), _ptr(te), _stream()))
+        return p, re, te
+
     # ---- E: estimators -----------------------------------------------------------------------------
     def gather_kps(self, kps0, kps1, pairs):
         k0, k1, pr = self._f64(kps0), self._f64(kps1), self._i64(pairs)
