@@ -28,6 +28,7 @@ SOURCES = {
     "lift.cu": [],
     "fourier.cu": [],
     "fourier_mma.cu": [],
+    "fourier_tc.cu": [],
     "estimator.cu": ["-fmad=false"],
     "metrics.cu": ["-fmad=false"],
 }
