@@ -47,7 +47,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         child(int(sys.argv[1]))
     else:
-        for flags in (3 | 256, 3 | 256 | 512):
+        for flags in (3 | 256,):
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), str(flags)], capture_output=True, text=True, timeout=240)
                 print(r.stdout.strip())

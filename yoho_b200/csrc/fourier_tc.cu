@@ -35,7 +35,7 @@ struct XtArgs {
     unsigned short* out_hi;           // [B][60][C]
     unsigned short* out_lo;
     int B, C, tiles;
-    int desc_swap;                    // debugging aid: swap the LBO / SBO fields of the MN-major descriptor
+    int reserved;
 };
 
 struct __align__(8) XtBars {
@@ -58,13 +58,40 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, uint32_t& lo) {
     return hu;
 }
 
-template <bool TWO>
+// RES: a [60][128] FP32 shortcut tile rides in the stage ring next to the operand images (the epilogue reads it from shared
+// memory, one conflict-free word per lane, instead of 60 dependent global loads per thread).  C is a template parameter so
+// that every store address is base + immediate.
+template <bool RES>
+struct StageBytes { static constexpr int value = 2 * D_TILE + (RES ? YG * XCH * 4 : 0); };
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// one value -> bf16 hi / lo halves, stored to element `o` of the two output tensors
+__device__ __forceinline__ void store_split(unsigned short* __restrict__ oh, unsigned short* __restrict__ ol, size_t o, float x) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    oh[o] = __bfloat16_as_ushort(h);
+    ol[o] = __bfloat16_as_ushort(l);
+}
+
+template <bool TWO, bool RES, int C>
 __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const XtArgs p) {
+    constexpr int STAGE = StageBytes<RES>::value;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* mats = smem;                                   // m1h, m1l, (m2h, m2l)
-    uint8_t* stages = mats + (TWO ? 4 : 2) * M_IMG;         // NST x {hi, lo} data images
-    uint8_t* mids = stages + NST * 2 * D_TILE;              // TWO: 2 x {hi, lo} K-major images
+    uint8_t* stages = mats + (TWO ? 4 : 2) * M_IMG;         // NST x {hi image, lo image, (shortcut tile)}
+    uint8_t* mids = stages + NST * STAGE;                   // TWO: 2 x {hi, lo} K-major images
     XtBars* bars = (XtBars*)(mids + (TWO ? 2 * 2 * A2_TILE : 0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -82,10 +109,13 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     // k rows 60..63 of every data image stay zero: rows 4..7 of the k-group-7 atom of both channel blocks
     for (int i = threadIdx.x; i < NST * 2 * 2 * 32; i += XT_THREADS) {
         const int img = i / 64, rem = i % 64, nb = rem / 32, q = rem % 32;          // 32 x 16 B = rows 4..7 of one atom
-        *reinterpret_cast<uint4*>(stages + img * D_TILE + (nb * 8 + 7) * 1024 + 512 + q * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(stages + (img >> 1) * STAGE + (img & 1) * D_TILE + (nb * 8 + 7) * 1024 + 512 + q * 16) = make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&bars->full[s], 128); mbar_init(&bars->empty[s], 1); }
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&bars->full[s], 128);
+            mbar_init(&bars->empty[s], RES ? 1 + 128 : 1);    // tcgen05.commit (+ the epilogue threads that read the shortcut tile)
+        }
         for (int e = 0; e < 2; ++e) {
             mbar_init(&bars->acc1_full[e], 1); mbar_init(&bars->acc1_empty[e], 128);
             mbar_init(&bars->mid_full[e], 128); mbar_init(&bars->acc2_full[e], 1);
@@ -101,15 +131,15 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const int cblocks = p.C / XCH;
+    constexpr int cblocks = C / XCH;
 
     if (warp < 4) {
-        // ================= producers: [60 k][128 c] hi/lo rows -> MN-major swizzled atoms =================
+        // ================= producers: [60 k][128 c] hi/lo rows -> MN-major swizzled atoms (+ the shortcut rows) =================
         uint32_t stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int b = tile / cblocks, cb = (tile - b * cblocks) * XCH;
-            const size_t base = (size_t)b * YG * p.C + cb;
-            uint8_t* st = stages + stage * 2 * D_TILE;
+            const size_t base = (size_t)b * YG * C + cb;
+            uint8_t* st = stages + stage * STAGE;
             mbar_wait(&bars->empty[stage], phase ^ 1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -117,9 +147,17 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
                 if (item < YG * 16) {
                     const int k = item >> 4, j16 = item & 15, nb = j16 >> 3, j = j16 & 7;
                     const uint32_t o = (nb * 8 + (k >> 3)) * 1024 + (k & 7) * 128 + ((j ^ (k & 7)) << 4);
-                    const size_t g = base + (size_t)k * p.C + j16 * 8;
+                    const size_t g = base + (size_t)k * C + j16 * 8;
                     cp_async16(st + o, p.in_hi + g, true);
                     cp_async16(st + D_TILE + o, p.in_lo + g, true);
+                }
+            }
+            if (RES) {
+#pragma unroll
+                for (int i = 0; i < 15; ++i) {
+                    const int item = threadIdx.x + 128 * i;           // 60 rows x 32 chunks of 4 floats
+                    const int k = item >> 5, j = item & 31;
+                    cp_async16(st + 2 * D_TILE + k * (XCH * 4) + j * 16, p.resid + base + (size_t)k * C + j * 4, true);
                 }
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bars->full[stage])) : "memory");
@@ -128,7 +166,6 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     } else if (warp == 12) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t lbo = p.desc_swap ? 1024u : 8192u, sbo = p.desc_swap ? 8192u : 1024u;
             const uint64_t b1h = umma_desc(mats), b1l = umma_desc(mats + M_IMG);
             const uint64_t b2h = umma_desc(mats + 2 * M_IMG), b2l = umma_desc(mats + 3 * M_IMG);
             uint32_t stage = 0, phase = 0;
@@ -142,8 +179,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
                     mbar_wait(&bars->full[stage], phase);
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
                     tc_fence_after();
-                    const uint8_t* st = stages + stage * 2 * D_TILE;
-                    const uint64_t ah = umma_desc_mn(st, lbo, sbo), al = umma_desc_mn(st + D_TILE, lbo, sbo);
+                    const uint8_t* st = stages + stage * STAGE;
+                    // MN-major operand: 64-channel blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO)
+                    const uint64_t ah = umma_desc_mn(st, 8192u, 1024u), al = umma_desc_mn(st + D_TILE, 8192u, 1024u);
                     const uint32_t d = tmem_base + e * 64;
 #pragma unroll
                     for (uint32_t ks = 0; ks < 4; ++ks) {
@@ -183,6 +221,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
         const int q = warp & 3;                              // TMEM lane quadrant this warp may read
         const int cl = q * 32 + lane;                        // channel of this thread inside the tile
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const bool act = p.scale != nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
             if ((it & 1) != e) continue;
@@ -190,88 +229,54 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             const int b = tile / cblocks, cb = (tile - b * cblocks) * XCH;
             const int c = cb + cl;
             const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
-            const float sc = p.scale ? __ldg(p.scale + c) : 1.f, sh = p.scale ? __ldg(p.shift + c) : 0.f;
-            const size_t row0 = (size_t)b * YG * p.C + c;    // element offset of (b, m = 0, c)
-            float rcur[16];
-            if (p.resid) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) rcur[i] = __ldg(p.resid + row0 + (size_t)i * p.C);
-            }
+            const float sc = act ? __ldg(p.scale + c) : 1.f, sh = act ? __ldg(p.shift + c) : 0.f;
+            unsigned short* oh = p.out_hi + (size_t)b * YG * C + c;      // (b, m = 0, c); row m is at + m * C (immediate offsets)
+            unsigned short* ol = p.out_lo + (size_t)b * YG * C + c;
+            const int stage = it % NST;
+            const float* rs = (const float*)(stages + stage * STAGE + 2 * D_TILE) + cl;
             mbar_wait(&bars->acc1_full[e], par);
             tc_fence_after();
-            uint8_t* md = mids + e * 2 * A2_TILE;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + e * 64 + ch * 16 + lane_off, v);
-                float rnext[16];
-                if (p.resid && ch < 3) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int m = (ch + 1) * 16 + i;
-                        rnext[i] = m < YG ? __ldg(p.resid + row0 + (size_t)m * p.C) : 0.f;
-                    }
-                }
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x = __uint_as_float(v[i]) + bias;
-                    if (p.resid) x += rcur[i];
-                    if (p.scale) x = fmaxf(fmaf(x, sc, sh), 0.f);
-                    f[i] = (ch * 16 + i) < YG ? x : 0.f;
-                }
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hi[i] = pack2(f[2 * i], f[2 * i + 1], lo[i]);
-                if (TWO) {
-                    // row `cl` of the K-major image: 16 values = chunks 2ch, 2ch+1 of the 128-byte row
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t o = cl * 128 + (((2 * ch + h) ^ (cl & 7)) << 4);
-                        *reinterpret_cast<uint4*>(md + o) = make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
-                        *reinterpret_cast<uint4*>(md + A2_TILE + o) = make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int m = ch * 16 + i;
-                        if (m < YG) {
-                            const size_t o = row0 + (size_t)m * p.C;
-                            p.out_hi[o] = (unsigned short)(i & 1 ? hi[i >> 1] >> 16 : hi[i >> 1] & 0xffffu);
-                            p.out_lo[o] = (unsigned short)(i & 1 ? lo[i >> 1] >> 16 : lo[i >> 1] & 0xffffu);
-                        }
-                    }
-                }
-                if (p.resid) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) rcur[i] = rnext[i];
-                }
-            }
+            uint32_t v[64];
+            tmem_ld32_nowait(tmem_base + e * 64 + lane_off, v);
+            tmem_ld32_nowait(tmem_base + e * 64 + 32 + lane_off, v + 32);
+            if (RES) mbar_wait(&bars->full[stage], (uint32_t)(it / NST) & 1u);   // the shortcut tile has landed (same barrier the MMA waited on)
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             tc_fence_before();
-            mbar_arrive(&bars->acc1_empty[e]);
+            mbar_arrive(&bars->acc1_empty[e]);               // accumulator 1 is in registers
+            uint8_t* md = mids + e * 2 * A2_TILE;
+#pragma unroll
+            for (int m = 0; m < 64; ++m) {
+                float x = 0.f;
+                if (m < YG) {
+                    x = __uint_as_float(v[m]) + bias;
+                    if (RES) x += rs[m * XCH];
+                    if (act) x = fmaxf(fmaf(x, sc, sh), 0.f);
+                    if (!TWO) store_split(oh, ol, (size_t)m * C, x);
+                }
+                v[m] = __float_as_uint(x);
+            }
+            if (RES) mbar_arrive(&bars->empty[stage]);       // shortcut tile consumed: the stage may be refilled
             if (TWO) {
+                // row `cl` of the K-major image: 64 values = the 8 chunks of the 128-byte row (hi and lo)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) hi[i] = pack2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]), lo[i]);
+                    const uint32_t o = cl * 128 + ((j ^ (cl & 7)) << 4);
+                    *reinterpret_cast<uint4*>(md + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(md + A2_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the K-major image (generic stores) -> UMMA
                 mbar_arrive(&bars->mid_full[e]);
                 mbar_wait(&bars->acc2_full[e], par);
                 tc_fence_after();
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + 128 + e * 64 + ch * 16 + lane_off, v);
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) hi[i] = pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), lo[i]);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int m = ch * 16 + i;
-                        if (m < YG) {
-                            const size_t o = row0 + (size_t)m * p.C;
-                            p.out_hi[o] = (unsigned short)(i & 1 ? hi[i >> 1] >> 16 : hi[i >> 1] & 0xffffu);
-                            p.out_lo[o] = (unsigned short)(i & 1 ? lo[i >> 1] >> 16 : lo[i >> 1] & 0xffffu);
-                        }
-                    }
-                }
+                tmem_ld32_nowait(tmem_base + 128 + e * 64 + lane_off, v);
+                tmem_ld32_nowait(tmem_base + 128 + e * 64 + 32 + lane_off, v + 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                 tc_fence_before();       // orders these TMEM reads before the next mid_full arrive (which lets product 2 overwrite)
+#pragma unroll
+                for (int m = 0; m < YG; ++m) store_split(oh, ol, (size_t)m * C, __uint_as_float(v[m]));
             }
         }
     }
@@ -283,27 +288,33 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     }
 }
 
-template <bool TWO>
-constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)NST * 2 * D_TILE + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
+template <bool TWO, bool RES>
+constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)NST * StageBytes<RES>::value + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
+
+template <bool TWO, bool RES, int C>
+int xt_launch(yoho_ctx* ctx, const XtArgs& p, cudaStream_t st) {
+    YCHECK(cudaFuncSetAttribute(group_transform_tc_kernel<TWO, RES, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xt_smem<TWO, RES>()));
+    const int grid = p.tiles < ctx->num_sms ? p.tiles : ctx->num_sms;
+    group_transform_tc_kernel<TWO, RES, C><<<grid, XT_THREADS, xt_smem<TWO, RES>(), st>>>(p);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
+}
 
 }  // namespace
+
+// The three shapes PartI uses are instantiated: forward only (C=256), inverse -> activation -> forward (C=512), inverse +
+// shortcut -> activation (C=256).  Returns YOHO_ERR_ARG-free `-1` for any other shape: the caller falls back to the warp-MMA kernel.
+bool group_transform_tc_supported(int C, bool two, bool res) { return (C == 256 && !two) || (C == 512 && two && !res); }
 
 int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                        void* out_hi, void* out_lo, cudaStream_t st) {
-    YARG(C % XCH == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
+    YARG(B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo && group_transform_tc_supported(C, m2_hi != nullptr, resid != nullptr));
     XtArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const unsigned short*)m1_hi, (const unsigned short*)m1_lo,
              (const unsigned short*)m2_hi, (const unsigned short*)m2_lo, bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo,
-             B, C, B * (C / XCH), (ctx->tc_flags & 512) ? 1 : 0};
-    const int grid = p.tiles < ctx->num_sms ? p.tiles : ctx->num_sms;
-    if (m2_hi) {
-        YCHECK(cudaFuncSetAttribute(group_transform_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xt_smem<true>()));
-        group_transform_tc_kernel<true><<<grid, XT_THREADS, xt_smem<true>(), st>>>(p);
-    } else {
-        YCHECK(cudaFuncSetAttribute(group_transform_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xt_smem<false>()));
-        group_transform_tc_kernel<false><<<grid, XT_THREADS, xt_smem<false>(), st>>>(p);
-    }
-    ctx->launches++;
-    YCHECK(cudaGetLastError());
-    return YOHO_OK;
+             B, C, B * (C / XCH), 0};
+    if (m2_hi) return xt_launch<true, false, 512>(ctx, p, st);
+    if (resid) return xt_launch<false, true, 256>(ctx, p, st);
+    return xt_launch<false, false, 256>(ctx, p, st);
 }
