@@ -151,8 +151,8 @@ def test_part2_tc_realckpt(engine, tables, impl):
 
 
 def test_fourier_transform_kernels_agree(engine, tables):
-    """The warp-autonomous MMA transform kernel (default) against its FP32 SIMT twin (tuning flag 4) and the two block-tiled
-    MMA variants (flags 8, 32), through the whole PartI."""
+    """The tcgen05 transform kernel (default, flag 256) against the warp-autonomous MMA transform kernel (flags 3), its FP32
+    SIMT twin (flag 4) and the block-tiled MMA variants (flags 8, 32, 64, 128), through the whole PartI."""
     _, _, N = tables
     sd = synth.synth_state_dict("PartI", 2)
     engine.load_part1(sd)
@@ -173,14 +173,18 @@ def test_fourier_transform_kernels_agree(engine, tables):
         e = engine.part1(x)
         engine.set_tuning(0, 3 | 128)        # 12 single-buffered warps per CTA
         f = engine.part1(x)
+        engine.set_tuning(0, 3 | 256)        # tcgen05 transform kernel (the default)
+        g = engine.part1(x)
         torch.cuda.synchronize()
     finally:
-        engine.set_tuning(0, 3)
+        engine.set_tuning(0, engine.DEFAULT_TUNING)
         engine.set_gconv_impl("simt")
     ref = O.part1_forward(x, sd, N)
     _report("fourier mma-xf vs simt-xf", _np(a["eqv"]), _np(b["eqv"]))
     e1, _ = _report("fourier mma-xf vs oracle", _np(a["eqv"]), ref["eqv"].numpy())
     e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
-    assert e1 <= DESC_TOL and e2 <= DESC_TOL
+    e3, _ = _report("fourier tcgen05-xf vs oracle", _np(g["eqv"]), ref["eqv"].numpy())
+    e4, _ = _report("fourier tcgen05-xf vs mma-xf", _np(g["eqv"]), _np(a["eqv"]))
+    assert e1 <= DESC_TOL and e2 <= DESC_TOL and e3 <= DESC_TOL and e4 <= 2e-5
     assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], c2["eqv"]) and torch.equal(a["eqv"], d["eqv"])
     assert torch.equal(a["eqv"], e["eqv"]) and torch.equal(a["eqv"], f["eqv"])

@@ -48,7 +48,7 @@ eng.set_tuning(0, 2)
 
 # ---- whole PartI forward per implementation (5000 keypoints) ------------------------------------------------------
 x = torch.from_numpy(synth.make_fragment(5000, 3)[0]).cuda()
-for impl, flags in [("tcgen05_split", 3), ("tcgen05_fourier", 3), ("tcgen05_fourier", 3 | 64), ("tcgen05_fourier", 3 | 128), ("tcgen05_fourier", 3 | 32)]:
+for impl, flags in [("tcgen05_split", 3), ("tcgen05_fourier", 3 | 256), ("tcgen05_fourier", 3), ("tcgen05_fourier", 3 | 64), ("tcgen05_fourier", 3 | 128), ("tcgen05_fourier", 3 | 32)]:
     eng.set_gconv_impl(impl)
     eng.set_tuning(0, flags)
     ms = time_it(lambda: eng.part1(x, want_inv=False))
@@ -57,5 +57,5 @@ for impl, flags in [("tcgen05_split", 3), ("tcgen05_fourier", 3), ("tcgen05_four
     pr = eng.profile_read()
     eng.profile(False)
     print(f"part1 5000 kpts {impl} flags={flags}: {ms:.3f} ms; " + ", ".join(f"{q['name']}={q['ms']:.3f}" for q in pr if q['launches']), flush=True)
-eng.set_tuning(0, 3)
+eng.set_tuning(0, eng.DEFAULT_TUNING)
 eng.set_gconv_impl("tcgen05_fourier")

@@ -6,8 +6,9 @@
 //     D2[c][m'] = sum_m mid[c][m] M2t[m'][m]     A = the pointwise result, written by the epilogue as a K-major image, B = M2t
 // Each product is 3 bf16 MMAs (hi*hi, lo*hi, hi*lo), M128 x N64 x K16, four K steps.  The transform is HBM-bound (60x60 per
 // channel): a persistent CTA per SM streams (keypoint, 128-channel) tiles through a 3-stage cp.async ring; warps 0-3 load,
-// warp 12 issues the MMAs, two sets of four epilogue warps (4-7, 8-11) alternate tiles so that the pointwise stage, the
-// hi/lo packing and the stores of one tile overlap the loads and MMAs of the next.
+// warp 12 issues the MMAs, warps 4-11 are the epilogue.  One-product kernels: two sets of four warps (4-7, 8-11) alternate
+// tiles.  Two-product kernel: all eight warps share every tile (half of the coefficient columns each) and are software
+// pipelined — pointwise stage of tile i, then the stores of tile i-1 — so nobody waits for the round trip through product 2.
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -86,6 +87,7 @@ __device__ __forceinline__ void store_split(unsigned short* __restrict__ oh, uns
 
 template <bool TWO, bool RES, int C>
 __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const XtArgs p) {
+    static_assert(!(TWO && RES), "the two-product kernel carries no shortcut tile");
     constexpr int STAGE = StageBytes<RES>::value;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -117,8 +119,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             mbar_init(&bars->empty[s], RES ? 1 + 128 : 1);    // tcgen05.commit (+ the epilogue threads that read the shortcut tile)
         }
         for (int e = 0; e < 2; ++e) {
-            mbar_init(&bars->acc1_full[e], 1); mbar_init(&bars->acc1_empty[e], 128);
-            mbar_init(&bars->mid_full[e], 128); mbar_init(&bars->acc2_full[e], 1);
+            mbar_init(&bars->acc1_full[e], 1); mbar_init(&bars->acc1_empty[e], TWO ? 256 : 128);
+            mbar_init(&bars->mid_full[e], TWO ? 256 : 128); mbar_init(&bars->acc2_full[e], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -215,8 +217,74 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
                 }
             }
         }
+    } else if constexpr (TWO) {
+        // ================= epilogue, two products: all eight warps work on EVERY tile =================
+        // Warp (q = warp % 4, h = (warp - 4) / 4) owns channels q*32.. (its TMEM lane quadrant) and coefficient columns
+        // 32h..32h+31.  Software pipelined: iteration `it` runs the pointwise stage of tile `it` (accumulator 1 -> K-major image
+        // for product 2) and THEN the stores of tile `it - 1` (accumulator 2), so the round trip through the MMA issuer
+        // (image -> product 2 -> commit) is hidden behind the previous tile's stores instead of stalling the warp.
+        const int h = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const int cl = q * 32 + lane;
+        const uint32_t lane_off = ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * h);
+        const bool act = p.scale != nullptr;
+        unsigned short* oh_prev = nullptr;
+        unsigned short* ol_prev = nullptr;
+        int it = 0;
+        auto store_prev = [&](int pit) {
+            const int e = pit & 1;
+            uint32_t v[32];
+            mbar_wait(&bars->acc2_full[e], (uint32_t)(pit >> 1) & 1u);
+            tc_fence_after();
+            tmem_ld32_nowait(tmem_base + 128 + e * 64 + lane_off, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            tc_fence_before();       // orders these TMEM reads before this thread's next mid_full arrive (-> product 2 may overwrite)
+#pragma unroll
+            for (int m = 0; m < 32; ++m)
+                if (32 * h + m < YG) store_split(oh_prev, ol_prev, (size_t)(32 * h + m) * C, __uint_as_float(v[m]));
+        };
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            const int e = it & 1;
+            const int b = tile / cblocks, cb = (tile - b * cblocks) * XCH;
+            const int c = cb + cl;
+            const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
+            const float sc = act ? __ldg(p.scale + c) : 1.f, sh = act ? __ldg(p.shift + c) : 0.f;
+            mbar_wait(&bars->acc1_full[e], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32_nowait(tmem_base + e * 64 + lane_off, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&bars->acc1_empty[e]);               // this thread's part of accumulator 1 is in registers
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                float x = 0.f;
+                if (32 * h + m < YG) {
+                    x = __uint_as_float(v[m]) + bias;
+                    if (act) x = fmaxf(fmaf(x, sc, sh), 0.f);
+                }
+                v[m] = __float_as_uint(x);
+            }
+            // row `cl` of the K-major image: this thread's 32 values = chunks 4h..4h+3 of the 128-byte row (hi and lo)
+            uint8_t* md = mids + e * 2 * A2_TILE;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hi[i] = pack2(__uint_as_float(v[8 * jj + 2 * i]), __uint_as_float(v[8 * jj + 2 * i + 1]), lo[i]);
+                const uint32_t o = cl * 128 + (((uint32_t)(4 * h + jj) ^ (uint32_t)(cl & 7)) << 4);
+                *reinterpret_cast<uint4*>(md + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(md + A2_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the K-major image (generic stores) -> UMMA
+            mbar_arrive(&bars->mid_full[e]);
+            if (it > 0) store_prev(it - 1);
+            oh_prev = p.out_hi + (size_t)b * YG * C + c;     // (b, m = 0, c); row m is at + m * C (immediate offsets)
+            ol_prev = p.out_lo + (size_t)b * YG * C + c;
+        }
+        if (it > 0) store_prev(it - 1);
     } else {
-        // ================= epilogue sets: warps 4-7 take even local tiles, warps 8-11 odd ones =================
+        // ================= epilogue sets, one product: warps 4-7 take even local tiles, warps 8-11 odd ones =================
         const int e = (warp - 4) >> 2;
         const int q = warp & 3;                              // TMEM lane quadrant this warp may read
         const int cl = q * 32 + lane;                        // channel of this thread inside the tile
@@ -243,41 +311,14 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             tc_fence_before();
             mbar_arrive(&bars->acc1_empty[e]);               // accumulator 1 is in registers
-            uint8_t* md = mids + e * 2 * A2_TILE;
 #pragma unroll
-            for (int m = 0; m < 64; ++m) {
-                float x = 0.f;
-                if (m < YG) {
-                    x = __uint_as_float(v[m]) + bias;
-                    if (RES) x += rs[m * XCH];
-                    if (act) x = fmaxf(fmaf(x, sc, sh), 0.f);
-                    if (!TWO) store_split(oh, ol, (size_t)m * C, x);
-                }
-                v[m] = __float_as_uint(x);
+            for (int m = 0; m < YG; ++m) {
+                float x = __uint_as_float(v[m]) + bias;
+                if (RES) x += rs[m * XCH];
+                if (act) x = fmaxf(fmaf(x, sc, sh), 0.f);
+                store_split(oh, ol, (size_t)m * C, x);
             }
             if (RES) mbar_arrive(&bars->empty[stage]);       // shortcut tile consumed: the stage may be refilled
-            if (TWO) {
-                // row `cl` of the K-major image: 64 values = the 8 chunks of the 128-byte row (hi and lo)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) hi[i] = pack2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]), lo[i]);
-                    const uint32_t o = cl * 128 + ((j ^ (cl & 7)) << 4);
-                    *reinterpret_cast<uint4*>(md + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(md + A2_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the K-major image (generic stores) -> UMMA
-                mbar_arrive(&bars->mid_full[e]);
-                mbar_wait(&bars->acc2_full[e], par);
-                tc_fence_after();
-                tmem_ld32_nowait(tmem_base + 128 + e * 64 + lane_off, v);
-                tmem_ld32_nowait(tmem_base + 128 + e * 64 + 32 + lane_off, v + 32);
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                tc_fence_before();       // orders these TMEM reads before the next mid_full arrive (which lets product 2 overwrite)
-#pragma unroll
-                for (int m = 0; m < YG; ++m) store_split(oh, ol, (size_t)m * C, __uint_as_float(v[m]));
-            }
         }
     }
     tc_fence_before();

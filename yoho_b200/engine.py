@@ -92,6 +92,8 @@ class Engine:
         self.impl_name = impl
         _lib.check(self.lib.yoho_set_gconv_impl(self.h, {"simt": 0, "tcgen05": 1, "tcgen05_split": 2, "tcgen05_fourier": 3}.get(impl, impl)))
 
+    DEFAULT_TUNING = 3 | 256      # csrc/common.cuh yoho_ctx::tc_flags
+
     def set_tuning(self, key, value):
         _lib.check(self.lib.yoho_set_tuning(self.h, int(key), int(value)))
 
