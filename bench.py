@@ -219,6 +219,8 @@ def run_ours(args):
     for i in range(args.warmup):
         results.append(pipe.register(*sets_d[i % N_SETS]))
         pipe.register_pinned(*sets_p[i % N_SETS])
+    for _ in pipe.register_stream(sets_p[i % N_SETS] for i in range(2)):
+        pass
     # ---- device-resident timed region -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     eng.profile(True)
@@ -242,8 +244,12 @@ def run_ours(args):
     # ---- end-to-end timed region: host buffers in, host transforms out ----------------------------------------
     barrier()
     ev0.record()
-    for i in range(args.steps):
-        out = pipe.register_pinned(*sets_p[i % N_SETS])      # H2D from pinned memory, pipeline, D2H of the transforms
+    # every step: H2D of that pair's inputs from pinned memory, the pipeline, D2H of its transforms; the copies of pair i+1
+    # are prefetched while pair i computes (PairPipeline.register_stream, the dataset-throughput call)
+    n_out = 0
+    for out in pipe.register_stream(sets_p[i % N_SETS] for i in range(args.steps)):
+        n_out += 1
+    assert n_out == args.steps
     ev1.record()
     barrier()
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))

@@ -186,6 +186,24 @@ def test_scene_driver_matches_per_pair_pipeline(engine):
     assert _rot_err_deg(Tc[:, :3], a['R_gt']) < 3.0
 
 
+def test_register_stream_equals_per_pair_calls(engine):
+    """The prefetching throughput call returns, pair by pair, exactly what the one-pair host call returns (same seeds)."""
+    from yoho_b200.pipeline import PairPipeline
+    engine.load_part1(synth.synth_state_dict('PartI', 0))
+    engine.load_part2(synth.synth_state_dict('PartII', 0))
+    pairs = [synth.make_fragment_pair(300 + 50 * i, seed=20 + i, overlap=0.6) for i in range(4)]
+    pins = [PairPipeline.pin(p['feat_A'], p['feat_B'], p['kps_A'], p['kps_B']) for p in pairs]
+    # register() draws with seed = ++pipe.seed: a stream started at seed 5 runs pair i with seed 6 + i
+    one = [PairPipeline(engine, seed=5 + i).register_pinned(*pins[i]) for i in range(4)]
+    got = list(PairPipeline(engine, seed=5).register_stream(iter(pins)))
+    assert len(got) == 4
+    for i in range(4):
+        assert got[i]['M'] == one[i]['M']
+        assert np.array_equal(got[i]['T_c'], one[i]['T_c']) and np.array_equal(got[i]['T_o'], one[i]['T_o'])
+        assert _rot_err_deg(got[i]['T_c'][:, :3], pairs[i]['R_gt']) < 3.0
+    assert list(PairPipeline(engine, seed=0).register_stream(iter([]))) == []
+
+
 def test_pipeline_degenerate_statistics_gives_identity(engine):
     """Fewer than three matches per rotation bin: DR_statictic returns None and the reference writes the identity
     (tests/estimator.py:41-51,107-108)."""

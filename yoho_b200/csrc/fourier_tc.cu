@@ -15,12 +15,13 @@
 
 namespace {
 
-constexpr int XT_THREADS = 416;
+constexpr int XT_THREADS = 448;               // 4 producer warps, 8 epilogue warps, product-1 issuer, product-2 issuer
 constexpr int XCH = 128;                     // channels per tile (UMMA M)
 constexpr int D_TILE = 64 * XCH * 2;         // bytes of one [64 k][128 c] bf16 operand image (hi or lo): 2 x 8 atoms of 1 KB
 constexpr int M_IMG = 64 * 64 * 2;           // bytes of one [64][64] bf16 matrix image
 constexpr int A2_TILE = XCH * 64 * 2;        // bytes of one [128 c][64 k] K-major image (hi or lo)
-constexpr int NST = 3;
+constexpr int NST_MAX = 4;
+constexpr int NACC1_MAX = 4;
 
 struct XtArgs {
     const unsigned short* in_hi;      // [B][60][C] bf16 hi/lo split of the input
@@ -40,8 +41,8 @@ struct XtArgs {
 };
 
 struct __align__(8) XtBars {
-    unsigned long long full[NST], empty[NST];
-    unsigned long long acc1_full[2], acc1_empty[2];
+    unsigned long long full[NST_MAX], empty[NST_MAX];
+    unsigned long long acc1_full[NACC1_MAX], acc1_empty[NACC1_MAX];
     unsigned long long mid_full[2];
     unsigned long long acc2_full[2];
     uint32_t tmem_base;
@@ -89,6 +90,13 @@ template <bool TWO, bool RES, int C>
 __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const XtArgs p) {
     static_assert(!(TWO && RES), "the two-product kernel carries no shortcut tile");
     constexpr int STAGE = StageBytes<RES>::value;
+    // The two-product kernel is a longer pipeline (pointwise stage + second product between load and store): product 1 runs up
+    // to four tiles ahead of the epilogue into four TMEM accumulators, so a stage is released as soon as its tile has LANDED
+    // and been multiplied — the load ring (4 stages) stays in flight independently of the epilogue's progress.
+    constexpr int NST = TWO ? 4 : 3;
+    constexpr int NACC1 = TWO ? 4 : 2;
+    constexpr uint32_t ACC2_COL = NACC1 * 64;
+    constexpr uint32_t TMEM_COLS = TWO ? 512 : 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* mats = smem;                                   // m1h, m1l, (m2h, m2l)
@@ -118,14 +126,12 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             mbar_init(&bars->full[s], 128);
             mbar_init(&bars->empty[s], RES ? 1 + 128 : 1);    // tcgen05.commit (+ the epilogue threads that read the shortcut tile)
         }
-        for (int e = 0; e < 2; ++e) {
-            mbar_init(&bars->acc1_full[e], 1); mbar_init(&bars->acc1_empty[e], TWO ? 256 : 128);
-            mbar_init(&bars->mid_full[e], TWO ? 256 : 128); mbar_init(&bars->acc2_full[e], 1);
-        }
+        for (int e = 0; e < NACC1; ++e) { mbar_init(&bars->acc1_full[e], 1); mbar_init(&bars->acc1_empty[e], TWO ? 256 : 128); }
+        for (int e = 0; e < 2; ++e) { mbar_init(&bars->mid_full[e], 256); mbar_init(&bars->acc2_full[e], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 12) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // matrix images / zero rows -> async proxy (UMMA)
@@ -166,55 +172,54 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             if (++stage == NST) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 12) {
-        // ================= MMA issuer =================
+        // ================= product-1 issuer =================
         if (lane == 0) {
             const uint64_t b1h = umma_desc(mats), b1l = umma_desc(mats + M_IMG);
-            const uint64_t b2h = umma_desc(mats + 2 * M_IMG), b2l = umma_desc(mats + 3 * M_IMG);
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles + (TWO ? gridDim.x : 0); tile += gridDim.x, ++it) {
-                if (tile < p.tiles) {
-                    // product 1 of tile `it`
-                    const int e = it & 1;
-                    const uint32_t par = (uint32_t)(it >> 1) & 1u;
-                    mbar_wait(&bars->acc1_empty[e], par ^ 1);
-                    mbar_wait(&bars->full[stage], phase);
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
-                    tc_fence_after();
-                    const uint8_t* st = stages + stage * STAGE;
-                    // MN-major operand: 64-channel blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO)
-                    const uint64_t ah = umma_desc_mn(st, 8192u, 1024u), al = umma_desc_mn(st + D_TILE, 8192u, 1024u);
-                    const uint32_t d = tmem_base + e * 64;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                const int a = it % NACC1;
+                mbar_wait(&bars->acc1_empty[a], ((uint32_t)(it / NACC1) & 1u) ^ 1u);
+                mbar_wait(&bars->full[stage], phase);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
+                tc_fence_after();
+                const uint8_t* st = stages + stage * STAGE;
+                // MN-major operand: 64-channel blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO)
+                const uint64_t ah = umma_desc_mn(st, 8192u, 1024u), al = umma_desc_mn(st + D_TILE, 8192u, 1024u);
+                const uint32_t d = tmem_base + a * 64;
 #pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks) {
-                        const uint64_t aadv = (uint64_t)(ks * 128);            // two 8-row K groups = 2048 B, in 16-byte units
-                        const uint64_t badv = (uint64_t)(ks * 2);              // 32 bytes
-                        tc_mma(d, ah + aadv, b1h + badv, IDESC_MN, ks ? 1u : 0u);
-                        tc_mma(d, al + aadv, b1h + badv, IDESC_MN, 1u);
-                        tc_mma(d, ah + aadv, b1l + badv, IDESC_MN, 1u);
-                    }
-                    tc_commit(&bars->empty[stage]);
-                    tc_commit(&bars->acc1_full[e]);
-                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                for (uint32_t ks = 0; ks < 4; ++ks) {
+                    const uint64_t aadv = (uint64_t)(ks * 128);            // two 8-row K groups = 2048 B, in 16-byte units
+                    const uint64_t badv = (uint64_t)(ks * 2);              // 32 bytes
+                    tc_mma(d, ah + aadv, b1h + badv, IDESC_MN, ks ? 1u : 0u);
+                    tc_mma(d, al + aadv, b1h + badv, IDESC_MN, 1u);
+                    tc_mma(d, ah + aadv, b1l + badv, IDESC_MN, 1u);
                 }
-                if (TWO && it > 0) {
-                    // product 2 of tile `it - 1` (its pointwise stage ran while product 1 of tile `it` was issued)
-                    const int e = (it - 1) & 1;
-                    const uint32_t par = (uint32_t)((it - 1) >> 1) & 1u;
-                    mbar_wait(&bars->mid_full[e], par);
-                    tc_fence_after();
-                    const uint8_t* md = mids + e * 2 * A2_TILE;
-                    const uint64_t ah = umma_desc(md), al = umma_desc(md + A2_TILE);
-                    const uint32_t d = tmem_base + 128 + e * 64;
+                tc_commit(&bars->empty[stage]);
+                tc_commit(&bars->acc1_full[a]);
+                if (++stage == NST) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 13) {
+        // ================= product-2 issuer (its own thread: never queued behind a product 1 that waits for a load) =================
+        if (TWO && lane == 0) {
+            const uint64_t b2h = umma_desc(mats + 2 * M_IMG), b2l = umma_desc(mats + 3 * M_IMG);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                const int e = it & 1;
+                mbar_wait(&bars->mid_full[e], (uint32_t)(it >> 1) & 1u);
+                tc_fence_after();
+                const uint8_t* md = mids + e * 2 * A2_TILE;
+                const uint64_t ah = umma_desc(md), al = umma_desc(md + A2_TILE);
+                const uint32_t d = tmem_base + ACC2_COL + e * 64;
 #pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks) {
-                        const uint64_t adv = (uint64_t)(ks * 2);
-                        tc_mma(d, ah + adv, b2h + adv, IDESC_K, ks ? 1u : 0u);
-                        tc_mma(d, al + adv, b2h + adv, IDESC_K, 1u);
-                        tc_mma(d, ah + adv, b2l + adv, IDESC_K, 1u);
-                    }
-                    tc_commit(&bars->acc2_full[e]);
+                for (uint32_t ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);
+                    tc_mma(d, ah + adv, b2h + adv, IDESC_K, ks ? 1u : 0u);
+                    tc_mma(d, al + adv, b2h + adv, IDESC_K, 1u);
+                    tc_mma(d, ah + adv, b2l + adv, IDESC_K, 1u);
                 }
+                tc_commit(&bars->acc2_full[e]);
             }
         }
     } else if constexpr (TWO) {
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             uint32_t v[32];
             mbar_wait(&bars->acc2_full[e], (uint32_t)(pit >> 1) & 1u);
             tc_fence_after();
-            tmem_ld32_nowait(tmem_base + 128 + e * 64 + lane_off, v);
+            tmem_ld32_nowait(tmem_base + ACC2_COL + e * 64 + lane_off, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             tc_fence_before();       // orders these TMEM reads before this thread's next mid_full arrive (-> product 2 may overwrite)
 #pragma unroll
@@ -249,13 +254,14 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             const int c = cb + cl;
             const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
             const float sc = act ? __ldg(p.scale + c) : 1.f, sh = act ? __ldg(p.shift + c) : 0.f;
-            mbar_wait(&bars->acc1_full[e], (uint32_t)(it >> 1) & 1u);
+            const int a = it % NACC1;
+            mbar_wait(&bars->acc1_full[a], (uint32_t)(it / NACC1) & 1u);
             tc_fence_after();
             uint32_t v[32];
-            tmem_ld32_nowait(tmem_base + e * 64 + lane_off, v);
+            tmem_ld32_nowait(tmem_base + a * 64 + lane_off, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             tc_fence_before();
-            mbar_arrive(&bars->acc1_empty[e]);               // this thread's part of accumulator 1 is in registers
+            mbar_arrive(&bars->acc1_empty[a]);               // this thread's part of accumulator 1 is in registers
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
                 float x = 0.f;
@@ -325,12 +331,12 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     __syncthreads();
     if (warp == 12) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
 template <bool TWO, bool RES>
-constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)NST * StageBytes<RES>::value + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
+constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)(TWO ? 4 : 3) * StageBytes<RES>::value + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
 
 template <bool TWO, bool RES, int C>
 int xt_launch(yoho_ctx* ctx, const XtArgs& p, cudaStream_t st) {

@@ -30,8 +30,8 @@ constexpr int BK = 64;                       // bf16 elements per K block = one 
 constexpr int A_TILE = BM * BK * 2;          // 16 KB (hi or lo)
 constexpr int THREADS = 448;               // 4 A-producer warps, 8 epilogue warps, W producer, MMA issuer
 constexpr int EPI_THREADS = 256;
-constexpr int EPI_ROW = 80;                 // bytes per staged row: 64 payload + 16 pad (16-byte aligned, conflict-free)
-constexpr int EPI_WBUF = 32 * EPI_ROW;      // per-epilogue-warp staging buffer (2.5 KB)
+constexpr int EPI_ROW = 64;                 // bytes per staged row (unpadded, XOR-swizzled: see coalesced_store)
+constexpr int EPI_WBUF = 32 * EPI_ROW;      // per-epilogue-warp staging buffer (2 KB)
 constexpr int MAX_STAGES = 4;
 
 // Tile width BN = 256 for the wide layers (2 stages of 96 KB, two 256-column accumulators = all of TMEM) and
@@ -101,23 +101,35 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
 };
 
-// Epilogue store of a [32 rows x NB bytes] block held one row per lane (NB/16 uint4 registers per lane): staged through a
-// per-warp shared-memory buffer so that each warp-wide store instruction writes NB contiguous bytes of 512/NB rows instead of
-// 16 bytes of 32 different rows (the L1TEX tag stage serialises on cache lines touched per instruction).
+// Epilogue store of a [32 rows x 64 bytes] block held one row per lane (four uint4 registers per lane): staged through a
+// per-warp 2 KB shared-memory buffer so that each warp-wide store instruction writes 64 contiguous bytes of 8 rows instead of
+// 16 bytes of 32 different rows (the L1TEX tag stage serialises on cache lines touched per instruction).  The buffer is
+// unpadded and XOR-swizzled — 16-byte piece i of row r lives at r*64 + ((i ^ (r >> 1)) & 3)*16 — which makes both the row-per-
+// lane writes and the 4-lanes-per-row reads conflict-free (the former 80-byte pitch cost two wavefronts per read quarter).
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
 template <int NB>
 __device__ __forceinline__ void coalesced_store(uint8_t* wbuf, const uint4* regs, uint8_t* my_row, int lane, uint32_t okmask) {
     // my_row: global address of THIS lane's row (column offset applied); rows need not be equally spaced (remapped outputs)
+    static_assert(NB == 64, "the swizzle below is written for four 16-byte pieces per row");
     constexpr int Q = NB / 16;                       // 16-byte pieces per row
     const unsigned long long addr = (unsigned long long)my_row;
+    const uint32_t wb = smem_u32(wbuf);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < Q; ++i) *reinterpret_cast<uint4*>(wbuf + lane * EPI_ROW + i * 16) = regs[i];
+    for (int i = 0; i < Q; ++i) sts128(wb + lane * EPI_ROW + (((uint32_t)i ^ ((uint32_t)lane >> 1)) & 3u) * 16, regs[i]);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < Q; ++it) {
         const int item = it * 32 + lane;
         const int row = item / Q, q = item % Q;
-        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + row * EPI_ROW + q * 16);
+        const uint4 v = lds128(wb + row * EPI_ROW + (((uint32_t)q ^ ((uint32_t)row >> 1)) & 3u) * 16);
         const unsigned long long ra = __shfl_sync(0xffffffffu, addr, row);
         if ((okmask >> row) & 1u) *reinterpret_cast<uint4*>((uint8_t*)ra + q * 16) = v;
     }

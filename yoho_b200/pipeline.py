@@ -100,6 +100,61 @@ class PairPipeline:
         res = torch.stack([r["T_c"], r["T_o"]]).cpu().numpy()          # D2H of the result (synchronises)
         return dict(T_c=res[0], T_o=res[1], M=r["M"])
 
+    def register_stream(self, pinned_pairs):
+        """Throughput form of `register_pinned` for a sequence of pairs (the way a dataset is processed, tests/evaluator.py:41-47):
+        generator over `(fa_pin, fb_pin, ka_pin, kb_pin)` tuples yielding one `dict(T_c, T_o, M)` per pair, in order.  The H2D
+        copies of pair i+1 run on the side stream while pair i computes, and the D2H of pair i's transforms (into a pinned
+        buffer) is awaited only when pair i+1 has been queued, so neither copy sits on the critical path.  Every pair's inputs
+        still cross PCIe from host memory and every result is read back to the host."""
+        dev = self.eng.device
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+
+        def upload(pp):
+            with torch.cuda.stream(cs):
+                ts = [t.to(dev, non_blocking=True) for t in pp]
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            for t in ts:
+                t.record_stream(main)
+            return ts, ev
+
+        def finish(pend):
+            host, ev, M = pend
+            ev.synchronize()
+            res = host.numpy().copy()
+            return dict(T_c=res[0], T_o=res[1], M=M)
+
+        it = iter(pinned_pairs)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        pending = None
+        n = 0
+        while nxt is not None:
+            (fa, fb, ka, kb), ev = nxt
+            try:
+                nxt = upload(next(it))                  # prefetch: overlaps this pair's PartI
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            r = self.register(fa, fb, ka, kb)
+            if not hasattr(self, "_res_pin"):
+                self._res_pin = [torch.empty((2, 3, 4), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            host = self._res_pin[n & 1]
+            host.copy_(torch.stack([r["T_c"], r["T_o"]]), non_blocking=True)
+            dv = torch.cuda.Event()
+            dv.record(main)
+            if pending is not None:
+                yield finish(pending)
+            pending = (host, dv, r["M"])
+            n += 1
+        if pending is not None:
+            yield finish(pending)
+
     def register_host(self, featA, featB, kpsA, kpsB):
         """numpy in (feat [K,32,60] f32, kps [K,3] f64) -> numpy transforms out; staging + H2D + D2H inside."""
         return self.register_pinned(*self.pin(featA, featB, kpsA, kpsB))
