@@ -86,6 +86,69 @@ __device__ __forceinline__ void store_split(unsigned short* __restrict__ oh, uns
     ol[o] = __bfloat16_as_ushort(l);
 }
 
+// Epilogue of the two-product kernel.  Warp (q = warp % 4, H = (warp - 4) / 4) owns channels q*32.. (its TMEM lane quadrant)
+// and coefficient columns 32H..32H+31 (H = 1: 28 valid ones).  Software pipelined: iteration `it` runs the pointwise stage of
+// tile `it` (accumulator 1 -> K-major image for product 2) and THEN the stores of tile `it - 1` (accumulator 2), so the round
+// trip through the product-2 issuer is hidden behind the previous tile's stores.  H and C are compile-time: every store is
+// base register + immediate, no per-element predicates.  Bias and the folded BN (scale, shift) are mandatory here.
+template <int H, int C, int NACC1>
+__device__ __forceinline__ void two_epilogue(const XtArgs& p, XtBars* bars, uint8_t* mids, uint32_t tmem_base, uint32_t acc2_col, int q, int lane) {
+    constexpr int NV = H == 0 ? 32 : YG - 32;            // valid coefficient columns in this half
+    constexpr int cblocks = C / XCH;
+    const int cl = q * 32 + lane;
+    const uint32_t lane_off = ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * H);
+    unsigned short* oh_prev = nullptr;
+    unsigned short* ol_prev = nullptr;
+    int it = 0;
+    auto store_prev = [&](int pit) {
+        const int e = pit & 1;
+        uint32_t v[32];
+        mbar_wait(&bars->acc2_full[e], (uint32_t)(pit >> 1) & 1u);
+        tc_fence_after();
+        tmem_ld32_nowait(tmem_base + acc2_col + e * 64 + lane_off, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        tc_fence_before();       // orders these TMEM reads before this thread's next mid_full arrive (-> product 2 may overwrite)
+        unsigned short* oh = oh_prev + (size_t)(32 * H) * C;
+        unsigned short* ol = ol_prev + (size_t)(32 * H) * C;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) store_split(oh, ol, (size_t)m * C, __uint_as_float(v[m]));
+    };
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const int e = it & 1;
+        const int b = tile / cblocks, cb = (tile - b * cblocks) * XCH;
+        const int c = cb + cl;
+        const float bias = __ldg(p.bias + c), sc = __ldg(p.scale + c), sh = __ldg(p.shift + c);
+        const int a = it % NACC1;
+        mbar_wait(&bars->acc1_full[a], (uint32_t)(it / NACC1) & 1u);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32_nowait(tmem_base + a * 64 + lane_off, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&bars->acc1_empty[a]);               // this thread's part of accumulator 1 is in registers
+#pragma unroll
+        for (int m = 0; m < 32; ++m)
+            v[m] = m < NV ? __float_as_uint(fmaxf(fmaf(__uint_as_float(v[m]) + bias, sc, sh), 0.f)) : 0u;
+        // row `cl` of the K-major image: this thread's 32 values = chunks 4H..4H+3 of the 128-byte row (hi and lo)
+        uint8_t* md = mids + e * 2 * A2_TILE + cl * 128;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hi[i] = pack2(__uint_as_float(v[8 * jj + 2 * i]), __uint_as_float(v[8 * jj + 2 * i + 1]), lo[i]);
+            const uint32_t o = ((uint32_t)(4 * H + jj) ^ (uint32_t)(cl & 7)) << 4;
+            *reinterpret_cast<uint4*>(md + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(md + A2_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the K-major image (generic stores) -> UMMA
+        mbar_arrive(&bars->mid_full[e]);
+        if (it > 0) store_prev(it - 1);
+        oh_prev = p.out_hi + (size_t)b * YG * C + c;     // (b, m = 0, c); row m is at + m * C (immediate offsets)
+        ol_prev = p.out_lo + (size_t)b * YG * C + c;
+    }
+    if (it > 0) store_prev(it - 1);
+}
+
 template <bool TWO, bool RES, int C>
 __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const XtArgs p) {
     static_assert(!(TWO && RES), "the two-product kernel carries no shortcut tile");
@@ -223,72 +286,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
             }
         }
     } else if constexpr (TWO) {
-        // ================= epilogue, two products: all eight warps work on EVERY tile =================
-        // Warp (q = warp % 4, h = (warp - 4) / 4) owns channels q*32.. (its TMEM lane quadrant) and coefficient columns
-        // 32h..32h+31.  Software pipelined: iteration `it` runs the pointwise stage of tile `it` (accumulator 1 -> K-major image
-        // for product 2) and THEN the stores of tile `it - 1` (accumulator 2), so the round trip through the MMA issuer
-        // (image -> product 2 -> commit) is hidden behind the previous tile's stores instead of stalling the warp.
-        const int h = (warp - 4) >> 2;
-        const int q = warp & 3;
-        const int cl = q * 32 + lane;
-        const uint32_t lane_off = ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * h);
-        const bool act = p.scale != nullptr;
-        unsigned short* oh_prev = nullptr;
-        unsigned short* ol_prev = nullptr;
-        int it = 0;
-        auto store_prev = [&](int pit) {
-            const int e = pit & 1;
-            uint32_t v[32];
-            mbar_wait(&bars->acc2_full[e], (uint32_t)(pit >> 1) & 1u);
-            tc_fence_after();
-            tmem_ld32_nowait(tmem_base + ACC2_COL + e * 64 + lane_off, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            tc_fence_before();       // orders these TMEM reads before this thread's next mid_full arrive (-> product 2 may overwrite)
-#pragma unroll
-            for (int m = 0; m < 32; ++m)
-                if (32 * h + m < YG) store_split(oh_prev, ol_prev, (size_t)(32 * h + m) * C, __uint_as_float(v[m]));
-        };
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-            const int e = it & 1;
-            const int b = tile / cblocks, cb = (tile - b * cblocks) * XCH;
-            const int c = cb + cl;
-            const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
-            const float sc = act ? __ldg(p.scale + c) : 1.f, sh = act ? __ldg(p.shift + c) : 0.f;
-            const int a = it % NACC1;
-            mbar_wait(&bars->acc1_full[a], (uint32_t)(it / NACC1) & 1u);
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32_nowait(tmem_base + a * 64 + lane_off, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(&bars->acc1_empty[a]);               // this thread's part of accumulator 1 is in registers
-#pragma unroll
-            for (int m = 0; m < 32; ++m) {
-                float x = 0.f;
-                if (32 * h + m < YG) {
-                    x = __uint_as_float(v[m]) + bias;
-                    if (act) x = fmaxf(fmaf(x, sc, sh), 0.f);
-                }
-                v[m] = __float_as_uint(x);
-            }
-            // row `cl` of the K-major image: this thread's 32 values = chunks 4h..4h+3 of the 128-byte row (hi and lo)
-            uint8_t* md = mids + e * 2 * A2_TILE;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) hi[i] = pack2(__uint_as_float(v[8 * jj + 2 * i]), __uint_as_float(v[8 * jj + 2 * i + 1]), lo[i]);
-                const uint32_t o = cl * 128 + (((uint32_t)(4 * h + jj) ^ (uint32_t)(cl & 7)) << 4);
-                *reinterpret_cast<uint4*>(md + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(md + A2_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the K-major image (generic stores) -> UMMA
-            mbar_arrive(&bars->mid_full[e]);
-            if (it > 0) store_prev(it - 1);
-            oh_prev = p.out_hi + (size_t)b * YG * C + c;     // (b, m = 0, c); row m is at + m * C (immediate offsets)
-            ol_prev = p.out_lo + (size_t)b * YG * C + c;
-        }
-        if (it > 0) store_prev(it - 1);
+        // ================= epilogue, two products: all eight warps work on EVERY tile (two_epilogue below) =================
+        if (warp < 8) two_epilogue<0, C, NACC1>(p, bars, mids, tmem_base, ACC2_COL, warp & 3, lane);
+        else two_epilogue<1, C, NACC1>(p, bars, mids, tmem_base, ACC2_COL, warp & 3, lane);
     } else {
         // ================= epilogue sets, one product: warps 4-7 take even local tiles, warps 8-11 odd ones =================
         const int e = (warp - 4) >> 2;
@@ -361,7 +361,7 @@ int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int 
     XtArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const unsigned short*)m1_hi, (const unsigned short*)m1_lo,
              (const unsigned short*)m2_hi, (const unsigned short*)m2_lo, bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo,
              B, C, B * (C / XCH), 0};
-    if (m2_hi) return xt_launch<true, false, 512>(ctx, p, st);
+    if (m2_hi) { YARG(bias && scale && shift); return xt_launch<true, false, 512>(ctx, p, st); }
     if (resid) return xt_launch<false, true, 256>(ctx, p, st);
     return xt_launch<false, false, 256>(ctx, p, st);
 }
