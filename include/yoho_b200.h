@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YOHO_ABI_VERSION 1
+#define YOHO_ABI_VERSION 2
 #define YOHO_G 60      /* group order */
 #define YOHO_TAPS 13   /* group-convolution kernel support */
 #define YOHO_F 32      /* descriptor channels */
@@ -96,25 +96,33 @@ int yoho_ctx_destroy(yoho_ctx* ctx);
 int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w);
 int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w);
 
-/* Group-Fourier form of the two wide PartI layers (implementation 3).  F_host: orthogonal 60x60 transform, row m = Fourier
+/* Group-Fourier form of the PartI layers (implementation 3).  F_host: orthogonal 60x60 transform, row m = Fourier
  * coefficient (irrep, l, j), column g = group element (yoho_b200/fourier.py).  Per real irrep (dims 1,3,3,4,5): the weights of
  * PartI layer 2 (w_a_host [d][256][d*512]) and layer 3 (w_b_host [d][512][d*256]) as d-tap gather-GEMM weights with column
- * n = i*O + o, the input-row table idx_host[j*d + l] and the output-row table omap_host[j*d + i]. */
+ * n = i*O + o, the input-row table idx_host[j*d + l] and the output-row table omap_host[j*d + i].
+ * Optional (both or neither; NULL keeps layers 1 and 4 as direct 13-tap convolutions): layer 1 (w_in_host [d][32][d*256]) and
+ * layer 4 (w_out_host [d][256][d*32]) in the same form — the whole stack then stays in the Fourier domain between the
+ * BatchNorm/ReLU points, including the shortcut of the residual block (the transform is linear). */
 typedef struct {
     int d, off;
     const float* w_a_host;
     const float* w_b_host;
     const int32_t* idx_host;
     const int32_t* omap_host;
+    const float* w_in_host;
+    const float* w_out_host;
 } yoho_fourier_irrep;
 int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n_irreps, const yoho_fourier_irrep* irreps);
 
 /* Implementation of the group-convolution layers: 0 = FP32 SIMT (default), 1 = tcgen05 split-BF16,
  * 2 = tcgen05 split-BF16 with the small (lo) products in a separate TMEM accumulator (shorter rounding chain),
- * 3 = as 2, with PartI layers 2 and 3 evaluated in the group-Fourier domain (needs yoho_part1_load_fourier). */
+ * 3 = as 2, with PartI layers 2 and 3 — and, when their weights were loaded, layers 1 and 4 — evaluated in the
+ * group-Fourier domain (needs yoho_part1_load_fourier). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
-/* Tuning knobs of the tensor-core kernel (experiments; defaults are the measured best).  key 0 = producer flags. */
+/* Tuning knobs (experiments; defaults are the measured best).  key 0 = flag word: 1, 2 = producer protocol / lane map of the
+ * tensor-core GEMM; 4, 8, 32, 64, 128 = older transform kernels (FP32 SIMT, block-tiled / single-buffered warp-MMA); 16 = one
+ * launch per irrep; 256 = tcgen05 transform kernel (default on); 512 = keep PartI layers 1 and 4 as direct convolutions. */
 int yoho_set_tuning(yoho_ctx* ctx, int key, int value);
 
 /* A1-A6 — PartI_test.forward (utils/network.py:86-105,140-147) on B keypoints.

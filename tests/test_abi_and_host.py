@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.yoho_abi_version() == 1
+    assert lib.yoho_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")

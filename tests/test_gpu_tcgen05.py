@@ -173,8 +173,10 @@ def test_fourier_transform_kernels_agree(engine, tables):
         e = engine.part1(x)
         engine.set_tuning(0, 3 | 128)        # 12 single-buffered warps per CTA
         f = engine.part1(x)
-        engine.set_tuning(0, 3 | 256)        # tcgen05 transform kernel (the default)
+        engine.set_tuning(0, 3 | 256)        # the default: tcgen05 transform kernel, all four layers in the Fourier domain
         g = engine.part1(x)
+        engine.set_tuning(0, 3 | 256 | 512)  # tcgen05 transform kernel, layers 1 and 4 as direct convolutions
+        h = engine.part1(x)
         torch.cuda.synchronize()
     finally:
         engine.set_tuning(0, engine.DEFAULT_TUNING)
@@ -184,7 +186,11 @@ def test_fourier_transform_kernels_agree(engine, tables):
     e1, _ = _report("fourier mma-xf vs oracle", _np(a["eqv"]), ref["eqv"].numpy())
     e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
     e3, _ = _report("fourier tcgen05-xf vs oracle", _np(g["eqv"]), ref["eqv"].numpy())
-    e4, _ = _report("fourier tcgen05-xf vs mma-xf", _np(g["eqv"]), _np(a["eqv"]))
-    assert e1 <= DESC_TOL and e2 <= DESC_TOL and e3 <= DESC_TOL and e4 <= 2e-5
+    e4, _ = _report("fourier tcgen05-xf (layers 2+3) vs mma-xf", _np(h["eqv"]), _np(a["eqv"]))
+    e5, _ = _report("all-Fourier vs oracle", _np(g["eqv"]), ref["eqv"].numpy())
+    _report("all-Fourier inv vs oracle", _np(g["inv"]), ref["inv"].numpy())
+    e6, _ = _report("tcgen05-xf (layers 2+3) vs oracle", _np(h["eqv"]), ref["eqv"].numpy())
+    assert e1 <= DESC_TOL and e2 <= DESC_TOL and e3 <= DESC_TOL and e4 <= 2e-5 and e5 <= DESC_TOL and e6 <= DESC_TOL
+    assert float(np.abs(_np(g["inv"]) - ref["inv"].numpy()).max()) <= DESC_TOL
     assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], c2["eqv"]) and torch.equal(a["eqv"], d["eqv"])
     assert torch.equal(a["eqv"], e["eqv"]) and torch.equal(a["eqv"], f["eqv"])

@@ -30,7 +30,7 @@ def child(flags):
     print(f"flags={flags}: max|eqv - default| = {d:.3e}  (ref max {a.abs().max().item():.3f})", flush=True)
     x5, _ = synth.make_fragment(5000, 7)
     xd = torch.from_numpy(x5).to(eng.device)
-    for f in (3, flags):
+    for f in (3, 3 | 256 | 512, flags):
         eng.set_tuning(0, f)
         for _ in range(2):
             eng.part1(xd)

@@ -35,7 +35,8 @@ class yoho_part2_weights(ctypes.Structure):
 
 class yoho_fourier_irrep(ctypes.Structure):
     _fields_ = [("d", ctypes.c_int), ("off", ctypes.c_int), ("w_a_host", _c_f), ("w_b_host", _c_f),
-                ("idx_host", ctypes.POINTER(ctypes.c_int32)), ("omap_host", ctypes.POINTER(ctypes.c_int32))]
+                ("idx_host", ctypes.POINTER(ctypes.c_int32)), ("omap_host", ctypes.POINTER(ctypes.c_int32)),
+                ("w_in_host", _c_f), ("w_out_host", _c_f)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/yoho_b200.h

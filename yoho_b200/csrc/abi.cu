@@ -134,8 +134,11 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     for (GBn* b : bns) free_bn(*b);
     cudaFree(c->d_rot); cudaFree(c->d_rot32); cudaFree(c->d_perm); cudaFree(c->d_perm_t);
     cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one); cudaFree(c->d_idx_ident);
-    for (int r = 0; r < 8; ++r) { free_layer(c->p1f_a[r]); free_layer(c->p1f_b[r]); cudaFree(c->d_fidx[r]); cudaFree(c->d_fomap[r]); }
-    cudaFree(c->d_Fg2m); cudaFree(c->d_Fm2g);
+    for (int r = 0; r < 8; ++r) {
+        free_layer(c->p1f_a[r]); free_layer(c->p1f_b[r]); free_layer(c->p1f_in[r]); free_layer(c->p1f_out[r]);
+        cudaFree(c->d_fidx[r]); cudaFree(c->d_fomap[r]); cudaFree(c->d_fomap_out[r]);
+    }
+    cudaFree(c->d_Fg2m); cudaFree(c->d_Fm2g); cudaFree(c->d_F); cudaFree(c->d_p1_bias31);
     cudaFree(c->d_fwd_hi); cudaFree(c->d_fwd_lo); cudaFree(c->d_inv_hi); cudaFree(c->d_inv_lo);
     cudaFree(c->ws);
     delete c;
@@ -199,6 +202,13 @@ extern "C" int yoho_part1_load(yoho_ctx* ctx, const yoho_part1_weights* w) {
         if ((rc = gconv_tc_pack(ctx, L, wc))) return rc;
     }
     ctx->p1_in.prof_class = 0; ctx->p1_a.prof_class = 1; ctx->p1_b.prof_class = 2; ctx->p1_out.prof_class = 3;
+    {   // bias of the residual block's output plus the bias of its identity shortcut (all-Fourier path: the shortcut travels as
+        // Fourier coefficients without its bias)
+        std::vector<float> b31(256);
+        for (int o = 0; o < 256; ++o) b31[o] = w->conv_b.bias_host[o] + w->conv_in.bias_host[o];
+        cudaFree(ctx->d_p1_bias31); ctx->d_p1_bias31 = nullptr;
+        if ((rc = upload(&ctx->d_p1_bias31, b31))) return rc;
+    }
     ctx->has_p1 = true;
     return YOHO_OK;
 }
@@ -207,13 +217,18 @@ extern "C" int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n
     YARG(ctx && F_host && irreps && n_irreps >= 1 && n_irreps <= 8);
     YCHECK(cudaSetDevice(ctx->device));
     ctx->has_p1f = false;
+    ctx->has_p1f_io = false;
     for (int r = 0; r < 8; ++r) {
-        free_layer(ctx->p1f_a[r]); free_layer(ctx->p1f_b[r]);
-        cudaFree(ctx->d_fidx[r]); cudaFree(ctx->d_fomap[r]);
-        ctx->d_fidx[r] = ctx->d_fomap[r] = nullptr;
+        free_layer(ctx->p1f_a[r]); free_layer(ctx->p1f_b[r]); free_layer(ctx->p1f_in[r]); free_layer(ctx->p1f_out[r]);
+        cudaFree(ctx->d_fidx[r]); cudaFree(ctx->d_fomap[r]); cudaFree(ctx->d_fomap_out[r]);
+        ctx->d_fidx[r] = ctx->d_fomap[r] = ctx->d_fomap_out[r] = nullptr;
     }
-    cudaFree(ctx->d_Fg2m); cudaFree(ctx->d_Fm2g);
-    ctx->d_Fg2m = ctx->d_Fm2g = nullptr;
+    cudaFree(ctx->d_Fg2m); cudaFree(ctx->d_Fm2g); cudaFree(ctx->d_F);
+    ctx->d_Fg2m = ctx->d_Fm2g = ctx->d_F = nullptr;
+    {
+        std::vector<float> Fv(F_host, F_host + YG * YG);
+        if (int rc0 = upload(&ctx->d_F, Fv)) return rc0;
+    }
     std::vector<float> g2m(YG * 64, 0.f), m2g(YG * 64, 0.f);
     for (int m = 0; m < YG; ++m)
         for (int g = 0; g < YG; ++g) { g2m[g * 64 + m] = F_host[m * YG + g]; m2g[m * 64 + g] = F_host[m * YG + g]; }
@@ -237,10 +252,36 @@ extern "C" int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n
         if ((rc = upload((unsigned short**)&ctx->d_inv_hi, ih))) return rc;
         if ((rc = upload((unsigned short**)&ctx->d_inv_lo, il))) return rc;
     }
-    int total = 0;
+    int total = 0, n_io = 0;
     for (int r = 0; r < n_irreps; ++r) {
         const yoho_fourier_irrep& ir = irreps[r];
         YARG(ir.d >= 1 && ir.d <= 5 && ir.w_a_host && ir.w_b_host && ir.idx_host && ir.omap_host);
+        YARG((ir.w_in_host == nullptr) == (ir.w_out_host == nullptr));
+        if (ir.w_in_host) {
+            ++n_io;
+            // layer 1: 32 -> d*256, d taps
+            GLayer& Li = ctx->p1f_in[r];
+            Li.cin = 32; Li.cout = ir.d * 256; Li.taps = ir.d; Li.tc_dense = 1; Li.prof_class = 0;
+            std::vector<float> wi(ir.w_in_host, ir.w_in_host + (size_t)ir.d * 32 * Li.cout), zbi(Li.cout, 0.f);
+            if ((rc = upload(&Li.bias, zbi))) return rc;
+            if ((rc = gconv_tc_pack(ctx, Li, wi))) return rc;
+            YARG(Li.w_hi && Li.w_lo);
+            // layer 4: 256 -> d*32, d taps, columns zero-padded to one 256-wide tile; output-row table [j][8 column groups]
+            GLayer& Lo = ctx->p1f_out[r];
+            Lo.cin = 256; Lo.cout = 256; Lo.taps = ir.d; Lo.tc_dense = 1; Lo.prof_class = 3;
+            const int nv = ir.d * 32;
+            std::vector<float> wo((size_t)ir.d * 256 * 256, 0.f), zbo(256, 0.f);
+            for (int l = 0; l < ir.d; ++l)
+                for (int c = 0; c < 256; ++c)
+                    memcpy(&wo[((size_t)l * 256 + c) * 256], ir.w_out_host + ((size_t)l * 256 + c) * nv, nv * sizeof(float));
+            if ((rc = upload(&Lo.bias, zbo))) return rc;
+            if ((rc = gconv_tc_pack(ctx, Lo, wo))) return rc;
+            YARG(Lo.w_hi && Lo.w_lo);
+            std::vector<int> om8(ir.d * 8, 0);
+            for (int j = 0; j < ir.d; ++j)
+                for (int i = 0; i < ir.d; ++i) om8[j * 8 + i] = ir.omap_host[j * ir.d + i];
+            if ((rc = upload(&ctx->d_fomap_out[r], om8))) return rc;
+        }
         total += ir.d * ir.d;
         ctx->fd[r] = ir.d;
         std::vector<int> idx(ir.idx_host, ir.idx_host + ir.d * ir.d), om(ir.omap_host, ir.omap_host + ir.d * ir.d);
@@ -257,9 +298,10 @@ extern "C" int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n
             YARG(L.w_hi && L.w_lo);
         }
     }
-    YARG(total == YG);
+    YARG(total == YG && (n_io == 0 || n_io == n_irreps));
     ctx->nf = n_irreps;
     ctx->has_p1f = true;
+    ctx->has_p1f_io = n_io == n_irreps;
     return YOHO_OK;
 }
 

@@ -79,6 +79,13 @@ struct yoho_ctx {
     GLayer p1f_a[8], p1f_b[8];
     int* d_fidx[8] = {nullptr};
     int* d_fomap[8] = {nullptr};
+    // ... and layers 1 and 4 (optional): 32 -> d*256 and 256 -> d*32 (the latter zero-padded to 256 columns, output-row table
+    // with 8 column groups of 32 per GEMM row)
+    bool has_p1f_io = false;
+    GLayer p1f_in[8], p1f_out[8];
+    int* d_fomap_out[8] = {nullptr};
+    float* d_p1_bias31 = nullptr;   // [256] bias of layer 3 + bias of layer 1 (the shortcut's bias, added in the group domain)
+    float* d_F = nullptr;           // [60 m][60 g] FP32 (input transform and the finalize kernel's inverse transform)
     float* d_Fg2m = nullptr;        // [60][64]: Fg2m[g][m] = F[m][g]   (forward transform as M1[k=g][m])
     float* d_Fm2g = nullptr;        // [60][64]: Fm2g[m][g] = F[m][g]   (inverse transform as M1[k=m][g])
     // the same two matrices for the mma.sync transform kernel: [64 out][64 in] bf16 hi/lo (row = OUTPUT index)

@@ -446,7 +446,7 @@ constexpr size_t xm_smem() { return (size_t)(4 * 64 * MP + 6 * 64 * (XC + 8)) * 
 
 int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
-                       void* out_hi, void* out_lo, cudaStream_t st);
+                       void* out_hi, void* out_lo, cudaStream_t st, const void* in2_hi, const void* in2_lo);
 bool group_transform_tc_supported(int C, bool two, bool res);
 
 int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
@@ -454,7 +454,7 @@ int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int
                         void* out_hi, void* out_lo, cudaStream_t st) {
     YARG(C % 128 == 0 && B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo);
     if ((ctx->tc_flags & 256) && group_transform_tc_supported(C, m2_hi != nullptr, resid != nullptr))      // tcgen05 variant (fourier_tc.cu)
-        return group_transform_tc(ctx, in_hi, in_lo, B, C, m1_hi, m1_lo, m2_hi, m2_lo, bias, resid, scale, shift, out_hi, out_lo, st);
+        return group_transform_tc(ctx, in_hi, in_lo, B, C, m1_hi, m1_lo, m2_hi, m2_lo, bias, resid, scale, shift, out_hi, out_lo, st, nullptr, nullptr);
     XmArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const __nv_bfloat16*)m1_hi, (const __nv_bfloat16*)m1_lo, (const __nv_bfloat16*)m2_hi, (const __nv_bfloat16*)m2_lo,
              bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo, B, C};
     if ((ctx->tc_flags & (8 | 32)) == 0) {   // default: warp-autonomous 32-channel tiles, one CTA per SM

@@ -26,6 +26,8 @@ constexpr int NACC1_MAX = 4;
 struct XtArgs {
     const unsigned short* in_hi;      // [B][60][C] bf16 hi/lo split of the input
     const unsigned short* in_lo;
+    const unsigned short* in2_hi;     // FS: a second input of the same shape, ADDED to the first before product 1 (a shortcut kept
+    const unsigned short* in2_lo;     //     in the Fourier domain: the transform is linear, so its images simply join the accumulation)
     const unsigned short* m1_hi;      // [64 m][64 k] bf16: M1^T, zero padded
     const unsigned short* m1_lo;
     const unsigned short* m2_hi;      // nullable
@@ -63,8 +65,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, uint32_t& lo) {
 // RES: a [60][128] FP32 shortcut tile rides in the stage ring next to the operand images (the epilogue reads it from shared
 // memory, one conflict-free word per lane, instead of 60 dependent global loads per thread).  C is a template parameter so
 // that every store address is base + immediate.
-template <bool RES>
-struct StageBytes { static constexpr int value = 2 * D_TILE + (RES ? YG * XCH * 4 : 0); };
+template <bool RES, bool FS>
+struct StageBytes { static constexpr int value = (FS ? 4 : 2) * D_TILE + (RES ? YG * XCH * 4 : 0); };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -149,14 +151,16 @@ __device__ __forceinline__ void two_epilogue(const XtArgs& p, XtBars* bars, uint
     if (it > 0) store_prev(it - 1);
 }
 
-template <bool TWO, bool RES, int C>
+template <bool TWO, bool RES, bool FS, int C>
 __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const XtArgs p) {
-    static_assert(!(TWO && RES), "the two-product kernel carries no shortcut tile");
-    constexpr int STAGE = StageBytes<RES>::value;
+    static_assert(!(TWO && RES), "the two-product kernel carries no FP32 shortcut tile (its shortcut is a Fourier-domain input: FS)");
+    static_assert(!FS || TWO, "FS is a variant of the two-product kernel");
+    constexpr int STAGE = StageBytes<RES, FS>::value;
+    constexpr int IMGS = FS ? 4 : 2;                     // operand images per stage
     // The two-product kernel is a longer pipeline (pointwise stage + second product between load and store): product 1 runs up
     // to four tiles ahead of the epilogue into four TMEM accumulators, so a stage is released as soon as its tile has LANDED
     // and been multiplied — the load ring (4 stages) stays in flight independently of the epilogue's progress.
-    constexpr int NST = TWO ? 4 : 3;
+    constexpr int NST = FS ? 2 : TWO ? 4 : 3;            // FS: two 64 KB stages (same bytes in flight as four 32 KB ones)
     constexpr int NACC1 = TWO ? 4 : 2;
     constexpr uint32_t ACC2_COL = NACC1 * 64;
     constexpr uint32_t TMEM_COLS = TWO ? 512 : 128;
@@ -180,9 +184,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
         }
     }
     // k rows 60..63 of every data image stay zero: rows 4..7 of the k-group-7 atom of both channel blocks
-    for (int i = threadIdx.x; i < NST * 2 * 2 * 32; i += XT_THREADS) {
+    for (int i = threadIdx.x; i < NST * IMGS * 2 * 32; i += XT_THREADS) {
         const int img = i / 64, rem = i % 64, nb = rem / 32, q = rem % 32;          // 32 x 16 B = rows 4..7 of one atom
-        *reinterpret_cast<uint4*>(stages + (img >> 1) * STAGE + (img & 1) * D_TILE + (nb * 8 + 7) * 1024 + 512 + q * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(stages + (img / IMGS) * STAGE + (img % IMGS) * D_TILE + (nb * 8 + 7) * 1024 + 512 + q * 16) = make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -221,6 +225,10 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
                     const size_t g = base + (size_t)k * C + j16 * 8;
                     cp_async16(st + o, p.in_hi + g, true);
                     cp_async16(st + D_TILE + o, p.in_lo + g, true);
+                    if (FS) {
+                        cp_async16(st + 2 * D_TILE + o, p.in2_hi + g, true);
+                        cp_async16(st + 3 * D_TILE + o, p.in2_lo + g, true);
+                    }
                 }
             }
             if (RES) {
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
                 const uint8_t* st = stages + stage * STAGE;
                 // MN-major operand: 64-channel blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO)
                 const uint64_t ah = umma_desc_mn(st, 8192u, 1024u), al = umma_desc_mn(st + D_TILE, 8192u, 1024u);
+                const uint64_t a2h = umma_desc_mn(st + 2 * D_TILE, 8192u, 1024u), a2l = umma_desc_mn(st + 3 * D_TILE, 8192u, 1024u);
                 const uint32_t d = tmem_base + a * 64;
 #pragma unroll
                 for (uint32_t ks = 0; ks < 4; ++ks) {
@@ -257,6 +266,11 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
                     tc_mma(d, ah + aadv, b1h + badv, IDESC_MN, ks ? 1u : 0u);
                     tc_mma(d, al + aadv, b1h + badv, IDESC_MN, 1u);
                     tc_mma(d, ah + aadv, b1l + badv, IDESC_MN, 1u);
+                    if (FS) {
+                        tc_mma(d, a2h + aadv, b1h + badv, IDESC_MN, 1u);
+                        tc_mma(d, a2l + aadv, b1h + badv, IDESC_MN, 1u);
+                        tc_mma(d, a2h + aadv, b1l + badv, IDESC_MN, 1u);
+                    }
                 }
                 tc_commit(&bars->empty[stage]);
                 tc_commit(&bars->acc1_full[a]);
@@ -335,14 +349,15 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     }
 }
 
-template <bool TWO, bool RES>
-constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)(TWO ? 4 : 3) * StageBytes<RES>::value + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
+template <bool TWO, bool RES, bool FS>
+constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)(FS ? 2 : TWO ? 4 : 3) * StageBytes<RES, FS>::value + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
+static_assert(xt_smem<true, false, true>() <= 232448 && xt_smem<true, false, false>() <= 232448 && xt_smem<false, true, false>() <= 232448, "227 KB per CTA");
 
-template <bool TWO, bool RES, int C>
+template <bool TWO, bool RES, bool FS, int C>
 int xt_launch(yoho_ctx* ctx, const XtArgs& p, cudaStream_t st) {
-    YCHECK(cudaFuncSetAttribute(group_transform_tc_kernel<TWO, RES, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xt_smem<TWO, RES>()));
+    YCHECK(cudaFuncSetAttribute(group_transform_tc_kernel<TWO, RES, FS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xt_smem<TWO, RES, FS>()));
     const int grid = p.tiles < ctx->num_sms ? p.tiles : ctx->num_sms;
-    group_transform_tc_kernel<TWO, RES, C><<<grid, XT_THREADS, xt_smem<TWO, RES>(), st>>>(p);
+    group_transform_tc_kernel<TWO, RES, FS, C><<<grid, XT_THREADS, xt_smem<TWO, RES, FS>(), st>>>(p);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
@@ -350,18 +365,25 @@ int xt_launch(yoho_ctx* ctx, const XtArgs& p, cudaStream_t st) {
 
 }  // namespace
 
-// The three shapes PartI uses are instantiated: forward only (C=256), inverse -> activation -> forward (C=512), inverse +
-// shortcut -> activation (C=256).  Returns YOHO_ERR_ARG-free `-1` for any other shape: the caller falls back to the warp-MMA kernel.
-bool group_transform_tc_supported(int C, bool two, bool res) { return (C == 256 && !two) || (C == 512 && two && !res); }
+// The shapes PartI uses are instantiated: forward only (C=256), inverse -> activation -> forward (C=256, 512), the latter with a
+// Fourier-domain shortcut input (C=256), inverse + FP32 shortcut -> activation (C=256).  The caller falls back to the warp-MMA
+// kernel for any other shape.
+bool group_transform_tc_supported(int C, bool two, bool res) { return (C == 256 && !(two && res)) || (C == 512 && two && !res); }
 
 int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
-                       void* out_hi, void* out_lo, cudaStream_t st) {
+                       void* out_hi, void* out_lo, cudaStream_t st, const void* in2_hi, const void* in2_lo) {
     YARG(B > 0 && in_hi && in_lo && m1_hi && m1_lo && out_hi && out_lo && group_transform_tc_supported(C, m2_hi != nullptr, resid != nullptr));
-    XtArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const unsigned short*)m1_hi, (const unsigned short*)m1_lo,
+    YARG((in2_hi == nullptr) == (in2_lo == nullptr) && (!in2_hi || (m2_hi && C == 256)));
+    XtArgs p{(const unsigned short*)in_hi, (const unsigned short*)in_lo, (const unsigned short*)in2_hi, (const unsigned short*)in2_lo,
+             (const unsigned short*)m1_hi, (const unsigned short*)m1_lo,
              (const unsigned short*)m2_hi, (const unsigned short*)m2_lo, bias, resid, scale, shift, (unsigned short*)out_hi, (unsigned short*)out_lo,
              B, C, B * (C / XCH), 0};
-    if (m2_hi) { YARG(bias && scale && shift); return xt_launch<true, false, 512>(ctx, p, st); }
-    if (resid) return xt_launch<false, true, 256>(ctx, p, st);
-    return xt_launch<false, false, 256>(ctx, p, st);
+    if (m2_hi) {
+        YARG(bias && scale && shift);
+        if (in2_hi) return xt_launch<true, false, true, 256>(ctx, p, st);
+        return C == 512 ? xt_launch<true, false, false, 512>(ctx, p, st) : xt_launch<true, false, false, 256>(ctx, p, st);
+    }
+    if (resid) return xt_launch<false, true, false, 256>(ctx, p, st);
+    return xt_launch<false, false, false, 256>(ctx, p, st);
 }

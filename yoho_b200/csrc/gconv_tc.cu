@@ -63,6 +63,9 @@ struct TcGroup {
     const int* idx;              // [Jout][taps] input-row table
     const int* omap;             // [Jout][Cout/ogroup] output-row table (nullptr: plain [rows][Cout] output)
     int Jout, taps, Cout, nkb, m_total, n_tiles, tile_begin, idx_off, omap_off;
+    int n_valid;                 // columns >= n_valid are not written
+    int n_mma;                   // UMMA N of this GEMM (multiple of 16, <= BN): rows n_mma..BN-1 of its W tiles are zero padding and are
+                                 // neither fetched nor multiplied (PartI layer 4 in the group-Fourier domain: d*32 of 256 columns)
 };
 
 struct TcArgs {
@@ -80,7 +83,6 @@ struct TcArgs {
     __nv_bfloat16* out_lo;
     const float* scale;
     const float* shift;
-    int n_valid;                 // columns >= n_valid are not written
     int flags;                   // bit0: non-blocking producer completion, bit1: line-per-8-lanes producer mapping
     // remapped output rows (group-Fourier layers): columns are groups of `ogroup`; group i of GEMM row (b,j) is written to
     // row b*out_J + omap[j*n_groups + i] of an [.., ogroup]-wide output.
@@ -267,12 +269,13 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                 const int n_tile = (tile - G.tile_begin) % G.n_tiles;
                 const uint8_t* wh = G.w_hi + (size_t)n_tile * G.nkb * W_TILE;
                 const uint8_t* wl = G.w_lo + (size_t)n_tile * G.nkb * W_TILE;
+                const uint32_t wbytes = (uint32_t)G.n_mma * (BK * 2);       // rows [0, n_mma) of the tile image
                 for (int kb = 0; kb < G.nkb; ++kb) {
                     uint8_t* dst = stage_base + stage * STAGE_BYTES + 2 * A_TILE;
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bars->full[stage], 2 * W_TILE);
-                    bulk_g2s(dst, wh + (size_t)kb * W_TILE, W_TILE, &bars->full[stage]);
-                    bulk_g2s(dst + W_TILE, wl + (size_t)kb * W_TILE, W_TILE, &bars->full[stage]);
+                    mbar_expect_tx(&bars->full[stage], 2 * wbytes);
+                    bulk_g2s(dst, wh + (size_t)kb * W_TILE, wbytes, &bars->full[stage]);
+                    bulk_g2s(dst + W_TILE, wl + (size_t)kb * W_TILE, wbytes, &bars->full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -286,7 +289,10 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 const uint32_t d_lo = SPLIT ? d_tmem + BN : d_tmem;
-                const int nkb = p.grp[find_group(p, tile)].nkb;
+                const TcGroup& G = p.grp[find_group(p, tile)];
+                const int nkb = G.nkb;
+                // instruction descriptor with this GEMM's N (bits 17..22 hold N >> 3)
+                const uint32_t idesc = (IDESC & ~(0x3Fu << 17)) | ((uint32_t)(G.n_mma >> 3) << 17);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
                     if (p.flags & 1) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
@@ -298,9 +304,9 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                     for (uint32_t ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per 16 bf16, in 16-byte units
                         const uint32_t first = (kb | (int)ks) ? 1u : 0u;
-                        tc_mma(d_tmem, a_hi + adv, w_hi + adv, IDESC, first);
-                        tc_mma(d_lo, a_lo + adv, w_hi + adv, IDESC, SPLIT ? first : 1u);
-                        tc_mma(d_lo, a_hi + adv, w_lo + adv, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + adv, w_hi + adv, idesc, first);
+                        tc_mma(d_lo, a_lo + adv, w_hi + adv, idesc, SPLIT ? first : 1u);
+                        tc_mma(d_lo, a_hi + adv, w_lo + adv, idesc, 1u);
                     }
                     tc_commit(&bars->empty[stage]);            // stage reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
                 }
-                if (n0 + cc * 32 < p.n_valid) {       // warp-uniform
+                if (n0 + cc * 32 < G.n_valid) {       // warp-uniform
                     if (has_ep) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] += ep_bias[n0 + cc * 32 + i];
@@ -538,7 +544,6 @@ static void tc_fill_common(TcArgs& p, const GLayer& L, const GConvArgs& a, yoho_
     p.out_raw = a.out_raw; p.out_act = a.out_act;
     p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
     p.scale = a.scale; p.shift = a.shift;
-    p.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
     p.flags = ctx->tc_flags;
     p.ogroup = a.omap ? a.ogroup : L.cout; p.out_J = a.out_J;
 }
@@ -551,6 +556,12 @@ static void tc_fill_group(TcGroup& G, const GLayer& L, const GConvArgs& a, int b
     G.m_total = a.B * a.Jout;
     G.n_tiles = L.cout / bn;
     G.tile_begin = tile_begin; G.idx_off = idx_off; G.omap_off = omap_off;
+    G.n_valid = a.n_valid > 0 ? a.n_valid : L.cout;
+    G.n_mma = bn;
+    if (bn == 256 && G.n_tiles == 1 && G.n_valid < bn) {            // single-tile GEMM with zero-padded columns
+        G.n_mma = ((G.n_valid + 15) / 16) * 16;
+        if (G.n_mma < 32) G.n_mma = 32;
+    }
 }
 
 int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
@@ -577,7 +588,6 @@ int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConv
     TcArgs p;
     tc_fill_common(p, *Ls[0], as[0], ctx);
     p.ngroups = n;
-    p.n_valid = 1 << 30;          // every group writes all of its columns
     int tiles = 0;
     for (int g = 0; g < n; ++g) {
         const GLayer& L = *Ls[g];
@@ -585,7 +595,7 @@ int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConv
         YARG(gconv_tc_eligible(L, a) && tc_tile_n(L) == 256 && a.omap && !a.out_act && !a.resid);
         YARG(L.cin == Ls[0]->cin && a.ogroup == as[0].ogroup && a.act_hi == as[0].act_hi && a.out_hi == as[0].out_hi &&
              a.out_raw == as[0].out_raw && a.B == as[0].B && a.Jin == as[0].Jin && L.cout % a.ogroup == 0);
-        tc_fill_group(p.grp[g], L, a, 256, tiles, g * 32, 160 + g * 32);
+        tc_fill_group(p.grp[g], L, a, 256, tiles, g * 32, 160 + g * 40);   // <= 25 index entries, <= 5 x 8 output-row entries
         tiles += ((p.grp[g].m_total + BM - 1) / BM) * p.grp[g].n_tiles;
     }
     p.total_tiles = tiles;

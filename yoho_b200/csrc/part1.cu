@@ -16,6 +16,9 @@ int group_transform(yoho_ctx* ctx, const float* in, int B, int C, const float* m
 int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                         const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                         void* out_hi, void* out_lo, cudaStream_t st);
+int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
+                       const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
+                       void* out_hi, void* out_lo, cudaStream_t st, const void* in2_hi, const void* in2_lo);
 int gconv_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st);
 void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st);
 void yoho_prof_end(yoho_ctx* ctx, cudaStream_t st);
@@ -128,6 +131,103 @@ __global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restr
     if (t < YF && desc) desc[(size_t)b * YF + t] = numpy_mean60(&e[t][0], 1);
 }
 
+// Input side of the all-Fourier PartI: X0[m][c] = sum_g F[m][g] x[c][g], written as the bf16 hi/lo pair [B][60][32] that the
+// layer-1 per-irrep GEMMs consume.  One CTA (128 threads) per keypoint: thread (c = t % 32, rows m = t / 32 + 4 i).
+__global__ void __launch_bounds__(128) fourier_in_kernel(const float* __restrict__ x, const float* __restrict__ F,
+                                                        unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
+    __shared__ float xs[YF][YG + 1];
+    __shared__ float Fs[YG][YG];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float* src = x + (size_t)b * YF * YG;
+    for (int i = t; i < YF * YG; i += 128) xs[i / YG][i % YG] = src[i];
+    for (int i = t; i < YG * YG; i += 128) Fs[i / YG][i % YG] = __ldg(F + i);
+    __syncthreads();
+    const int c = t & 31;
+    const size_t o = (size_t)b * YG * YF;
+#pragma unroll 1
+    for (int m = t >> 5; m < YG; m += 4) {
+        float acc = 0.f;
+#pragma unroll 12
+        for (int g = 0; g < YG; ++g) acc = fmaf(Fs[m][g], xs[c][g], acc);
+        const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+        hi[o + m * YF + c] = __bfloat16_as_ushort(h);
+        lo[o + m * YF + c] = __bfloat16_as_ushort(__float2bfloat16_rn(acc - __bfloat162float(h)));
+    }
+}
+
+// Output side of the all-Fourier PartI: the layer-4 result arrives as Fourier coefficients Y4 [B][60 m][32 c] (no bias);
+//     e[c][g] = bias4[c] + sum_m F[m][g] Y4[m][c] + x[c][g]
+// followed by the same tail as part1_finalize_kernel (both L2 norms, invariant pool, numpy's pairwise mean_g).
+// One CTA (64 threads) per keypoint; thread g < 60 accumulates its 32 channels in registers.
+__global__ void __launch_bounds__(64) part1_finalize_fourier_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
+                                                                   const float* __restrict__ bias4, const float* __restrict__ x,
+                                                                   float* __restrict__ eqv, float* __restrict__ inv,
+                                                                   float* __restrict__ desc, int B) {
+    __shared__ float Fs[YG][YG];
+    __shared__ __align__(16) float ys[YG][YF];
+    __shared__ float e[YF][YG + 1];
+    __shared__ float invn[YG];
+    __shared__ float red[YF];
+    const int b = blockIdx.x;
+    const int t = threadIdx.x;
+    const float* xs = x + (size_t)b * YF * YG;
+    const float* yb = y4f + (size_t)b * YG * YF;
+    for (int i = t; i < YG * YG; i += 64) Fs[i / YG][i % YG] = __ldg(F + i);
+    for (int i = t; i < YG * YF / 4; i += 64) reinterpret_cast<float4*>(&ys[0][0])[i] = reinterpret_cast<const float4*>(yb)[i];
+    __syncthreads();
+    if (t < YG) {
+        float acc[YF];
+#pragma unroll
+        for (int c = 0; c < YF; ++c) acc[c] = bias4[c];
+#pragma unroll 2
+        for (int m = 0; m < YG; ++m) {
+            const float f = Fs[m][t];
+#pragma unroll
+            for (int c4 = 0; c4 < YF / 4; ++c4) {
+                const float4 y = *reinterpret_cast<const float4*>(&ys[m][c4 * 4]);
+                acc[c4 * 4 + 0] = fmaf(f, y.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(f, y.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(f, y.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(f, y.w, acc[c4 * 4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < YF; ++c) e[c][t] = acc[c];
+    }
+    __syncthreads();
+    for (int i = t; i < YF * YG; i += 64) {
+        const int c = i / YG, g = i % YG;
+        e[c][g] = e[c][g] + xs[i];
+    }
+    __syncthreads();
+    if (t < YG) {
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < YF; ++c) ss = fmaf(e[c][t], e[c][t], ss);
+        invn[t] = fmaxf(sqrtf(ss), 1e-4f);   // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
+    }
+    float m = 0.f;
+    if (t < YF) {
+        float s = 0.f;
+        for (int g = 0; g < YG; ++g) s += e[t][g];
+        m = s / 60.0f;
+        red[t] = m * m;
+    }
+    __syncthreads();
+    if (t < YF && inv) {
+        float ss = 0.f;
+        for (int c = 0; c < YF; ++c) ss += red[c];
+        inv[(size_t)b * YF + t] = m / fmaxf(sqrtf(ss), 1e-4f);
+    }
+    float* out = eqv + (size_t)b * YF * YG;
+    for (int i = t; i < YF * YG; i += 64) {
+        const int c = i / YG, g = i % YG;
+        const float v = e[c][g] / invn[g];
+        e[c][g] = v;
+        out[i] = v;
+    }
+    __syncthreads();
+    if (t < YF && desc) desc[(size_t)b * YF + t] = numpy_mean60(&e[t][0], 1);
+}
+
 __global__ void __launch_bounds__(64) group_mean_kernel(const float* __restrict__ eqv, float* __restrict__ desc, int K) {
     __shared__ float e[YF][YG + 1];
     const int b = blockIdx.x;
@@ -178,6 +278,63 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         unsigned short* a3_hi = (unsigned short*)a3;
         unsigned short* a3_lo = a3_hi + (size_t)n * YG * 256;
         const float* xs = x + (size_t)s * YF * YG;
+        // ---- the whole stack in the group-Fourier domain: per-irrep GEMMs for all four layers, transforms only
+        // at the three BatchNorm/ReLU points, shortcut added as Fourier coefficients.  Needs the tcgen05 transform kernel.
+        if (fourier_on && ctx->has_p1f_io && n >= 128 && (ctx->tc_flags & 256) && !(ctx->tc_flags & (4 | 16 | 512))) {
+            const size_t R = (size_t)n * YG;
+            unsigned short* w16 = (unsigned short*)ctx->ws;
+            unsigned short* X0h = w16;            unsigned short* X0l = X0h + R * 32;
+            unsigned short* Y1h = X0l + R * 32;   unsigned short* Y1l = Y1h + R * 256;
+            unsigned short* X1h = Y1l + R * 256;  unsigned short* X1l = X1h + R * 256;
+            unsigned short* Y2h = X1l + R * 256;  unsigned short* Y2l = Y2h + R * 512;
+            unsigned short* X2h = Y2l + R * 512;  unsigned short* X2l = X2h + R * 512;
+            unsigned short* Y3h = X2l + R * 512;  unsigned short* Y3l = Y3h + R * 256;
+            unsigned short* X3h = Y3l + R * 256;  unsigned short* X3l = X3h + R * 256;
+            float* Y4 = (float*)(X3l + R * 256);
+            fourier_in_kernel<<<n, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
+            ctx->launches++;
+            GConvArgs f{};
+            f.B = n; f.Jin = YG; f.out_J = YG;
+            GConvArgs fs[8];
+            const GLayer* Ls[8];
+            auto layer = [&](const GLayer* Lr, const unsigned short* ih, const unsigned short* il, unsigned short* oh, unsigned short* ol,
+                             float* oraw, int ogroup, bool out4) -> int {
+                for (int q = 0; q < ctx->nf; ++q) {
+                    const int r = ctx->nf - 1 - q;                           // largest irrep first: short tiles make up the tail
+                    f.act_hi = ih; f.act_lo = il; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
+                    f.omap = out4 ? ctx->d_fomap_out[r] : ctx->d_fomap[r]; f.ogroup = ogroup;
+                    f.out_raw = oraw; f.out_hi = oh; f.out_lo = ol;
+                    f.n_valid = out4 ? ctx->fd[r] * 32 : 0;
+                    fs[q] = f; Ls[q] = &Lr[r];
+                }
+                return gconv_forward_grouped(ctx, Ls, fs, ctx->nf, st);
+            };
+            // layer 1 (32 -> 256): Y1 = Fourier coefficients of y1 (without bias: it joins in the group domain below)
+            if (int rc = layer(ctx->p1f_in, X0h, X0l, Y1h, Y1l, nullptr, 256, false)) return rc;
+            // X1 = F relu(BN_a(F^T Y1 + b1))
+            yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 7200.0, st);
+            if (int rc = group_transform_tc(ctx, Y1h, Y1l, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_in.bias, nullptr,
+                                            ctx->p1_bn_a.scale, ctx->p1_bn_a.shift, X1h, X1l, st, nullptr, nullptr)) return rc;
+            yoho_prof_end(ctx, st);
+            if (int rc = layer(ctx->p1f_a, X1h, X1l, Y2h, Y2l, nullptr, 512, false)) return rc;
+            yoho_prof_begin(ctx, 8, 2.0 * n * 512 * 7200.0, st);
+            if (int rc = group_transform_tc(ctx, Y2h, Y2l, n, 512, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_a.bias, nullptr,
+                                            ctx->p1_bn_b.scale, ctx->p1_bn_b.shift, X2h, X2l, st, nullptr, nullptr)) return rc;
+            yoho_prof_end(ctx, st);
+            if (int rc = layer(ctx->p1f_b, X2h, X2l, Y3h, Y3l, nullptr, 256, false)) return rc;
+            // X3 = F relu(BN_o(F^T (Y3 + Y1) + b3 + b1)): the identity shortcut y1 = F^T Y1 + b1 rides along as coefficients
+            yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 7200.0, st);
+            if (int rc = group_transform_tc(ctx, Y3h, Y3l, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->d_p1_bias31, nullptr,
+                                            ctx->p1_bn_out.scale, ctx->p1_bn_out.shift, X3h, X3l, st, Y1h, Y1l)) return rc;
+            yoho_prof_end(ctx, st);
+            // layer 4 (256 -> 32): Fourier coefficients of y4, FP32 [n][60][32]
+            if (int rc = layer(ctx->p1f_out, X3h, X3l, nullptr, nullptr, Y4, 32, true)) return rc;
+            part1_finalize_fourier_kernel<<<n, 64, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+                                                            inv ? inv + (size_t)s * YF : nullptr,
+                                                            desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
+            ctx->launches++;
+            continue;
+        }
         transpose_in_kernel<<<n, 128, 0, st>>>(xs, xt, tc ? xt_hi : nullptr, tc ? xt_lo : nullptr, n);
         ctx->launches++;
         GConvArgs a{};

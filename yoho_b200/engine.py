@@ -62,19 +62,24 @@ class Engine:
             self._load_part1_fourier(_lib._to_numpy_sd(state_dict))
 
     def _load_part1_fourier(self, sd):
-        """Group-Fourier weights of PartI layers 2 and 3 (yoho_b200/fourier.py) for implementation 'tcgen05_fourier'."""
+        """Group-Fourier weights of the four PartI layers (yoho_b200/fourier.py) for implementation 'tcgen05_fourier'."""
         from . import fourier
         T = fourier.build(self.tables.dir if self.tables.dir != _group._PKG_DIR else None)
         blk = "PartI_net.SO3_Conv_layers.0."
         pa = fourier.pack_layer(sd[blk + "comb_layer_in.2.weight"], T)
         pb = fourier.pack_layer(sd[blk + "comb_layer_out.2.weight"], T)
+        pi = fourier.pack_layer(sd["PartI_net.Conv_in.0.weight"], T)
+        po = fourier.pack_layer(sd["PartI_net.Conv_out.comb_layer.2.weight"], T)
         n = len(pa)
         arr = (_lib.yoho_fourier_irrep * n)()
         keep = []
         for r in range(n):
             wa, wb = np.ascontiguousarray(pa[r]["w"]), np.ascontiguousarray(pb[r]["w"])
             idx, om = np.ascontiguousarray(pa[r]["idx"], np.int32), np.ascontiguousarray(pa[r]["omap"], np.int32)
-            keep += [wa, wb, idx, om]
+            wi, wo = np.ascontiguousarray(pi[r]["w"]), np.ascontiguousarray(po[r]["w"])
+            keep += [wa, wb, idx, om, wi, wo]
+            arr[r].w_in_host = wi.ctypes.data_as(_lib._c_f)
+            arr[r].w_out_host = wo.ctypes.data_as(_lib._c_f)
             arr[r].d, arr[r].off = pa[r]["d"], pa[r]["off"]
             arr[r].w_a_host = wa.ctypes.data_as(_lib._c_f)
             arr[r].w_b_host = wb.ctypes.data_as(_lib._c_f)
