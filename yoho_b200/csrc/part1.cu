@@ -132,100 +132,130 @@ __global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restr
 }
 
 // Input side of the all-Fourier PartI: X0[m][c] = sum_g F[m][g] x[c][g], written as the bf16 hi/lo pair [B][60][32] that the
-// layer-1 per-irrep GEMMs consume.  One CTA (128 threads) per keypoint: thread (c = t % 32, rows m = t / 32 + 4 i).
+// layer-1 per-irrep GEMMs consume.  CTAs of 128 threads stride over the keypoints with F^T resident in shared memory; thread
+// (c = t % 32, quarter = t / 32) accumulates the 16 coefficient rows m = 16*quarter .. +15 of its channel in registers (one
+// conflict-free scalar read of x and four broadcast 16-byte reads of F^T per 16 FMAs).
 __global__ void __launch_bounds__(128) fourier_in_kernel(const float* __restrict__ x, const float* __restrict__ F,
                                                         unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
     __shared__ float xs[YF][YG + 1];
-    __shared__ float Fs[YG][YG];
-    const int b = blockIdx.x, t = threadIdx.x;
-    const float* src = x + (size_t)b * YF * YG;
-    for (int i = t; i < YF * YG; i += 128) xs[i / YG][i % YG] = src[i];
-    for (int i = t; i < YG * YG; i += 128) Fs[i / YG][i % YG] = __ldg(F + i);
-    __syncthreads();
-    const int c = t & 31;
-    const size_t o = (size_t)b * YG * YF;
-#pragma unroll 1
-    for (int m = t >> 5; m < YG; m += 4) {
-        float acc = 0.f;
-#pragma unroll 12
-        for (int g = 0; g < YG; ++g) acc = fmaf(Fs[m][g], xs[c][g], acc);
-        const __nv_bfloat16 h = __float2bfloat16_rn(acc);
-        hi[o + m * YF + c] = __bfloat16_as_ushort(h);
-        lo[o + m * YF + c] = __bfloat16_as_ushort(__float2bfloat16_rn(acc - __bfloat162float(h)));
+    __shared__ __align__(16) float Ft[YG][64];           // Ft[g][m] = F[m][g], m padded to 64 with zeros
+    const int t = threadIdx.x;
+    for (int i = t; i < YG * 64; i += 128) {
+        const int g = i >> 6, m = i & 63;
+        Ft[g][m] = m < YG ? __ldg(F + m * YG + g) : 0.f;
+    }
+    const int c = t & 31, m0 = (t >> 5) * 16;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* src = x + (size_t)b * YF * YG;
+        __syncthreads();                                 // previous keypoint's reads of xs are done (and Ft is complete)
+        for (int i = t; i < YF * YG; i += 128) xs[i / YG][i % YG] = src[i];
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 4
+        for (int g = 0; g < YG; ++g) {
+            const float xv = xs[c][g];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 f = *reinterpret_cast<const float4*>(&Ft[g][m0 + 4 * i4]);
+                acc[4 * i4 + 0] = fmaf(f.x, xv, acc[4 * i4 + 0]); acc[4 * i4 + 1] = fmaf(f.y, xv, acc[4 * i4 + 1]);
+                acc[4 * i4 + 2] = fmaf(f.z, xv, acc[4 * i4 + 2]); acc[4 * i4 + 3] = fmaf(f.w, xv, acc[4 * i4 + 3]);
+            }
+        }
+        const size_t o = (size_t)b * YG * YF + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (m0 + i < YG) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(acc[i]);
+                hi[o + (m0 + i) * YF] = __bfloat16_as_ushort(h);
+                lo[o + (m0 + i) * YF] = __bfloat16_as_ushort(__float2bfloat16_rn(acc[i] - __bfloat162float(h)));
+            }
+        }
     }
 }
 
 // Output side of the all-Fourier PartI: the layer-4 result arrives as Fourier coefficients Y4 [B][60 m][32 c] (no bias);
 //     e[c][g] = bias4[c] + sum_m F[m][g] Y4[m][c] + x[c][g]
 // followed by the same tail as part1_finalize_kernel (both L2 norms, invariant pool, numpy's pairwise mean_g).
-// One CTA (64 threads) per keypoint; thread g < 60 accumulates its 32 channels in registers.
-__global__ void __launch_bounds__(64) part1_finalize_fourier_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
-                                                                   const float* __restrict__ bias4, const float* __restrict__ x,
-                                                                   float* __restrict__ eqv, float* __restrict__ inv,
-                                                                   float* __restrict__ desc, int B) {
-    __shared__ float Fs[YG][YG];
+// CTAs of 128 threads stride over the keypoints with F resident in shared memory; thread (g = t % 64 < 60, half = t / 64)
+// accumulates 16 channels of its group element in registers.
+__global__ void __launch_bounds__(128) part1_finalize_fourier_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
+                                                                    const float* __restrict__ bias4, const float* __restrict__ x,
+                                                                    float* __restrict__ eqv, float* __restrict__ inv,
+                                                                    float* __restrict__ desc, int B) {
+    __shared__ float Fs[YG][64];                         // Fs[m][g], g padded to 64 (threads g >= 60 read zeros)
     __shared__ __align__(16) float ys[YG][YF];
     __shared__ float e[YF][YG + 1];
     __shared__ float invn[YG];
     __shared__ float red[YF];
-    const int b = blockIdx.x;
     const int t = threadIdx.x;
-    const float* xs = x + (size_t)b * YF * YG;
-    const float* yb = y4f + (size_t)b * YG * YF;
-    for (int i = t; i < YG * YG; i += 64) Fs[i / YG][i % YG] = __ldg(F + i);
-    for (int i = t; i < YG * YF / 4; i += 64) reinterpret_cast<float4*>(&ys[0][0])[i] = reinterpret_cast<const float4*>(yb)[i];
-    __syncthreads();
-    if (t < YG) {
-        float acc[YF];
+    for (int i = t; i < YG * 64; i += 128) {
+        const int m = i >> 6, g = i & 63;
+        Fs[m][g] = g < YG ? __ldg(F + m * YG + g) : 0.f;
+    }
+    const int g = t & 63, c0 = (t >> 6) * 16;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* xs = x + (size_t)b * YF * YG;
+        const float* yb = y4f + (size_t)b * YG * YF;
+        __syncthreads();                                 // previous keypoint done with ys / e / red (and Fs is complete)
+        for (int i = t; i < YG * YF / 4; i += 128) reinterpret_cast<float4*>(&ys[0][0])[i] = reinterpret_cast<const float4*>(yb)[i];
+        __syncthreads();
+        {
+            float acc[16];
 #pragma unroll
-        for (int c = 0; c < YF; ++c) acc[c] = bias4[c];
-#pragma unroll 2
-        for (int m = 0; m < YG; ++m) {
-            const float f = Fs[m][t];
+            for (int c = 0; c < 16; ++c) acc[c] = __ldg(bias4 + c0 + c);
+#pragma unroll 4
+            for (int m = 0; m < YG; ++m) {
+                const float f = Fs[m][g];
 #pragma unroll
-            for (int c4 = 0; c4 < YF / 4; ++c4) {
-                const float4 y = *reinterpret_cast<const float4*>(&ys[m][c4 * 4]);
-                acc[c4 * 4 + 0] = fmaf(f, y.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(f, y.y, acc[c4 * 4 + 1]);
-                acc[c4 * 4 + 2] = fmaf(f, y.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(f, y.w, acc[c4 * 4 + 3]);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 y = *reinterpret_cast<const float4*>(&ys[m][c0 + c4 * 4]);
+                    acc[c4 * 4 + 0] = fmaf(f, y.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(f, y.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(f, y.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(f, y.w, acc[c4 * 4 + 3]);
+                }
+            }
+            if (g < YG) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) e[c0 + c][g] = acc[c];
             }
         }
+        __syncthreads();
+        for (int i = t; i < YF * YG; i += 128) {
+            const int c = i / YG, gg = i % YG;
+            e[c][gg] = e[c][gg] + xs[i];
+        }
+        __syncthreads();
+        if (t < YG) {
+            float ss = 0.f;
 #pragma unroll
-        for (int c = 0; c < YF; ++c) e[c][t] = acc[c];
+            for (int c = 0; c < YF; ++c) ss = fmaf(e[c][t], e[c][t], ss);
+            invn[t] = fmaxf(sqrtf(ss), 1e-4f);   // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
+        }
+        // invariant pooling uses the UN-normalised e (utils/network.py:99 precedes :102)
+        float m = 0.f;
+        if (t >= 64 && t < 64 + YF) {
+            float sum = 0.f;
+            for (int gg = 0; gg < YG; ++gg) sum += e[t - 64][gg];
+            m = sum / 60.0f;
+            red[t - 64] = m * m;
+        }
+        __syncthreads();
+        if (t >= 64 && t < 64 + YF && inv) {
+            float ss = 0.f;
+            for (int c = 0; c < YF; ++c) ss += red[c];
+            inv[(size_t)b * YF + t - 64] = m / fmaxf(sqrtf(ss), 1e-4f);
+        }
+        float* out = eqv + (size_t)b * YF * YG;
+        for (int i = t; i < YF * YG; i += 128) {
+            const int c = i / YG, gg = i % YG;
+            const float v = e[c][gg] / invn[gg];
+            e[c][gg] = v;
+            out[i] = v;
+        }
+        __syncthreads();
+        if (t < YF && desc) desc[(size_t)b * YF + t] = numpy_mean60(&e[t][0], 1);
     }
-    __syncthreads();
-    for (int i = t; i < YF * YG; i += 64) {
-        const int c = i / YG, g = i % YG;
-        e[c][g] = e[c][g] + xs[i];
-    }
-    __syncthreads();
-    if (t < YG) {
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < YF; ++c) ss = fmaf(e[c][t], e[c][t], ss);
-        invn[t] = fmaxf(sqrtf(ss), 1e-4f);   // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
-    }
-    float m = 0.f;
-    if (t < YF) {
-        float s = 0.f;
-        for (int g = 0; g < YG; ++g) s += e[t][g];
-        m = s / 60.0f;
-        red[t] = m * m;
-    }
-    __syncthreads();
-    if (t < YF && inv) {
-        float ss = 0.f;
-        for (int c = 0; c < YF; ++c) ss += red[c];
-        inv[(size_t)b * YF + t] = m / fmaxf(sqrtf(ss), 1e-4f);
-    }
-    float* out = eqv + (size_t)b * YF * YG;
-    for (int i = t; i < YF * YG; i += 64) {
-        const int c = i / YG, g = i % YG;
-        const float v = e[c][g] / invn[g];
-        e[c][g] = v;
-        out[i] = v;
-    }
-    __syncthreads();
-    if (t < YF && desc) desc[(size_t)b * YF + t] = numpy_mean60(&e[t][0], 1);
 }
 
 __global__ void __launch_bounds__(64) group_mean_kernel(const float* __restrict__ eqv, float* __restrict__ desc, int K) {
@@ -291,7 +321,8 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             unsigned short* Y3h = X2l + R * 512;  unsigned short* Y3l = Y3h + R * 256;
             unsigned short* X3h = Y3l + R * 256;  unsigned short* X3l = X3h + R * 256;
             float* Y4 = (float*)(X3l + R * 256);
-            fourier_in_kernel<<<n, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
+            const int sgrid = n < 8 * ctx->num_sms ? n : 8 * ctx->num_sms;      // keypoint-striding CTAs, F resident in shared memory
+            fourier_in_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
             ctx->launches++;
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
@@ -329,7 +360,7 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             yoho_prof_end(ctx, st);
             // layer 4 (256 -> 32): Fourier coefficients of y4, FP32 [n][60][32]
             if (int rc = layer(ctx->p1f_out, X3h, X3l, nullptr, nullptr, Y4, 32, true)) return rc;
-            part1_finalize_fourier_kernel<<<n, 64, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+            part1_finalize_fourier_kernel<<<n < 6 * ctx->num_sms ? n : 6 * ctx->num_sms, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
                                                             inv ? inv + (size_t)s * YF : nullptr,
                                                             desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
             ctx->launches++;
