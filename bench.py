@@ -219,7 +219,7 @@ def run_ours(args):
     for i in range(args.warmup):
         results.append(pipe.register(*sets_d[i % N_SETS]))
         pipe.register_pinned(*sets_p[i % N_SETS])
-    for _ in pipe.register_stream(sets_p[i % N_SETS] for i in range(2)):
+    for _ in pipe.register_stream(sets_p[i % N_SETS] for i in range(4)):
         pass
     # ---- device-resident timed region -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)

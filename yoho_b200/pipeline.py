@@ -112,14 +112,26 @@ class PairPipeline:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
 
-        def upload(pp):
+        # two persistent sets of device input buffers (no allocator traffic in steady state): pair n uses set n % 2; the copy of
+        # pair n + 2 into the same set waits for the event recorded after pair n's last kernel was queued
+        if not hasattr(self, "_in_sets"):
+            self._in_sets = [None, None]
+            self._in_free = [None, None]
+
+        def upload(pp, slot):
+            cur = self._in_sets[slot]
+            if cur is None or any(c.shape != t.shape or c.dtype != t.dtype for c, t in zip(cur, pp)):
+                cur = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in pp]
+                self._in_sets[slot] = cur
+                cs.wait_stream(main)
+            if self._in_free[slot] is not None:
+                cs.wait_event(self._in_free[slot])
             with torch.cuda.stream(cs):
-                ts = [t.to(dev, non_blocking=True) for t in pp]
+                for c, t in zip(cur, pp):
+                    c.copy_(t, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            for t in ts:
-                t.record_stream(main)
-            return ts, ev
+            return cur, ev
 
         def finish(pend):
             host, ev, M = pend
@@ -129,7 +141,7 @@ class PairPipeline:
 
         it = iter(pinned_pairs)
         try:
-            nxt = upload(next(it))
+            nxt = upload(next(it), 0)
         except StopIteration:
             return
         pending = None
@@ -137,11 +149,14 @@ class PairPipeline:
         while nxt is not None:
             (fa, fb, ka, kb), ev = nxt
             try:
-                nxt = upload(next(it))                  # prefetch: overlaps this pair's PartI
+                nxt = upload(next(it), (n + 1) & 1)     # prefetch: overlaps this pair's PartI
             except StopIteration:
                 nxt = None
             main.wait_event(ev)
             r = self.register(fa, fb, ka, kb)
+            free = torch.cuda.Event()
+            free.record(main)                           # every kernel reading this input set has been queued
+            self._in_free[n & 1] = free
             if not hasattr(self, "_res_pin"):
                 self._res_pin = [torch.empty((2, 3, 4), dtype=torch.float64, pin_memory=True) for _ in range(2)]
             host = self._res_pin[n & 1]
