@@ -128,7 +128,8 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     if (!c) return YOHO_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p1_out_cat, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3};
+    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p1_out_cat, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3,
+                        &c->p2_b_split[0], &c->p2_b_split[1], &c->p2_b_split[2], &c->p2_b_split[3], &c->p2_b_split[4]};
     for (GLayer* l : layers) free_layer(*l);
     GBn* bns[] = {&c->p1_bn_a, &c->p1_bn_b, &c->p1_bn_out, &c->p2_bn_init, &c->p2_bn_a, &c->p2_bn_b, &c->p2_bn1, &c->p2_bn2};
     for (GBn* b : bns) free_bn(*b);
@@ -316,6 +317,22 @@ extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
     if ((rc = pack_conv(ctx, ctx->p2_a, w->conv_a, 256, 512, YT))) return rc;
     if ((rc = pack_bn(ctx->p2_bn_b, w->bn_b, 512))) return rc;
     if ((rc = pack_conv(ctx, ctx->p2_b, w->conv_b, 512, 256, YT))) return rc;
+    {   // the last group convolution is evaluated at g = 0 only: M rows instead of 60 M.  Cut along the taps so that one launch
+        // fills the machine; the five partial sums are added in a fixed order by part2_reduce_kernel.
+        const int cuts[6] = {0, 3, 6, 9, 11, 13};
+        std::vector<float> wf((size_t)YT * 512 * 256);
+        for (int o = 0; o < 256; ++o)
+            for (int c = 0; c < 512; ++c)
+                for (int k = 0; k < YT; ++k) wf[((size_t)k * 512 + c) * 256 + o] = w->conv_b.weight_host[((size_t)o * 512 + c) * YT + k];
+        for (int q = 0; q < 5; ++q) {
+            GLayer& L = ctx->p2_b_split[q];
+            free_layer(L);
+            L.cin = 512; L.cout = 256; L.taps = cuts[q + 1] - cuts[q]; L.tc_dense = 1; L.prof_class = 6;
+            std::vector<float> wq(wf.begin() + (size_t)cuts[q] * 512 * 256, wf.begin() + (size_t)cuts[q + 1] * 512 * 256), zb(256, 0.f);
+            if ((rc = upload(&L.bias, zb))) return rc;
+            if ((rc = gconv_tc_pack(ctx, L, wq))) return rc;
+        }
+    }
     if ((rc = pack_conv(ctx, ctx->p2_fc1, w->fc1, 256, 512, 1))) return rc;
     if ((rc = pack_bn(ctx->p2_bn1, w->bn1, 512))) return rc;
     if ((rc = pack_conv(ctx, ctx->p2_fc2, w->fc2, 512, 128, 1))) return rc;

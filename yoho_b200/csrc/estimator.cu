@@ -242,40 +242,55 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
         atomicAdd(&cnt[b], 1);
     }
     __syncthreads();
+    // DR_statictic weights (tests/estimator.py:41-51): the per-bin products in parallel, the two running sums serially in bin
+    // order on one thread (the same additions in the same order as the reference's loops), the divisions in parallel again
+    __shared__ double w_s[YG];
+    __shared__ double tot_s, last_s;
+    if (t < YG) {
+        double p = 0.0;
+        if (cnt[t] >= 2) {
+            const double num = (double)cnt[t] / 100.0;
+            p = num * (num - 0.01) * (num - 0.02);
+        }
+        w_s[t] = p;
+    }
+    __syncthreads();
     if (t == 0) {
-        double tot = 0.0, w[YG];
+        double tot = 0.0;
         int o = 0;
-        for (int i = 0; i < YG; ++i) {
-            off[i] = o;
-            o += cnt[i];
-            double p = 0.0;
-            if (cnt[i] >= 2) {
-                const double num = (double)cnt[i] / 100.0;
-                p = num * (num - 0.01) * (num - 0.02);
-            }
-            w[i] = p;
-            tot += p;
-        }
+        for (int i = 0; i < YG; ++i) { off[i] = o; o += cnt[i]; tot += w_s[i]; }
         off[YG] = o;
+        tot_s = tot;
         ok_s = !(tot < 1e-4);
-        if (ok_s) {
-            // np.random.choice: cdf = cumsum(p / sum); cdf /= cdf[-1]
-            double c = 0.0;
-            for (int i = 0; i < YG; ++i) { c += w[i] / tot; cdf[i] = c; }
-            const double last = cdf[YG - 1];
-            for (int i = 0; i < YG; ++i) cdf[i] = cdf[i] / last;
-        }
         *status = ok_s ? 0 : 1;
     }
     __syncthreads();
-    // stable bucket fill: thread b owns bin b and scans the matches in order (M is a few thousand at most)
-    if (t < YG) {
-        int o = off[t];
-        const int ms = M < 16384 ? M : 16384;
-        for (int m = 0; m < ms; ++m)
-            if (bins[m] == t) members_ws[o++] = m;
-        for (int m = ms; m < M; ++m)
-            if ((int)dr_index[m] == t) members_ws[o++] = m;
+    if (ok_s) {
+        // np.random.choice: cdf = cumsum(p / sum); cdf /= cdf[-1]
+        if (t < YG) w_s[t] = w_s[t] / tot_s;
+        __syncthreads();
+        if (t == 0) {
+            double c = 0.0;
+            for (int i = 0; i < YG; ++i) { c += w_s[i]; cdf[i] = c; }
+            last_s = c;
+        }
+        __syncthreads();
+        if (t < YG) cdf[t] = cdf[t] / last_s;
+    }
+    // stable bucket fill: warp w owns bins w and w + 32 and walks the matches 32 at a time (ballot + prefix popcount keeps the
+    // members of a bin in ascending match order, like the reference's append loop)
+    {
+        const int warp = t >> 5, lane = t & 31;
+        for (int bin = warp; bin < YG; bin += 32) {
+            int o = off[bin];
+            for (int m0 = 0; m0 < M; m0 += 32) {
+                const int m = m0 + lane;
+                const bool hit = m < M && (m < 16384 ? (int)bins[m] : (int)dr_index[m]) == bin;
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) members_ws[o + __popc(bal & ((1u << lane) - 1u))] = m;
+                o += __popc(bal);
+            }
+        }
     }
     __syncthreads();
     if (!ok_s) {
@@ -308,22 +323,33 @@ __global__ void o_keys_kernel(int M, unsigned long long seed, unsigned long long
     const uint4 r = philox4x32(make_uint4((unsigned)i, 2u, 0x59484f4fu, 0u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
     keys[i] = ((unsigned long long)r.x << 32) | r.y;
 }
+// 32 items per CTA; warp w compares its lane's key with every eighth key (slice w) staged in shared memory, the eight partial
+// ranks are added through shared memory.  M compares per item spread over 8 threads and M/32 CTAs.
 __global__ void __launch_bounds__(256) o_rank_kernel(int M, const unsigned long long* __restrict__ keys, int32_t* __restrict__ order) {
-    __shared__ unsigned long long ks[1024];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned long long ks[2048];
+    __shared__ int part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     const unsigned long long ki = i < M ? keys[i] : 0ull;
     int rank = 0;
-    for (int base = 0; base < M; base += 1024) {
-        for (int j = threadIdx.x; j < 1024; j += 256) ks[j] = base + j < M ? keys[base + j] : ~0ull;
+    for (int base = 0; base < M; base += 2048) {
+        for (int j = threadIdx.x; j < 2048; j += 256) ks[j] = base + j < M ? keys[base + j] : ~0ull;
         __syncthreads();
-        const int lim = M - base < 1024 ? M - base : 1024;
-        for (int j = 0; j < lim; ++j) {
+        const int lim = M - base < 2048 ? M - base : 2048;
+        for (int j = w; j < lim; j += 8) {
             const unsigned long long kj = ks[j];
             rank += (kj < ki || (kj == ki && base + j < i)) ? 1 : 0;
         }
         __syncthreads();
     }
-    if (i < M) order[rank] = i;
+    part[w][lane] = rank;
+    __syncthreads();
+    if (w == 0 && i < M) {
+        int r = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r += part[q][lane];
+        order[r] = i;
+    }
 }
 
 }  // namespace
@@ -374,7 +400,7 @@ extern "C" int yoho_o_order(yoho_ctx* ctx, int M, uint64_t seed, int32_t* order,
     if (int rc = yoho_ws_reserve(ctx, (size_t)M * 8)) return rc;
     unsigned long long* keys = (unsigned long long*)ctx->ws;
     o_keys_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, seed, keys);
-    o_rank_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, keys, order);
+    o_rank_kernel<<<(M + 31) / 32, 256, 0, (cudaStream_t)stream>>>(M, keys, order);
     ctx->launches += 2;
     YCHECK(cudaGetLastError());
     return YOHO_OK;

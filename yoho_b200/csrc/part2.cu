@@ -8,6 +8,8 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
+int gconv_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st);
+
 namespace {
 
 // z0a[m][g][0:128] = relu(BN_init(concat_c(P_r FCGF_B, FCGF_A, P_r YOHO_B, YOHO_A)))   one CTA per match.
@@ -119,6 +121,25 @@ __global__ void gather_kps_kernel(const double* __restrict__ kps0, const double*
     }
 }
 
+// z3[m][c] = bias[c] + z1[m][g = 0][c] + the five tap-split partial sums of the last group convolution, added in split order.
+__global__ void part2_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, const float* __restrict__ z1,
+                                    int zero_pos, float* __restrict__ z3, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index over [n][64]
+    if (i >= n * 64) return;
+    const int m = i >> 6, c4 = i & 63;
+    const float4* p = reinterpret_cast<const float4*>(part) + (size_t)m * 5 * 64 + c4;
+    float4 acc = p[0];
+#pragma unroll
+    for (int q = 1; q < 5; ++q) {
+        const float4 v = p[q * 64];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float4 b = reinterpret_cast<const float4*>(bias)[c4];
+    const float4 r = reinterpret_cast<const float4*>(z1 + ((size_t)m * 45 + zero_pos) * 256)[c4];
+    acc.x = (acc.x + b.x) + r.x; acc.y = (acc.y + b.y) + r.y; acc.z = (acc.z + b.z) + r.z; acc.w = (acc.w + b.w) + r.w;
+    reinterpret_cast<float4*>(z3)[i] = acc;
+}
+
 constexpr int P2_CHUNK = 4096;
 
 }  // namespace
@@ -135,7 +156,7 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
     if (M == 0) return YOHO_OK;
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
-    const size_t per = sizeof(float) * ((size_t)YG * 128 + 45 * 256 * 2 + 13 * 512 + 256 + 512 + 128);
+    const size_t per = sizeof(float) * ((size_t)YG * 128 + 45 * 256 * 2 + 13 * 512 + 256 + 512 + 128 + 5 * 256);
     const int chunk = M < P2_CHUNK ? M : P2_CHUNK;
     if (int rc = yoho_ws_reserve(ctx, per * (size_t)chunk)) return rc;
     for (int s = 0; s < M; s += chunk) {
@@ -147,6 +168,7 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
         float* z3 = a2 + (size_t)n * 13 * 512;
         float* h1 = z3 + (size_t)n * 256;
         float* h2 = h1 + (size_t)n * 512;
+        float* zpart = h2 + (size_t)n * 128;         // [n][5][256] tap-split partial sums of the last group convolution
         const int64_t* pr = pairs ? pairs + 2 * (size_t)s : nullptr;
         // without a match list the inputs are already per-match rows: advance them with the chunk
         const size_t adv = pairs ? 0 : (size_t)s * YF * YG;
@@ -179,7 +201,22 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
         a.resid = z1; a.Jres = 45; a.resid_off = ctx->hop2_zero_pos; a.resid_per_j = 0;
         a.out_raw = z3; a.out_act = nullptr; a.out_hi = a.out_lo = nullptr; a.scale = a.shift = nullptr;
         if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; } else { a.act = a2; }
-        if (int rc = gconv_forward(ctx, ctx->p2_b, a, st)) return rc;
+        if (tc && ctx->p2_b_split[4].w_hi && !(ctx->tc_flags & 1024)) {
+            GConvArgs fs[5];
+            const GLayer* Ls[5];
+            int t0 = 0;
+            for (int q = 0; q < 5; ++q) {
+                GConvArgs f{};
+                f.B = n; f.Jin = 13; f.Jout = 1; f.idx = ctx->d_idx_p2_b + t0;
+                f.act_hi = a2_hi; f.act_lo = a2_lo;
+                f.out_raw = zpart; f.omap = ctx->d_idx_ident + q; f.ogroup = 256; f.out_J = 5;
+                fs[q] = f; Ls[q] = &ctx->p2_b_split[q];
+                t0 += ctx->p2_b_split[q].taps;
+            }
+            if (int rc = gconv_forward_grouped(ctx, Ls, fs, 5, st)) return rc;
+            part2_reduce_kernel<<<(n * 64 + 255) / 256, 256, 0, st>>>(zpart, ctx->p2_b.bias, z1, ctx->hop2_zero_pos, z3, n);
+            ctx->launches++;
+        } else if (int rc = gconv_forward(ctx, ctx->p2_b, a, st)) return rc;
         a.act_hi = a.act_lo = nullptr;
         // head: 256 -> 512 -> 128 with BN+ReLU, as 1-tap layers
         a.resid = nullptr; a.idx = ctx->d_idx_one; a.Jin = 1; a.Jout = 1;
