@@ -145,3 +145,23 @@ def test_dropin_aliases():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_make_scene_plants_consistent_pairwise_transforms():
+    """yoho_b200.synth.make_scene (scene-level driver input, BASELINE.json configs 3-4): the planted pair transform maps the
+    shared points of fragment j onto fragment i, and the group features of shared points are related by ONE group element."""
+    import numpy as np
+    from yoho_b200 import synth, group
+    fr, pairs, gt = synth.make_scene(8, 200, seed=3)
+    assert len(fr) == 8 and len(pairs) == 28
+    P = group.load().P
+    for (i, j) in [pairs[0], pairs[9], pairs[27]]:
+        R, t = gt[(i, j)]
+        ki, kj = fr[i][1], fr[j][1] @ R.T + t
+        d = np.linalg.norm(ki[:, None, :] - kj[None, :, :], axis=2)
+        a, b = np.nonzero(d < 0.06)                                   # shared points (1 cm noise on both sides)
+        assert len(a) >= 0.25 * 200                                   # overlap rho_i * rho_j >= 0.55^2
+        fi, fj = fr[i][0][a], fr[j][0][b]
+        cor = np.array([(fi * fj[:, :, P[r]]).sum() for r in range(60)])
+        r = int(cor.argmax())
+        assert cor[r] > 0.9 * len(a) * 60 and np.sort(cor)[-2] < 0.5 * cor[r]

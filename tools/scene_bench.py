@@ -1,0 +1,76 @@
+"""Scene-level throughput (BASELINE.json configs 3-4, amortised regime): PartI once per FRAGMENT, then matching, rotation
+index, YOHO-C, PartII and YOHO-O once per PAIR from the cached descriptors (`yoho_b200.batch.register_scene`), pairs sharded
+over the ranks.  Prints one JSON line per configuration with the amortised keypoint-pairs/s and the YOHO-C success rate
+against the planted transforms.
+
+    python tools/scene_bench.py [--fragments 64] [--kpts 5000] [--config c3|c4|both]
+    python -m torch.distributed.run --nproc-per-node N ... tools/scene_bench.py      # pairs sharded over N ranks
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np                                 # noqa: E402
+import torch                                       # noqa: E402
+from yoho_b200 import synth, dist as ydist         # noqa: E402
+from yoho_b200.engine import get_engine            # noqa: E402
+from yoho_b200.pipeline import PairPipeline        # noqa: E402
+from yoho_b200.batch import register_scene         # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--fragments", type=int, default=64)
+ap.add_argument("--kpts", type=int, default=5000)
+ap.add_argument("--config", default="both", choices=["c3", "c4", "both"])
+args = ap.parse_args()
+
+rank, local_rank, world = ydist.init_from_env()
+torch.cuda.set_device(local_rank)
+eng = get_engine(local_rank)
+eng.load_part1(synth.synth_state_dict("PartI", 0))
+eng.load_part2(synth.synth_state_dict("PartII", 0))
+dev = eng.device
+CFG = {"c3": dict(name="configs[2] shape: 3DMatch-like scene, pair overlap ~U[0.3,0.9], YOHO-C 1000 iterations + YOHO-O", lo=0.55, hi=0.95),
+       "c4": dict(name="configs[3] shape: 3DLoMatch-like scene, pair overlap ~U[0.1,0.3], YOHO-C + YOHO-O 1000 hypotheses", lo=0.32, hi=0.55)}
+for key in (["c3", "c4"] if args.config == "both" else [args.config]):
+    c = CFG[key]
+    t0 = time.time()
+    frags, pair_ids, gts = synth.make_scene(args.fragments, args.kpts, seed=7, overlap_lo=c["lo"], overlap_hi=c["hi"])
+    gen_s = time.time() - t0
+    dfr = {k: (torch.from_numpy(f).to(dev), torch.from_numpy(p).to(dev)) for k, (f, p) in frags.items()}
+    pipe = PairPipeline(eng, seed=1)
+    register_scene(pipe, {k: dfr[k] for k in list(dfr)[:8]}, pair_ids[:8])          # warm-up (one cluster)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = register_scene(PairPipeline(eng, seed=1), dfr, pair_ids)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    T = res.cpu().numpy()
+    ok_c = []
+    for n, pid in enumerate(pair_ids):
+        R, t = gts[pid]
+        cosang = np.clip((np.trace(T[n, 0][:, :3].T @ R) - 1) / 2, -1, 1)
+        ok_c.append(bool(np.degrees(np.arccos(cosang)) < 5.0 and np.linalg.norm(T[n, 0][:, 3] - t) < 0.3))
+    if rank == 0:
+        print(json.dumps({"config": c["name"], "n_gpus": world, "fragments": args.fragments, "pairs": len(pair_ids), "kpts": args.kpts,
+                          "seconds": ms / 1e3, "ms_per_pair": ms / len(pair_ids),
+                          "keypoint_pairs_per_s": len(pair_ids) * args.kpts / (ms / 1e3),
+                          "pairs_per_s": len(pair_ids) / (ms / 1e3),
+                          "yoho_c_success_rate": float(np.mean(ok_c)),
+                          "extrapolated_full_set_seconds": {"3dmatch_433_fragments_1623_pairs" if key == "c3" else "3dlomatch_433_fragments_1781_pairs":
+                                                            ms / 1e3 * ((1623 if key == "c3" else 1781) / len(pair_ids))},
+                          "host_generation_seconds": gen_s, "data": "synthetic (yoho_b200.synth.make_scene)"}), flush=True)
+if world > 1:
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()

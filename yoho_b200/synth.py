@@ -136,3 +136,49 @@ def make_fragment_pair(K, seed=0, overlap=0.5, sigma=0.05, max_residual_deg=15.0
     kps_A[ids_A] = kps_B[ids_B] @ R_gt.T + t_gt + kp_noise * rs.standard_normal((n_ov, 3))
     return dict(feat_A=feat_A, feat_B=feat_B, kps_A=kps_A, kps_B=kps_B, r=r, R_gt=R_gt, t_gt=t_gt,
                 ids_A=ids_A, ids_B=ids_B)
+
+
+def make_scene(n_fragments, K, seed=0, cluster=8, overlap_lo=0.55, overlap_hi=0.95, sigma=0.05, max_residual_deg=15.0,
+               kp_noise=0.01, so3_dir=None):
+    """A 3DMatch-shaped scene (BASELINE.json configs 3-4): clusters of `cluster` fragments cut from one base cloud, every
+    fragment carrying its own rigid motion (group element r_j times a small residual rotation, translation t_j) and its own
+    subset S_j (fraction rho_j ~ U[overlap_lo, overlap_hi]) of the base points; the rest of each fragment is unrelated clutter.
+    Two fragments of a cluster overlap on S_i & S_j (fraction ~ rho_i rho_j), so all C(cluster, 2) pairs of a cluster are
+    genuine registration problems: 3.5 pairs per fragment at cluster = 8 (3DMatch: 1623 / 433 = 3.75).
+
+    Returns (fragments, pair_ids, gt): fragments {id: (feat [K,32,60] f32, kps [K,3] f64)}, pair_ids [(i, j)], gt {(i, j): (R, t)}
+    with pts_i = R pts_j + t on the overlap.
+    """
+    gt = _group.load(so3_dir)
+    rs = np.random.RandomState(seed)
+    fragments, pair_ids, gts = {}, [], {}
+    fid = 0
+    while fid < n_fragments:
+        n_c = min(cluster, n_fragments - fid)
+        base_f = _unit(rs.standard_normal((K, 32, 60)), 1)
+        base_k = rs.uniform(0.0, 3.0, (K, 3))
+        motions = []
+        for j in range(n_c):
+            r = int(rs.randint(0, 60))
+            R = _small_rotation(rs, max_residual_deg) @ gt.R[r]
+            t = rs.uniform(-1.0, 1.0, 3)
+            rho = rs.uniform(overlap_lo, overlap_hi)
+            n_ov = int(round(rho * K))
+            src = rs.permutation(K)[:n_ov]                 # base points seen by this fragment
+            dst = rs.permutation(K)[:n_ov]                 # where they sit in the fragment
+            feat = _unit(rs.standard_normal((K, 32, 60)), 1).astype(np.float32)
+            kps = rs.uniform(-2.0, 5.0, (K, 3))
+            # F(R_r pc)[:, :, g] = F(pc)[:, :, P[r][g]]  (SURVEY.md section 0)
+            feat[dst] = _unit(base_f[src][:, :, gt.P[r]] + sigma * rs.standard_normal((n_ov, 32, 60)), 1).astype(np.float32)
+            kps[dst] = base_k[src] @ R.T + t + kp_noise * rs.standard_normal((n_ov, 3))
+            fragments[fid + j] = (feat, kps)
+            motions.append((R, t))
+        for i in range(n_c):
+            for j in range(i + 1, n_c):
+                Ri, ti = motions[i]
+                Rj, tj = motions[j]
+                Rij = Ri @ Rj.T                            # pts_i = Ri p + ti, pts_j = Rj p + tj  ->  pts_i = Rij pts_j + (ti - Rij tj)
+                pair_ids.append((fid + i, fid + j))
+                gts[(fid + i, fid + j)] = (Rij, ti - Rij @ tj)
+        fid += n_c
+    return fragments, pair_ids, gts
