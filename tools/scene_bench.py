@@ -25,6 +25,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--fragments", type=int, default=64)
 ap.add_argument("--kpts", type=int, default=5000)
 ap.add_argument("--config", default="both", choices=["c3", "c4", "both"])
+ap.add_argument("--repeat", type=int, default=2, help="timed passes per configuration (the best is reported)")
 args = ap.parse_args()
 
 rank, local_rank, world = ydist.init_from_env()
@@ -46,12 +47,17 @@ for key in (["c3", "c4"] if args.config == "both" else [args.config]):
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    res = register_scene(PairPipeline(eng, seed=1), dfr, pair_ids)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    best = None
+    for rep in range(args.repeat):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tim = {}
+        e0.record()
+        res = register_scene(PairPipeline(eng, seed=1), dfr, pair_ids, timing=tim)
+        e1.record()
+        torch.cuda.synchronize()
+        if best is None or e0.elapsed_time(e1) < best[0]:
+            best = (e0.elapsed_time(e1), tim)
+    ms, tim = best
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -67,7 +73,7 @@ for key in (["c3", "c4"] if args.config == "both" else [args.config]):
                           "seconds": ms / 1e3, "ms_per_pair": ms / len(pair_ids),
                           "keypoint_pairs_per_s": len(pair_ids) * args.kpts / (ms / 1e3),
                           "pairs_per_s": len(pair_ids) / (ms / 1e3),
-                          "yoho_c_success_rate": float(np.mean(ok_c)),
+                          "yoho_c_success_rate": float(np.mean(ok_c)), "rank0_phases": tim, "timed_passes": args.repeat,
                           "extrapolated_full_set_seconds": {"3dmatch_433_fragments_1623_pairs" if key == "c3" else "3dlomatch_433_fragments_1781_pairs":
                                                             ms / 1e3 * ((1623 if key == "c3" else 1781) / len(pair_ids))},
                           "host_generation_seconds": gen_s, "data": "synthetic (yoho_b200.synth.make_scene)"}), flush=True)
