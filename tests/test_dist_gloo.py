@@ -40,6 +40,11 @@ def _worker(rank, world, port, q):
         got = yd.sharded_mutual_nn(torch.from_numpy(dA), torch.from_numpy(dB[lo:hi]), lo, Kb, nn1).numpy()
         want, _, _ = O.mutual_matches(dA, dB)
         assert np.array_equal(got, want), (got.shape, want.shape)
+        # 3. scene-driver exchange: items sharded round-robin come back complete and in order on every rank
+        for n_items in (2, 5):
+            mine_i = yd.shard(list(range(n_items)))
+            got_all = yd.allgather_sharded([torch.full((3, 4), float(i)) for i in mine_i], n_items)
+            assert [float(t[0, 0]) for t in got_all] == [float(i) for i in range(n_items)] and tuple(got_all[0].shape) == (3, 4)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -2,8 +2,9 @@
 
 The reference runs PartI once per FRAGMENT (tests/extractor.py:46-47) and everything else once per PAIR
 (tests/matcher.py:30, tests/extractor.py:91,162, tests/estimator.py:91,305).  Here:
-  phase 1  every rank runs PartI on the fragments its pairs touch (no collective; a fragment shared by pairs on different
-           ranks is recomputed rather than exchanged — 38 MB over NVLink would also do, PartI is 5 ms),
+  phase 1  PartI once per fragment ACROSS the job: fragments sharded round-robin, eqv and matcher descriptors exchanged with
+           one NCCL all-gather each (38 MB per fragment over NVLink; equal-shaped fragments only, else each rank computes the
+           fragments its own pairs touch),
   phase 2  every rank registers its round-robin share of the pairs from the cached eqv / matcher descriptors,
   phase 3  one tiny gather of the [n_pairs, 2, 3, 4] float64 transforms.
 """
@@ -25,15 +26,33 @@ def register_scene(pipe: PairPipeline, fragments, pair_ids, timing=None):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timing is not None else None
     if ev:
         ev[0].record()
-    # phase 1: PartI once per fragment this rank's pairs touch (tests/extractor.py:46-47)
-    for pi in mine:
-        for fid in pair_ids[pi]:
-            if fid not in cache:
-                feat, kps = fragments[fid]
-                feat = eng._f32(feat)
-                kps = eng._f64(kps)
-                o = eng.part1(feat, want_inv=False, want_desc=True)
-                cache[fid] = (feat, kps, o["eqv"], o["desc"])
+    # phase 1: PartI once per fragment (tests/extractor.py:46-47).  With several ranks the fragments of the whole pair list are
+    # sharded round-robin and their eqv / matcher descriptors exchanged with one all-gather each, when all fragments have the
+    # same shape (a 3DMatch scene: 5000 keypoints each); otherwise every rank computes the fragments its own pairs touch.
+    needed = sorted({fid for pid in pair_ids for fid in pid}, key=str)
+    w = ydist.world()
+    same = len({tuple(np.shape(fragments[f][0])) for f in needed}) == 1
+    if w > 1 and same and len(needed) >= w:
+        my_f = ydist.shard(needed)
+        loc = {}
+        for fid in my_f:
+            o = eng.part1(eng._f32(fragments[fid][0]), want_inv=False, want_desc=True)
+            loc[fid] = (o["eqv"], o["desc"])
+        eqvs = ydist.allgather_sharded([loc[f][0] for f in my_f], len(needed))
+        descs = ydist.allgather_sharded([loc[f][1] for f in my_f], len(needed))
+        mine_f = {fid for pi in mine for fid in pair_ids[pi]}
+        for i, fid in enumerate(needed):
+            if fid in mine_f:
+                cache[fid] = (eng._f32(fragments[fid][0]), eng._f64(fragments[fid][1]), eqvs[i], descs[i])
+    else:
+        for pi in mine:
+            for fid in pair_ids[pi]:
+                if fid not in cache:
+                    feat, kps = fragments[fid]
+                    feat = eng._f32(feat)
+                    kps = eng._f64(kps)
+                    o = eng.part1(feat, want_inv=False, want_desc=True)
+                    cache[fid] = (feat, kps, o["eqv"], o["desc"])
     if ev:
         ev[1].record()
     # phase 2: everything else once per pair

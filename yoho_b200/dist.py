@@ -4,7 +4,8 @@ The hot path shards over INDEPENDENT units: PartI per fragment 
 else per pair (tests/matcher.py:30, tests/extractor.py:91,162, tests/estimator.py:91,305) — the reference itself
 parallelises pairs with a process pool (tests/estimator.py:269-273).  So there is no data-path collective:
   * `shard(items)`            round-robin assignment of fragments / pairs to ranks,
-  * `gather_transforms(T)`    the one tiny exchange: every rank's [n_i,3,4] float64 results -> rank order.
+  * `gather_transforms(T)`    the one tiny exchange: every rank's [n_i,3,4] float64 results -> rank order,
+  * `allgather_sharded(...)`  scene driver only: PartI outputs computed once per fragment across the job, one all-gather.
 Config 5 (a 10 000-keypoint pair whose fragment-1 descriptors are sharded over the ranks) does have an exchange:
   * `sharded_mutual_nn(...)`  each rank searches all of A against its shard of B with the single-GPU kernel, then one
                               all-gather of the packed (distance, index) keys; the lexicographic min over ranks keeps
@@ -75,6 +76,26 @@ def gather_transforms(T_local):
     per_rank = [list(bufs[r][: ns[r]]) for r in range(w)]
     rows = unshard(per_rank)
     return torch.stack(rows) if rows else T_local
+
+
+def allgather_sharded(items_local, n_total):
+    """Every rank holds the tensors of items r, r+w, r+2w, ... (the `shard` order) of a list of n_total equally shaped
+    tensors; returns the full list, in item order, on every rank.  ONE all-gather of the stacked (zero-padded) shards — used
+    after phase 1 of the scene driver so that PartI runs once per fragment across the whole job (38 MB per 5000-keypoint
+    fragment over NVLink) instead of once per rank."""
+    w = world()
+    if w == 1:
+        return list(items_local)
+    cap = (n_total + w - 1) // w
+    assert 0 < len(items_local) <= cap, "every rank must own at least one item (n_total >= world size)"
+    ref = items_local[0]
+    shape, dt, dev = ref.shape, ref.dtype, ref.device
+    buf = torch.zeros((cap,) + tuple(shape), dtype=dt, device=dev)
+    for i, t in enumerate(items_local):
+        buf[i].copy_(t)
+    out = torch.empty((w * cap,) + tuple(shape), dtype=dt, device=dev)
+    dist.all_gather_into_tensor(out, buf)
+    return [out[(i % w) * cap + i // w] for i in range(n_total)]
 
 
 def pack_key(dist_f32, idx):
