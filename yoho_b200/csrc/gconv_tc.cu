@@ -116,24 +116,22 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
+// `rowoff[it]` = BYTE offset (from `base`) of row it*8 + lane/4 at this block's first column — the caller shuffles the
+// per-lane row offsets once per 32-column chunk and reuses them for every tensor it writes (FP32, hi, lo).
 template <int NB>
-__device__ __forceinline__ void coalesced_store(uint8_t* wbuf, const uint4* regs, uint8_t* my_row, int lane, uint32_t okmask) {
-    // my_row: global address of THIS lane's row (column offset applied); rows need not be equally spaced (remapped outputs)
+__device__ __forceinline__ void coalesced_store(uint32_t wb, const uint4* regs, uint8_t* base, const uint32_t* rowoff, int lane, uint32_t okmask) {
     static_assert(NB == 64, "the swizzle below is written for four 16-byte pieces per row");
     constexpr int Q = NB / 16;                       // 16-byte pieces per row
-    const unsigned long long addr = (unsigned long long)my_row;
-    const uint32_t wb = smem_u32(wbuf);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < Q; ++i) sts128(wb + lane * EPI_ROW + (((uint32_t)i ^ ((uint32_t)lane >> 1)) & 3u) * 16, regs[i]);
     __syncwarp();
+    const int q = lane & 3;
 #pragma unroll
     for (int it = 0; it < Q; ++it) {
-        const int item = it * 32 + lane;
-        const int row = item / Q, q = item % Q;
+        const int row = it * 8 + (lane >> 2);
         const uint4 v = lds128(wb + row * EPI_ROW + (((uint32_t)q ^ ((uint32_t)row >> 1)) & 3u) * 16);
-        const unsigned long long ra = __shfl_sync(0xffffffffu, addr, row);
-        if ((okmask >> row) & 1u) *reinterpret_cast<uint4*>((uint8_t*)ra + q * 16) = v;
+        if ((okmask >> row) & 1u) *reinterpret_cast<uint4*>(base + rowoff[it] + q * 16) = v;
     }
 }
 
@@ -339,7 +337,10 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
             const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-            uint8_t* wbuf = epi_stage + (warp - 4) * EPI_WBUF;
+            const uint32_t wb = smem_u32(epi_stage + (warp - 4) * EPI_WBUF);
+            // this lane's row as (keypoint, output row) — one division per tile; column groups are powers of two wide
+            const int row_b = (ok ? row : 0) / G.Jout, row_j = (ok ? row : 0) - row_b * G.Jout;
+            const int og_shift = 31 - __clz(p.ogroup), og_count = G.Cout >> og_shift;
             constexpr int NCH = BN / 32;                           // 32-column chunks of the tile
             constexpr int CH0 = NCH >= 2 ? NCH / 2 : 0;           // chunks [0,CH0) -> half 0, [CH0,NCH) -> half 1
             const int cc_lo = half == 0 ? 0 : CH0, cc_hi = half == 0 ? (NCH >= 2 ? CH0 : 0) : NCH;
@@ -367,17 +368,22 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                             f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
                         }
                     }
-                    // element offset of this lane's row at this chunk's first column
-                    size_t blk;
+                    // element offset of this lane's row at this chunk's first column (32-bit: every output tensor of a pass
+                    // has fewer than 2^32 elements), then the offsets of the four row groups this lane STORES (rows it*8 + lane/4)
+                    uint32_t blk;
                     if (G.omap) {
-                        const int n = n0 + cc * 32, grp = n / p.ogroup;
-                        const int rr = ok ? row : 0;
-                        const int b = rr / G.Jout, j = rr - b * G.Jout;
-                        blk = ((size_t)b * p.out_J + omap_s[j * (G.Cout / p.ogroup) + grp]) * p.ogroup + (n - grp * p.ogroup);
+                        const int n = n0 + cc * 32, grp = n >> og_shift;
+                        blk = ((uint32_t)(row_b * p.out_J + omap_s[row_j * og_count + grp]) << og_shift) + (uint32_t)(n - (grp << og_shift));
                     } else {
-                        blk = (size_t)(ok ? row : 0) * G.Cout + n0 + cc * 32;
+                        blk = (uint32_t)(ok ? row : 0) * (uint32_t)G.Cout + (uint32_t)(n0 + cc * 32);
                     }
+                    uint32_t ro[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) ro[it] = __shfl_sync(0xffffffffu, blk, it * 8 + (lane >> 2));
                     if (p.out_raw) {
+                        uint32_t ro4[4];
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) ro4[it] = ro[it] * 4u;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint4 r4[4];
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                             for (int i = 0; i < 4; ++i)
                                 r4[i] = make_uint4(__float_as_uint(f[16 * h + 4 * i]), __float_as_uint(f[16 * h + 4 * i + 1]),
                                                    __float_as_uint(f[16 * h + 4 * i + 2]), __float_as_uint(f[16 * h + 4 * i + 3]));
-                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_raw + blk + 16 * h), lane, okmask);
+                            coalesced_store<64>(wb, r4, (uint8_t*)(p.out_raw + 16 * h), ro4, lane, okmask);
                         }
                     }
                     if (p.out_act || p.out_hi) {
@@ -395,6 +401,9 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                                 f[i] = fmaxf(fmaf(f[i], ep_scale[n0 + cc * 32 + i], ep_shift[n0 + cc * 32 + i]), 0.f);
                         }
                         if (p.out_act) {
+                            uint32_t ro4[4];
+#pragma unroll
+                            for (int it = 0; it < 4; ++it) ro4[it] = ro[it] * 4u;
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 uint4 r4[4];
@@ -402,26 +411,29 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                                 for (int i = 0; i < 4; ++i)
                                     r4[i] = make_uint4(__float_as_uint(f[16 * h + 4 * i]), __float_as_uint(f[16 * h + 4 * i + 1]),
                                                        __float_as_uint(f[16 * h + 4 * i + 2]), __float_as_uint(f[16 * h + 4 * i + 3]));
-                                coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_act + blk + 16 * h), lane, okmask);
+                                coalesced_store<64>(wb, r4, (uint8_t*)(p.out_act + 16 * h), ro4, lane, okmask);
                             }
                         }
                         if (p.out_hi) {
                             uint32_t hi[16], lo[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
-                                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
-                                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
-                                hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * i] - __uint_as_float(hi[i] << 16),
+                                                                                f[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
+                                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
                             }
+                            uint32_t ro2[4];
+#pragma unroll
+                            for (int it = 0; it < 4; ++it) ro2[it] = ro[it] * 2u;
                             uint4 r4[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) r4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_hi + blk), lane, okmask);
+                            coalesced_store<64>(wb, r4, (uint8_t*)p.out_hi, ro2, lane, okmask);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) r4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                            coalesced_store<64>(wbuf, r4, (uint8_t*)(p.out_lo + blk), lane, okmask);
+                            coalesced_store<64>(wb, r4, (uint8_t*)p.out_lo, ro2, lane, okmask);
                         }
                     }
                 }
@@ -566,7 +578,7 @@ static void tc_fill_group(TcGroup& G, const GLayer& L, const GConvArgs& a, int b
 
 int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStream_t st) {
     YARG(gconv_tc_eligible(L, a));
-    YARG(a.omap ? (!a.out_act && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0) : L.cout <= 512);
+    YARG(a.omap ? (!a.out_act && !a.resid && L.cout % a.ogroup == 0 && a.ogroup % 32 == 0 && (a.ogroup & (a.ogroup - 1)) == 0) : L.cout <= 512);
     TcArgs p;
     tc_fill_common(p, L, a, ctx);
     const int bn = tc_tile_n(L);
@@ -594,7 +606,7 @@ int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConv
         const GConvArgs& a = as[g];
         YARG(gconv_tc_eligible(L, a) && tc_tile_n(L) == 256 && a.omap && !a.out_act && !a.resid);
         YARG(L.cin == Ls[0]->cin && a.ogroup == as[0].ogroup && a.act_hi == as[0].act_hi && a.out_hi == as[0].out_hi &&
-             a.out_raw == as[0].out_raw && a.B == as[0].B && a.Jin == as[0].Jin && L.cout % a.ogroup == 0);
+             a.out_raw == as[0].out_raw && a.B == as[0].B && a.Jin == as[0].Jin && L.cout % a.ogroup == 0 && (a.ogroup & (a.ogroup - 1)) == 0);
         tc_fill_group(p.grp[g], L, a, 256, tiles, g * 32, 160 + g * 40);   // <= 25 index entries, <= 5 x 8 output-row entries
         tiles += ((p.grp[g].m_total + BM - 1) / BM) * p.grp[g].n_tiles;
     }
