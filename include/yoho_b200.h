@@ -197,6 +197,36 @@ int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, int M, const
                  const int32_t* order, int H, double inlier_dist, double* T, int32_t* best_iter,
                  int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream);
 
+/* "Next" row — the in-memory pair pipeline as ONE call: what Evaluator_PartI/II.run_onescene
+ * (tests/evaluator.py:41-47,112-117) does for one pair through files — Extract (both fragments) -> match -> PartI_Rindex ->
+ * yohoc.ransac -> PartII_R_pre -> yohoo.ransac — with everything device resident and a single host synchronisation (the
+ * match count).  Same stages, order and arguments as calling yoho_part1_forward x2, yoho_mutual_nn, yoho_rot_argmax,
+ * yoho_gather_kps, yoho_c_draw, yoho_c_ransac, yoho_part2_forward, yoho_o_order and yoho_o_score one by one (bit-identical
+ * results).  All pointers are device pointers; M-sized buffers have capacity min(Ka, Kb) rows.
+ * have_part1 = 1: eqvA/eqvB/descA/descB already hold the PartI outputs of the two fragments (amortised regime:
+ * tests/extractor.py:46-47 runs PartI once per fragment); 0: they are computed here.
+ * Degenerate rotation statistics (c_status = 1) give T_c = [I|0], c_best = -1; M = 0 gives both transforms = [I|0]. */
+typedef struct {
+    const float* featA; const float* featB;      /* FCGF group features [Ka,32,60], [Kb,32,60] */
+    const double* kpsA; const double* kpsB;      /* keypoints [Ka,3], [Kb,3] */
+    int Ka, Kb;
+    int have_part1;
+    int c_iters, o_iters;                        /* YOHO-C hypotheses / YOHO-O evaluation cap (tests/estimator.py max_iter) */
+    double c_dist, o_dist;                       /* ransac_c_inlinerdist / ransac_o_inlinerdist */
+    uint64_t seed;                               /* Philox seed of the device-side draws (yoho_c_draw, yoho_o_order) */
+    float* eqvA; float* eqvB;                    /* [K,32,60] */
+    float* descA; float* descB;                  /* [K,32] matcher descriptors (mean over the group axis) */
+    int64_t* pairs; int32_t* n_pairs;            /* [cap,2], [1] */
+    int64_t* dr_index;                           /* [cap] */
+    double* k0; double* k1;                      /* [cap,3] matched keypoints */
+    int32_t* hyp; int32_t* c_status;             /* [c_iters,3], [1] */
+    double* T_c; int32_t* c_best; int32_t* c_inl; uint8_t* c_mask;      /* [12], [1], [1], [cap] */
+    float* quat; double* trans;                  /* [cap,4], [cap,12] */
+    int32_t* order;                              /* [cap] */
+    double* T_o; int32_t* o_best; int32_t* o_inl; uint8_t* o_mask;      /* [12], [1], [1], [cap] */
+} yoho_pair_io;
+int yoho_register_pair(yoho_ctx* ctx, const yoho_pair_io* io, int32_t* M_host, void* stream);
+
 /* "Next" row — the tail of the group-feature lift, YOHO_testset.py:153-166: for every group rotation g,
  * rotate the keypoints (Keys @ R_g^T, float64), 1-NN of each into that rotation's down-sampled cloud (float64 distances
  * against float32 points, first minimal index), gather the 32-d backbone feature: out[k,:,g] = feats[offsets[g] + nn, :].

@@ -186,6 +186,37 @@ def test_scene_driver_matches_per_pair_pipeline(engine):
     assert _rot_err_deg(Tc[:, :3], a['R_gt']) < 3.0
 
 
+def test_fused_pair_call_equals_stage_by_stage(engine):
+    """yoho_register_pair (one C-ABI call per pair) returns bit for bit what the per-stage entry points return, cold and with
+    precomputed PartI outputs, including an unrelated pair (few matches) and an empty fragment."""
+    from yoho_b200.pipeline import PairPipeline
+    engine.load_part1(synth.synth_state_dict('PartI', 0))
+    engine.load_part2(synth.synth_state_dict('PartII', 0))
+    dev = engine.device
+    t = lambda v: torch.from_numpy(v).to(dev)
+    cases = [synth.make_fragment_pair(500, seed=31, overlap=0.6), synth.make_fragment_pair(333, seed=32, overlap=0.3)]
+    a, ka = synth.make_fragment(150, 5)
+    b, kb = synth.make_fragment(140, 6)
+    cases.append(dict(feat_A=a, feat_B=b, kps_A=ka, kps_B=kb))
+    keys = ['pairs', 'dr_index', 'k0', 'k1', 'hyp', 'c_status', 'T_c', 'c_best', 'c_inl', 'c_mask', 'quat', 'trans_pre', 'T_o',
+            'o_best', 'o_inl', 'o_mask', 'eqvA', 'eqvB']
+    for p in cases:
+        args = (t(p['feat_A']), t(p['feat_B']), t(p['kps_A']), t(p['kps_B']))
+        r1 = PairPipeline(engine, seed=9, fused=True).register(*args)
+        r0 = PairPipeline(engine, seed=9, fused=False).register(*args)
+        assert r1['M'] == r0['M'] and r1['M'] > 0
+        for k in keys:
+            assert torch.equal(torch.as_tensor(r1[k]).reshape(-1).cpu(), torch.as_tensor(r0[k]).reshape(-1).cpu()), k
+        o = engine.part1(args[0], want_inv=False, want_desc=True)
+        o2 = engine.part1(args[1], want_inv=False, want_desc=True)
+        r2 = PairPipeline(engine, seed=9, fused=True).register(*args, eqvA=o['eqv'], eqvB=o2['eqv'], descA=o['desc'], descB=o2['desc'])
+        assert r2['M'] == r1['M'] and torch.equal(r2['T_c'], r1['T_c']) and torch.equal(r2['T_o'], r1['T_o'])
+    z = torch.zeros((0, 32, 60), device=dev)
+    zk = torch.zeros((0, 3), dtype=torch.float64, device=dev)
+    r = PairPipeline(engine, seed=1).register(z, t(cases[0]['feat_B']), zk, t(cases[0]['kps_B']))
+    assert r['M'] == 0 and np.array_equal(r['T_c'].cpu().numpy(), np.eye(4)[:3]) and np.array_equal(r['T_o'].cpu().numpy(), np.eye(4)[:3])
+
+
 def test_register_stream_equals_per_pair_calls(engine):
     """The prefetching throughput call returns, pair by pair, exactly what the one-pair host call returns (same seeds)."""
     from yoho_b200.pipeline import PairPipeline

@@ -39,6 +39,19 @@ class yoho_fourier_irrep(ctypes.Structure):
                 ("w_in_host", _c_f), ("w_out_host", _c_f)]
 
 
+class yoho_pair_io(ctypes.Structure):
+    _fields_ = [("featA", ctypes.c_void_p), ("featB", ctypes.c_void_p), ("kpsA", ctypes.c_void_p), ("kpsB", ctypes.c_void_p),
+                ("Ka", ctypes.c_int), ("Kb", ctypes.c_int), ("have_part1", ctypes.c_int),
+                ("c_iters", ctypes.c_int), ("o_iters", ctypes.c_int),
+                ("c_dist", ctypes.c_double), ("o_dist", ctypes.c_double), ("seed", ctypes.c_uint64),
+                ("eqvA", ctypes.c_void_p), ("eqvB", ctypes.c_void_p), ("descA", ctypes.c_void_p), ("descB", ctypes.c_void_p),
+                ("pairs", ctypes.c_void_p), ("n_pairs", ctypes.c_void_p), ("dr_index", ctypes.c_void_p),
+                ("k0", ctypes.c_void_p), ("k1", ctypes.c_void_p), ("hyp", ctypes.c_void_p), ("c_status", ctypes.c_void_p),
+                ("T_c", ctypes.c_void_p), ("c_best", ctypes.c_void_p), ("c_inl", ctypes.c_void_p), ("c_mask", ctypes.c_void_p),
+                ("quat", ctypes.c_void_p), ("trans", ctypes.c_void_p), ("order", ctypes.c_void_p),
+                ("T_o", ctypes.c_void_p), ("o_best", ctypes.c_void_p), ("o_inl", ctypes.c_void_p), ("o_mask", ctypes.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/yoho_b200.h
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -63,6 +76,7 @@ SYMBOLS = {
     "yoho_c_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_o_order": (_i, [_vp, _i, ctypes.c_uint64, _vp, _vp]),
     "yoho_o_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yoho_register_pair": (_i, [_vp, _vp, _vp, _vp]),
     "yoho_lift_group_features": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_fmr_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_double, _vp, _vp]),
     "yoho_registration_errors": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

@@ -29,6 +29,7 @@ SOURCES = {
     "fourier.cu": [],
     "fourier_mma.cu": [],
     "fourier_tc.cu": [],
+    "pair.cu": [],
     "estimator.cu": ["-fmad=false"],
     "metrics.cu": ["-fmad=false"],
 }

@@ -282,6 +282,52 @@ class Engine:
             _lib.check(self.lib.yoho_registration_errors(self.h, _ptr(e), _ptr(g), _ptr(inf), n, _ptr(p), _ptr(re), _ptr(te), _stream()))
         return p, re, te
 
+    # ---- the whole pair in one call (csrc/pair.cu) ---------------------------------------------------------
+    def register_pair(self, featA, featB, kpsA, kpsB, c_iters, o_iters, c_dist, o_dist, seed, eqvA=None, eqvB=None,
+                      descA=None, descB=None):
+        """yoho_register_pair: PartI x2 (unless eqv/desc are given), mutual matching, rotation index, YOHO-C, PartII, YOHO-O with
+        ONE host round trip.  All M-sized results are views (first M rows) of one allocation sized for min(Ka, Kb) matches."""
+        fa, fb, ka, kb = self._f32(featA), self._f32(featB), self._f64(kpsA), self._f64(kpsB)
+        Ka, Kb = fa.shape[0], fb.shape[0]
+        cap = max(1, min(Ka, Kb))
+        have = eqvA is not None
+        if have:
+            eqvA, eqvB, descA, descB = self._f32(eqvA), self._f32(eqvB), self._f32(descA), self._f32(descB)
+        spec = [("pairs", (cap, 2), torch.int64), ("n_pairs", (1,), torch.int32), ("dr_index", (cap,), torch.int64),
+                ("k0", (cap, 3), torch.float64), ("k1", (cap, 3), torch.float64), ("hyp", (max(1, c_iters), 3), torch.int32),
+                ("c_status", (1,), torch.int32), ("T_c", (3, 4), torch.float64), ("c_best", (1,), torch.int32),
+                ("c_inl", (1,), torch.int32), ("c_mask", (cap,), torch.uint8), ("quat", (cap, 4), torch.float32),
+                ("trans", (cap, 3, 4), torch.float64), ("order", (cap,), torch.int32), ("T_o", (3, 4), torch.float64),
+                ("o_best", (1,), torch.int32), ("o_inl", (1,), torch.int32), ("o_mask", (cap,), torch.uint8)]
+        if not have:
+            spec += [("eqvA", (Ka, 32, 60), torch.float32), ("eqvB", (Kb, 32, 60), torch.float32),
+                     ("descA", (Ka, 32), torch.float32), ("descB", (Kb, 32), torch.float32)]
+        offs, total = [], 0
+        for _, shape, dt in spec:
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            offs.append(total)
+            total += (n + 255) // 256 * 256
+        buf = torch.empty((max(total, 256),), dtype=torch.uint8, device=self.device)
+        t = {}
+        for (name, shape, dt), o in zip(spec, offs):
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            t[name] = buf[o:o + n].view(dt).view(shape)
+        if have:
+            t.update(eqvA=eqvA, eqvB=eqvB, descA=descA, descB=descB)
+        io = _lib.yoho_pair_io()
+        dummy = buf.data_ptr()                       # an empty fragment has no storage: any valid pointer will do (never read)
+        io.featA, io.featB, io.kpsA, io.kpsB = (x.data_ptr() or dummy for x in (fa, fb, ka, kb))
+        io.Ka, io.Kb, io.have_part1 = Ka, Kb, int(have)
+        io.c_iters, io.o_iters, io.c_dist, io.o_dist, io.seed = int(c_iters), int(o_iters), float(c_dist), float(o_dist), int(seed)
+        for name in ("eqvA", "eqvB", "descA", "descB", "pairs", "n_pairs", "dr_index", "k0", "k1", "hyp", "c_status", "T_c",
+                     "c_best", "c_inl", "c_mask", "quat", "trans", "order", "T_o", "o_best", "o_inl", "o_mask"):
+            setattr(io, name, t[name].data_ptr())
+        M = ctypes.c_int32(0)
+        _lib.check(self.lib.yoho_register_pair(self.h, ctypes.byref(io), ctypes.byref(M), _stream()))
+        t["M"] = int(M.value)
+        t["_keep"] = (fa, fb, ka, kb)
+        return t
+
     # ---- E: estimators -----------------------------------------------------------------------------
     def gather_kps(self, kps0, kps1, pairs):
         k0, k1, pr = self._f64(kps0), self._f64(kps1), self._i64(pairs)

@@ -3,7 +3,8 @@ transforms, device resident between stages (the reference round-trips every stag
 tests/evaluator.py:41-47,112-117).  This is the unit of work of BASELINE.json's metric: one cold pair =
 PartI on both fragments, mutual matching, rotation index, YOHO-C, PartII, YOHO-O.
 
-One host synchronisation per pair (the match count M sizes the downstream launches).
+One host synchronisation per pair (the match count M sizes the downstream launches).  By default the whole pair is ONE
+C-ABI call (`yoho_register_pair`, csrc/pair.cu); `fused=False` walks the stages through the per-stage entry points instead.
 """
 import numpy as np
 import torch
@@ -16,13 +17,14 @@ class PairResult(dict):
 
 
 class PairPipeline:
-    def __init__(self, engine=None, c_iters=1000, o_iters=1000, c_dist=0.07, o_dist=0.09, seed=0):
+    def __init__(self, engine=None, c_iters=1000, o_iters=1000, c_dist=0.07, o_dist=0.09, seed=0, fused=True):
         self.eng = engine or get_engine()
         if not (self.eng.has_part1 and self.eng.has_part2):
             raise RuntimeError("load PartI and PartII weights into the engine first (No model exists)")
         self.c_iters, self.o_iters = int(c_iters), int(o_iters)
         self.c_dist, self.o_dist = float(c_dist), float(o_dist)
         self.seed = int(seed)
+        self.fused = bool(fused)      # one C-ABI call per pair (csrc/pair.cu); False: one call per stage (same results)
         self._copy_stream = None
 
     # ---- device-resident pair ------------------------------------------------------------------------
@@ -30,6 +32,21 @@ class PairPipeline:
         """All inputs CUDA tensors: feat [K,32,60] f32, kps [K,3] f64.  Pass precomputed eqv/desc to skip PartI
         (the amortised regime: one PartI pass per fragment per dataset, tests/extractor.py:46-47)."""
         e = self.eng
+        if self.fused:
+            if seed is None:
+                self.seed += 1
+                seed = self.seed
+            t = e.register_pair(featA, featB, kpsA, kpsB, self.c_iters, self.o_iters, self.c_dist, self.o_dist, seed,
+                                eqvA=eqvA, eqvB=eqvB, descA=descA, descB=descB)
+            M = t["M"]
+            out = PairResult(M=M, pairs=t["pairs"][:M], eqvA=t["eqvA"], eqvB=t["eqvB"], T_c=t["T_c"], T_o=t["T_o"])
+            if M == 0:
+                out.update(dr_index=t["dr_index"][:0], c_best=-1, o_best=-1)
+                return out
+            out.update(dr_index=t["dr_index"][:M], k0=t["k0"][:M], k1=t["k1"][:M], hyp=t["hyp"][:self.c_iters], c_status=t["c_status"],
+                       c_best=t["c_best"], c_inl=t["c_inl"], c_mask=t["c_mask"][:M], quat=t["quat"][:M], trans_pre=t["trans"][:M],
+                       o_best=t["o_best"], o_inl=t["o_inl"], o_mask=t["o_mask"][:M])
+            return out
         if eqvA is None:
             oa = e.part1(featA, want_inv=False, want_desc=True)
             eqvA, descA = oa["eqv"], oa["desc"]
