@@ -321,7 +321,7 @@ class Engine:
         io.c_iters, io.o_iters, io.c_dist, io.o_dist, io.seed = int(c_iters), int(o_iters), float(c_dist), float(o_dist), int(seed)
         for name in ("eqvA", "eqvB", "descA", "descB", "pairs", "n_pairs", "dr_index", "k0", "k1", "hyp", "c_status", "T_c",
                      "c_best", "c_inl", "c_mask", "quat", "trans", "order", "T_o", "o_best", "o_inl", "o_mask"):
-            setattr(io, name, t[name].data_ptr())
+            setattr(io, name, t[name].data_ptr() or dummy)
         M = ctypes.c_int32(0)
         _lib.check(self.lib.yoho_register_pair(self.h, ctypes.byref(io), ctypes.byref(M), _stream()))
         t["M"] = int(M.value)
