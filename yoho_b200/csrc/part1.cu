@@ -132,64 +132,44 @@ __global__ void __launch_bounds__(64) part1_finalize_kernel(const float* __restr
 }
 
 // Input side of the all-Fourier PartI: X0[m][c] = sum_g F[m][g] x[c][g], written as the bf16 hi/lo pair [B][60][32] that the
-// layer-1 per-irrep GEMMs consume.  CTAs of 128 threads stride over GROUPS OF FOUR keypoints with F^T resident in shared
-// memory; thread (c = t % 32, quarter = t / 32) accumulates the 16 coefficient rows m = 16*quarter .. +15 of its channel for
-// the four keypoints in registers: per group element four conflict-free scalar reads of x and four broadcast 16-byte reads of
-// F^T feed 64 FMAs (the kernel is shared-memory-bandwidth bound: a broadcast 16-byte read costs two wavefronts).
-constexpr int FIN_KP = 4;
+// layer-1 per-irrep GEMMs consume.  CTAs of 128 threads stride over the keypoints with F^T resident in shared memory; thread
+// (c = t % 32, quarter = t / 32) accumulates the 16 coefficient rows m = 16*quarter .. +15 of its channel in registers (one
+// conflict-free scalar read of x and four broadcast 16-byte reads of F^T per 16 FMAs).
 __global__ void __launch_bounds__(128) fourier_in_kernel(const float* __restrict__ x, const float* __restrict__ F,
                                                         unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
-    __shared__ float xs[FIN_KP][YF][YG + 1];
+    __shared__ float xs[YF][YG + 1];
     __shared__ __align__(16) float Ft[YG][64];           // Ft[g][m] = F[m][g], m padded to 64 with zeros
     const int t = threadIdx.x;
     for (int i = t; i < YG * 64; i += 128) {
-        const int m = i / YG, g = i - m * YG;            // coalesced read of F (rows m < 64: the last four are padding)
+        const int g = i >> 6, m = i & 63;
         Ft[g][m] = m < YG ? __ldg(F + m * YG + g) : 0.f;
     }
     const int c = t & 31, m0 = (t >> 5) * 16;
-    const int groups = (B + FIN_KP - 1) / FIN_KP;
-    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-        const int b0 = grp * FIN_KP;
-        const int nb = B - b0 < FIN_KP ? B - b0 : FIN_KP;
-        const float* src = x + (size_t)b0 * YF * YG;
-        __syncthreads();                                 // previous group's reads of xs are done (and Ft is complete)
-        for (int i = t; i < FIN_KP * YF * YG; i += 128) {
-            const int k = i / (YF * YG), r = i - k * (YF * YG);
-            xs[k][r / YG][r % YG] = k < nb ? src[i] : 0.f;
-        }
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* src = x + (size_t)b * YF * YG;
+        __syncthreads();                                 // previous keypoint's reads of xs are done (and Ft is complete)
+        for (int i = t; i < YF * YG; i += 128) xs[i / YG][i % YG] = src[i];
         __syncthreads();
-        float acc[FIN_KP][16];
+        float acc[16];
 #pragma unroll
-        for (int k = 0; k < FIN_KP; ++k)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[k][i] = 0.f;
-#pragma unroll 2
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 4
         for (int g = 0; g < YG; ++g) {
-            float xv[FIN_KP];
-#pragma unroll
-            for (int k = 0; k < FIN_KP; ++k) xv[k] = xs[k][c][g];
+            const float xv = xs[c][g];
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 f = *reinterpret_cast<const float4*>(&Ft[g][m0 + 4 * i4]);
-#pragma unroll
-                for (int k = 0; k < FIN_KP; ++k) {
-                    acc[k][4 * i4 + 0] = fmaf(f.x, xv[k], acc[k][4 * i4 + 0]); acc[k][4 * i4 + 1] = fmaf(f.y, xv[k], acc[k][4 * i4 + 1]);
-                    acc[k][4 * i4 + 2] = fmaf(f.z, xv[k], acc[k][4 * i4 + 2]); acc[k][4 * i4 + 3] = fmaf(f.w, xv[k], acc[k][4 * i4 + 3]);
-                }
+                acc[4 * i4 + 0] = fmaf(f.x, xv, acc[4 * i4 + 0]); acc[4 * i4 + 1] = fmaf(f.y, xv, acc[4 * i4 + 1]);
+                acc[4 * i4 + 2] = fmaf(f.z, xv, acc[4 * i4 + 2]); acc[4 * i4 + 3] = fmaf(f.w, xv, acc[4 * i4 + 3]);
             }
         }
+        const size_t o = (size_t)b * YG * YF + c;
 #pragma unroll
-        for (int k = 0; k < FIN_KP; ++k) {
-            if (k < nb) {
-                const size_t o = (size_t)(b0 + k) * YG * YF + c;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (m0 + i < YG) {
-                        const __nv_bfloat16 h = __float2bfloat16_rn(acc[k][i]);
-                        hi[o + (m0 + i) * YF] = __bfloat16_as_ushort(h);
-                        lo[o + (m0 + i) * YF] = __bfloat16_as_ushort(__float2bfloat16_rn(acc[k][i] - __bfloat162float(h)));
-                    }
-                }
+        for (int i = 0; i < 16; ++i) {
+            if (m0 + i < YG) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(acc[i]);
+                hi[o + (m0 + i) * YF] = __bfloat16_as_ushort(h);
+                lo[o + (m0 + i) * YF] = __bfloat16_as_ushort(__float2bfloat16_rn(acc[i] - __bfloat162float(h)));
             }
         }
     }
@@ -198,93 +178,83 @@ __global__ void __launch_bounds__(128) fourier_in_kernel(const float* __restrict
 // Output side of the all-Fourier PartI: the layer-4 result arrives as Fourier coefficients Y4 [B][60 m][32 c] (no bias);
 //     e[c][g] = bias4[c] + sum_m F[m][g] Y4[m][c] + x[c][g]
 // followed by the same tail as part1_finalize_kernel (both L2 norms, invariant pool, numpy's pairwise mean_g).
-// CTAs of 128 threads stride over PAIRS of keypoints with F resident in shared memory; 64 threads per keypoint: thread
-// (slot = u % 32, half = u / 32) accumulates 16 channels of the two group elements g = slot and slot + 32 in registers (two
-// scalar reads of F and four broadcast 16-byte reads of Y4 per 32 FMAs — shared-memory bandwidth is the bound here).
-constexpr int FO_KP = 2;
+// CTAs of 128 threads stride over the keypoints with F resident in shared memory; thread (g = t % 64 < 60, half = t / 64)
+// accumulates 16 channels of its group element in registers.
 __global__ void __launch_bounds__(128) part1_finalize_fourier_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
                                                                     const float* __restrict__ bias4, const float* __restrict__ x,
                                                                     float* __restrict__ eqv, float* __restrict__ inv,
                                                                     float* __restrict__ desc, int B) {
-    __shared__ float Fs[YG][64];                         // Fs[m][g], g padded to 64 with zeros
-    __shared__ __align__(16) float ys[FO_KP][YG][YF];
-    __shared__ float e[FO_KP][YF][YG + 1];
-    __shared__ float invn[FO_KP][YG];
-    __shared__ float red[FO_KP][YF];
+    __shared__ float Fs[YG][64];                         // Fs[m][g], g padded to 64 (threads g >= 60 read zeros)
+    __shared__ __align__(16) float ys[YG][YF];
+    __shared__ float e[YF][YG + 1];
+    __shared__ float invn[YG];
+    __shared__ float red[YF];
     const int t = threadIdx.x;
     for (int i = t; i < YG * 64; i += 128) {
         const int m = i >> 6, g = i & 63;
         Fs[m][g] = g < YG ? __ldg(F + m * YG + g) : 0.f;
     }
-    const int kp = t >> 6, u = t & 63;                   // keypoint of the pair, thread within the keypoint
-    const int g0 = u & 31, g1 = g0 + 32, c0 = (u >> 5) * 16;
-    const int groups = (B + FO_KP - 1) / FO_KP;
-    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-        const int b0 = grp * FO_KP;
-        const int nb = B - b0 < FO_KP ? B - b0 : FO_KP;
-        const bool live = kp < nb;
-        const int b = b0 + kp;
-        __syncthreads();                                 // previous pair done with ys / e / red (and Fs is complete)
-        for (int i = t; i < nb * (YG * YF / 4); i += 128)
-            reinterpret_cast<float4*>(&ys[0][0][0])[i] = reinterpret_cast<const float4*>(y4f + (size_t)b0 * YG * YF)[i];
+    const int g = t & 63, c0 = (t >> 6) * 16;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* xs = x + (size_t)b * YF * YG;
+        const float* yb = y4f + (size_t)b * YG * YF;
+        __syncthreads();                                 // previous keypoint done with ys / e / red (and Fs is complete)
+        for (int i = t; i < YG * YF / 4; i += 128) reinterpret_cast<float4*>(&ys[0][0])[i] = reinterpret_cast<const float4*>(yb)[i];
         __syncthreads();
-        if (live) {
-            float a0[16], a1[16];
+        {
+            float acc[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) a0[c] = a1[c] = __ldg(bias4 + c0 + c);
-#pragma unroll 2
+            for (int c = 0; c < 16; ++c) acc[c] = __ldg(bias4 + c0 + c);
+#pragma unroll 4
             for (int m = 0; m < YG; ++m) {
-                const float f0 = Fs[m][g0], f1 = Fs[m][g1];
+                const float f = Fs[m][g];
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 y = *reinterpret_cast<const float4*>(&ys[kp][m][c0 + c4 * 4]);
-                    a0[c4 * 4 + 0] = fmaf(f0, y.x, a0[c4 * 4 + 0]); a0[c4 * 4 + 1] = fmaf(f0, y.y, a0[c4 * 4 + 1]);
-                    a0[c4 * 4 + 2] = fmaf(f0, y.z, a0[c4 * 4 + 2]); a0[c4 * 4 + 3] = fmaf(f0, y.w, a0[c4 * 4 + 3]);
-                    a1[c4 * 4 + 0] = fmaf(f1, y.x, a1[c4 * 4 + 0]); a1[c4 * 4 + 1] = fmaf(f1, y.y, a1[c4 * 4 + 1]);
-                    a1[c4 * 4 + 2] = fmaf(f1, y.z, a1[c4 * 4 + 2]); a1[c4 * 4 + 3] = fmaf(f1, y.w, a1[c4 * 4 + 3]);
+                    const float4 y = *reinterpret_cast<const float4*>(&ys[m][c0 + c4 * 4]);
+                    acc[c4 * 4 + 0] = fmaf(f, y.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(f, y.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(f, y.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(f, y.w, acc[c4 * 4 + 3]);
                 }
             }
+            if (g < YG) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                e[kp][c0 + c][g0] = a0[c];
-                if (g1 < YG) e[kp][c0 + c][g1] = a1[c];
+                for (int c = 0; c < 16; ++c) e[c0 + c][g] = acc[c];
             }
         }
         __syncthreads();
-        for (int i = t; i < nb * YF * YG; i += 128) {
-            const int k = i / (YF * YG), r = i - k * (YF * YG);
-            e[k][r / YG][r % YG] += x[(size_t)b0 * YF * YG + i];
+        for (int i = t; i < YF * YG; i += 128) {
+            const int c = i / YG, gg = i % YG;
+            e[c][gg] = e[c][gg] + xs[i];
         }
         __syncthreads();
-        if (live && u < YG) {
+        if (t < YG) {
             float ss = 0.f;
 #pragma unroll
-            for (int c = 0; c < YF; ++c) ss = fmaf(e[kp][c][u], e[kp][c][u], ss);
-            invn[kp][u] = fmaxf(sqrtf(ss), 1e-4f);       // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
+            for (int c = 0; c < YF; ++c) ss = fmaf(e[c][t], e[c][t], ss);
+            invn[t] = fmaxf(sqrtf(ss), 1e-4f);   // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
         }
         // invariant pooling uses the UN-normalised e (utils/network.py:99 precedes :102)
-        float mean = 0.f;
-        if (live && u < YF) {
+        float m = 0.f;
+        if (t >= 64 && t < 64 + YF) {
             float sum = 0.f;
-            for (int gg = 0; gg < YG; ++gg) sum += e[kp][u][gg];
-            mean = sum / 60.0f;
-            red[kp][u] = mean * mean;
+            for (int gg = 0; gg < YG; ++gg) sum += e[t - 64][gg];
+            m = sum / 60.0f;
+            red[t - 64] = m * m;
         }
         __syncthreads();
-        if (live && u < YF && inv) {
+        if (t >= 64 && t < 64 + YF && inv) {
             float ss = 0.f;
-            for (int c = 0; c < YF; ++c) ss += red[kp][c];
-            inv[(size_t)b * YF + u] = mean / fmaxf(sqrtf(ss), 1e-4f);
+            for (int c = 0; c < YF; ++c) ss += red[c];
+            inv[(size_t)b * YF + t - 64] = m / fmaxf(sqrtf(ss), 1e-4f);
         }
-        for (int i = t; i < nb * YF * YG; i += 128) {
-            const int k = i / (YF * YG), r = i - k * (YF * YG);
-            const int c = r / YG, gg = r % YG;
-            const float v = e[k][c][gg] / invn[k][gg];
-            e[k][c][gg] = v;
-            eqv[(size_t)b0 * YF * YG + i] = v;
+        float* out = eqv + (size_t)b * YF * YG;
+        for (int i = t; i < YF * YG; i += 128) {
+            const int c = i / YG, gg = i % YG;
+            const float v = e[c][gg] / invn[gg];
+            e[c][gg] = v;
+            out[i] = v;
         }
         __syncthreads();
-        if (live && u < YF && desc) desc[(size_t)b * YF + u] = numpy_mean60(&e[kp][u][0], 1);
+        if (t < YF && desc) desc[(size_t)b * YF + t] = numpy_mean60(&e[t][0], 1);
     }
 }
 
@@ -351,8 +321,8 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             unsigned short* Y3h = X2l + R * 512;  unsigned short* Y3l = Y3h + R * 256;
             unsigned short* X3h = Y3l + R * 256;  unsigned short* X3l = X3h + R * 256;
             float* Y4 = (float*)(X3l + R * 256);
-            const int in_groups = (n + 3) / 4;                                   // four keypoints per CTA iteration, F resident in shared memory
-            fourier_in_kernel<<<in_groups < 4 * ctx->num_sms ? in_groups : 4 * ctx->num_sms, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
+            const int sgrid = n < 8 * ctx->num_sms ? n : 8 * ctx->num_sms;      // keypoint-striding CTAs, F resident in shared memory
+            fourier_in_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
             ctx->launches++;
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
@@ -390,8 +360,7 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             yoho_prof_end(ctx, st);
             // layer 4 (256 -> 32): Fourier coefficients of y4, FP32 [n][60][32]
             if (int rc = layer(ctx->p1f_out, X3h, X3l, nullptr, nullptr, Y4, 32, true)) return rc;
-            const int out_groups = (n + 1) / 2;                                  // two keypoints per CTA iteration
-            part1_finalize_fourier_kernel<<<out_groups < 4 * ctx->num_sms ? out_groups : 4 * ctx->num_sms, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+            part1_finalize_fourier_kernel<<<n < 6 * ctx->num_sms ? n : 6 * ctx->num_sms, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
                                                             inv ? inv + (size_t)s * YF : nullptr,
                                                             desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
             ctx->launches++;
