@@ -120,7 +120,7 @@ int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n_irreps, co
  * group-Fourier domain (needs yoho_part1_load_fourier). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
-/* Tuning knobs (experiments; defaults are the measured best).  key 0 = flag word: 1, 2 = producer protocol / lane map of the
+/* Tuning knobs (experiments; defaults are the measured best).  key 0 = flag word: 1 = non-blocking producer protocol of the (2: ignored)
  * tensor-core GEMM; 4, 8, 32, 64, 128 = older transform kernels (FP32 SIMT, block-tiled / single-buffered warp-MMA); 16 = one
  * launch per irrep; 256 = tcgen05 transform kernel (default on); 512 = keep PartI layers 1 and 4 as direct convolutions;
  * 1024 = PartII last group convolution as one GEMM instead of five tap-split partial GEMMs. */

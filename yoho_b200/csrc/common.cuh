@@ -53,7 +53,7 @@ struct yoho_ctx {
     int device = 0;
     int num_sms = 148;
     int gconv_impl = 0;
-    int tc_flags = 3 | 256;         // tuning flags: bit0 noinc producers, bit1 line lane map (gconv_tc.cu); 256 = tcgen05 transform kernel (fourier_tc.cu)
+    int tc_flags = 3 | 256;         // tuning flags: bit0 noinc producers (gconv_tc.cu; bit1 is ignored); 256 = tcgen05 transform kernel (fourier_tc.cu)
     int64_t launches = 0;
     // group tables on the device
     double* d_rot = nullptr;        // [60][9] f64

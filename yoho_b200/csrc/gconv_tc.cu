@@ -8,13 +8,13 @@
 // BF16 peak by construction.
 //
 // Kernel (persistent, one CTA per SM, 448 threads, warp-specialised):
-//   warps 0-3   A producers: each thread owns one of the 128 tile rows and gathers its 64-channel slice (hi and
-//               lo) for the current tap straight from L2 with 16-byte cp.async into the 128B-swizzled K-major
-//               layout UMMA expects — the group gather idx[j][k] is pure address arithmetic here.
-//   warp  12    W producer: the weights are pre-packed on the host as ready-made swizzled 32 KB tiles, so one
+//   warps 0-3   A producers: four lanes per tile row gather its 32-channel slice (hi and lo) for the current tap
+//               straight from L2 with 16-byte cp.async into the 64B-swizzled K-major layout UMMA expects — the
+//               group gather idx[j][k] is pure address arithmetic here.
+//   warp  12    W producer: the weights are pre-packed on the host as ready-made swizzled 16 KB tiles, so one
 //               cp.async.bulk (TMA, 1-D) per tile lands them in shared memory and signals the stage mbarrier.
-//   warp  13    MMA issuer: one thread issues 12 tcgen05.mma (M128 x N256 x K16, kind::f16) per 64-wide K block,
-//               accumulating all 13 taps x Cin channels of a tile in TMEM; tcgen05.commit releases the stage.
+//   warp  13    MMA issuer: one thread issues 6 tcgen05.mma (M128 x N256 x K16, kind::f16) per 32-wide K block (four
+//               48 KB stages), accumulating all taps x Cin channels of a tile in TMEM; tcgen05.commit releases the stage.
 //   warps 4-11  epilogue (two warps per TMEM lane quadrant, splitting the columns): tcgen05.ld the 128x256 FP32 accumulator (double-buffered in the 512 TMEM columns, so the
 //               next tile's MMAs overlap), add bias / residual, apply the NEXT layer's folded BN + ReLU, and write
 //               the activation as a bf16 hi/lo pair (the next layer's A operand) and/or FP32.
@@ -26,23 +26,27 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;                       // bf16 elements per K block = one 128-byte swizzle row
-constexpr int A_TILE = BM * BK * 2;          // 16 KB (hi or lo)
+constexpr int BK = 32;                       // bf16 elements per K block = one 64-byte swizzle row (SWIZZLE_64B)
+constexpr int A_TILE = BM * BK * 2;          // 8 KB (hi or lo)
 constexpr int THREADS = 448;               // 4 A-producer warps, 8 epilogue warps, W producer, MMA issuer
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_ROW = 64;                 // bytes per staged row (unpadded, XOR-swizzled: see coalesced_store)
 constexpr int EPI_WBUF = 32 * EPI_ROW;      // per-epilogue-warp staging buffer (2 KB)
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 
-// Tile width BN = 256 for the wide layers (2 stages of 96 KB, two 256-column accumulators = all of TMEM) and
-// BN = 32 for the 256 -> 32 output layer (4 stages of 40 KB; that layer is bound by streaming A from L2).
+// Tile width BN = 256 for the wide layers (4 stages of 48 KB, two 256-column accumulators = all of TMEM) and
+// BN = 32 for the 256 -> 32 output layer (8 stages of 20 KB; that layer is bound by streaming A from L2).
+// K blocks are 32 wide (64-byte rows, SWIZZLE_64B): with 64-wide blocks only TWO 96 KB stages fit, and the refill of a stage
+// (~1.6 us: commit -> producers -> L2) could not hide behind the 0.8 us of MMAs of the other one — the tensor pipe idled a
+// third of the time (ncu: 66-68 % active, the issuing thread spinning on the `full` barrier).  Four half-size stages keep
+// three refills in flight for the same shared memory.
 // SPLIT: the hi*hi products accumulate in one TMEM accumulator and the two small cross products (a_lo*w_hi, a_hi*w_lo)
 // in a second one, summed in FP32 (round-to-nearest) by the epilogue.  The tensor core truncates when it adds into
 // the accumulator, so the error grows with the number of accumulation steps at full magnitude: SPLIT cuts that chain
 // from 3*K/16 to K/16 steps.  With BN = 256 it uses all 512 TMEM columns for one tile (no epilogue overlap).
 template <int BN, bool SPLIT>
 struct Cfg {
-    static constexpr int STAGES = BN == 256 ? 2 : 4;
+    static constexpr int STAGES = BN == 256 ? 4 : 8;
     static constexpr int W_TILE = BN * BK * 2;                        // bytes (hi or lo)
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * BN;             // TMEM columns of one tile's accumulator(s)
@@ -83,7 +87,7 @@ struct TcArgs {
     __nv_bfloat16* out_lo;
     const float* scale;
     const float* shift;
-    int flags;                   // bit0: non-blocking producer completion, bit1: line-per-8-lanes producer mapping
+    int flags;                   // bit0: non-blocking producer completion (bit1, once a lane-map choice, is ignored)
     // remapped output rows (group-Fourier layers): columns are groups of `ogroup`; group i of GEMM row (b,j) is written to
     // row b*out_J + omap[j*n_groups + i] of an [.., ogroup]-wide output.
     int ogroup, out_J;
@@ -93,6 +97,14 @@ __device__ __forceinline__ int find_group(const TcArgs& p, int tile) {
     int g = 0;
     while (g + 1 < p.ngroups && tile >= p.grp[g + 1].tile_begin) ++g;
     return g;
+}
+
+// K-major operand tile, 64-byte rows, SWIZZLE_64B (16-byte chunk c of row r stored at c ^ ((r >> 1) & 3)), 8-row groups 512 B
+// apart (cute::UMMA::SmemDescriptor, layout type 4).
+__device__ __forceinline__ uint64_t umma_desc_sw64(const void* smem_tile) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem_tile) >> 4) & 0x3FFFull;
+    return addr | (1ull << 16) /* LBO (unused for swizzled K-major) */ | (32ull << 32) /* SBO = 512 B */ |
+           (1ull << 46) /* descriptor version: Blackwell */ | (4ull << 61) /* SWIZZLE_64B */;
 }
 
 struct __align__(8) Barriers {
@@ -197,29 +209,23 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
 
     if (warp < 4) {
         // ================= A producers =================
-        // Two lane mappings (p.flags bit 1):
-        //   line map : 8 consecutive lanes copy the 8 16-byte chunks of ONE 128-byte row segment, so a warp-wide cp.async
-        //              touches 4 cache lines; warp w owns tile rows [32w, 32w+32), lane (rsub = lane/8, c = lane%8) copies
-        //              chunk c of rows 32w + 4i + rsub, i = 0..7.
-        //   row map  : one tile row per thread, all 8 chunks (32 cache lines per warp-wide cp.async).
-        // Two completion protocols (p.flags bit 0):
-        //   noinc    : cp.async.mbarrier.arrive.noinc — the barrier arrival fires when this thread's copies land and the
-        //              thread moves on (CUTLASS sm100 cp.async mainloop); the MMA thread fences the proxy.
-        //   blocking : wait_group 0, fence.proxy.async, arrive.
-        const bool linemap = (p.flags & 2) != 0;
+        // Lane map: 4 consecutive lanes copy the 4 16-byte chunks of ONE 64-byte row segment, so a warp-wide cp.async touches 8
+        // rows; warp w owns tile rows [32w, 32w+32), lane (rsub = lane/4, c = lane%4) copies chunk c of rows 32w + 8i + rsub.
+        // Completion protocol (p.flags bit 0): noinc = cp.async.mbarrier.arrive.noinc — the barrier arrival fires when this
+        // thread's copies land and the thread moves on (the MMA thread fences the proxy); otherwise wait_group 0, fence, arrive.
         const bool noinc = (p.flags & 1) != 0;
-        const uint32_t c = (uint32_t)(lane & 7);
-        const int rsub = lane >> 3;
+        const uint32_t c = (uint32_t)(lane & 3);          // 16-byte chunk of the 64-byte row this lane copies
+        const int rsub = lane >> 2;                       // row within a group of 8
         uint32_t stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const TcGroup& G = p.grp[find_group(p, tile)];
             const int m_tile = (tile - G.tile_begin) / G.n_tiles;
             const int* idx_g = idx_s + G.idx_off;
-            int rowbase[8], rowj[8];
+            int rowbase[4], rowj[4];
             uint32_t okmask = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = linemap ? warp * 32 + 4 * i + rsub : (int)threadIdx.x;
+            for (int i = 0; i < 4; ++i) {
+                const int r = warp * 32 + 8 * i + rsub;
                 const int row = m_tile * BM + r;
                 const bool ok = row < G.m_total;
                 const int rr = ok ? row : 0;
@@ -230,20 +236,17 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
             }
             for (int kb = 0; kb < G.nkb; ++kb) {
                 uint8_t* st_hi = stage_base + stage * STAGE_BYTES;
+                // K axis = tap-major, channel-minor; a 32-wide block never straddles a tap (Cin % 32 == 0)
+                const int kk0 = kb * BK + (int)c * 8;
+                const int k = kk0 / p.Cin;
+                const int coff = kk0 - k * p.Cin;
                 mbar_wait(&bars->empty[stage], phase ^ 1);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    // K axis = tap-major, channel-minor, 8-channel chunks never straddle a tap (Cin % 8 == 0); with
-                    // Cin == 32 a 64-wide block spans two taps and the 14th half-block is zero padding.
-                    const uint32_t ch = linemap ? c : (uint32_t)i;
-                    const int kk0 = kb * BK + (int)ch * 8;
-                    const int k = kk0 / p.Cin;
-                    const int coff = kk0 - k * p.Cin;
-                    const bool tap_ok = k < G.taps;
-                    const int r = linemap ? warp * 32 + 4 * i + rsub : (int)threadIdx.x;
-                    const size_t off = ((size_t)(rowbase[i] + idx_g[rowj[i] + (tap_ok ? k : 0)])) * p.Cin + coff;
-                    uint8_t* dst = st_hi + r * 128 + ((ch ^ (uint32_t)(r & 7)) << 4);
-                    const bool ok = tap_ok && ((okmask >> i) & 1u);
+                for (int i = 0; i < 4; ++i) {
+                    const int r = warp * 32 + 8 * i + rsub;
+                    const size_t off = ((size_t)(rowbase[i] + idx_g[rowj[i] + k])) * p.Cin + coff;
+                    uint8_t* dst = st_hi + r * 64 + ((c ^ (uint32_t)((r >> 1) & 3)) << 4);
+                    const bool ok = (okmask >> i) & 1u;
                     cp_async16(dst, p.a_hi + off, ok);
                     cp_async16(dst + A_TILE, p.a_lo + off, ok);
                 }
@@ -296,8 +299,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                     if (p.flags & 1) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async data -> UMMA (async proxy)
                     tc_fence_after();
                     const uint8_t* st = stage_base + stage * STAGE_BYTES;
-                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
-                    const uint64_t w_hi = umma_desc(st + 2 * A_TILE), w_lo = umma_desc(st + 2 * A_TILE + W_TILE);
+                    const uint64_t a_hi = umma_desc_sw64(st), a_lo = umma_desc_sw64(st + A_TILE);
+                    const uint64_t w_hi = umma_desc_sw64(st + 2 * A_TILE), w_lo = umma_desc_sw64(st + 2 * A_TILE + W_TILE);
 #pragma unroll
                     for (uint32_t ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per 16 bf16, in 16-byte units
@@ -483,9 +486,9 @@ inline float bf2f(unsigned short h) {
 
 }  // namespace
 
-// Host-side packing: W_k[c][o] fp32 -> bf16 hi/lo, laid out as [n_tile][kb] ready-to-copy tiles (BN rows x 128 B) in the
-// UMMA K-major SWIZZLE_128B image (row r at r*128 bytes, 16-byte chunk j stored at position j ^ (r & 7)).
-// K axis = tap-major, channel-minor, zero-padded to a multiple of 64 (only Cin = 32 needs padding: 416 -> 448).
+// Host-side packing: W_k[c][o] fp32 -> bf16 hi/lo, laid out as [n_tile][kb] ready-to-copy tiles (BN rows x 64 B) in the
+// UMMA K-major SWIZZLE_64B image (row r at r*64 bytes, 16-byte chunk j stored at position j ^ ((r >> 1) & 3)).
+// K axis = tap-major, channel-minor (Cin is a multiple of 32: no padding).
 static int tc_tile_n(const GLayer& L) {
     if (L.taps != YT && !L.tc_dense) return 0;
     if (!(L.cin == 32 || L.cin % BK == 0)) return 0;
@@ -512,7 +515,7 @@ int gconv_tc_pack(yoho_ctx*, GLayer& L, const std::vector<float>& w) {
                     const int k = kk / L.cin, c = kk - k * L.cin;
                     const float v = w[((size_t)k * L.cin + c) * L.cout + nt * bn + r];
                     const unsigned short h = f2bf(v);
-                    const size_t pos = tile + (size_t)r * 64 + (size_t)(((i >> 3) ^ (r & 7)) << 3) + (i & 7);
+                    const size_t pos = tile + (size_t)r * BK + (size_t)(((i >> 3) ^ ((r >> 1) & 3)) << 3) + (i & 7);
                     hi[pos] = h;
                     lo[pos] = f2bf(v - bf2f(h));
                 }
@@ -587,7 +590,7 @@ int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStr
     p.total_tiles = ((p.grp[0].m_total + BM - 1) / BM) * p.grp[0].n_tiles;
     // split accumulators only where the accumulation chain is long; short-K layers (PartI layers 1 and 4, the group-Fourier
     // GEMMs) keep two accumulator buffers in flight so that their (relatively heavy) epilogue overlaps the next tile's MMAs
-    const bool split = ctx->gconv_impl >= 2 && p.grp[0].nkb >= 16 && !a.omap;
+    const bool split = ctx->gconv_impl >= 2 && p.grp[0].nkb * BK >= 1024 && !a.omap;
     if (bn == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
     return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);
 }
