@@ -261,6 +261,20 @@ def run_ours(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()                      # samples of both timed regions (device-resident and end-to-end)
+    # raw H2D rate of one pinned fragment on this box (diagnostic next to e2e: 77 MB per pair must cross this link)
+    h2d_gbs = None
+    try:
+        xs_pin = sets_p[0][0]
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            xs_dev = xs_pin.to(dev, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 4 * xs_pin.numel() * 4 / (c0.elapsed_time(c1) / 1e3) / 1e9
+    except Exception:
+        pass
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
     e2e = world * args.steps * K / (ms_e2e / 1000.0)
 
@@ -313,7 +327,8 @@ def run_ours(args):
                            "l2": f"inputs rotate over {N_SETS} distinct pairs ({N_SETS * 2 * K * 7680 / 1e6:.0f} MB) > 126 MB L2",
                            "weights": "seeded synthetic (yoho_b200.synth), reference architecture"},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": PairPipeline.h2d_bytes(K), "d2h_bytes_per_step": PairPipeline.d2h_bytes()},
+                        "h2d_bytes_per_step": PairPipeline.h2d_bytes(K), "d2h_bytes_per_step": PairPipeline.d2h_bytes(),
+                        "h2d_link_gbs": h2d_gbs},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "layers": prof}
         if cpu:

@@ -85,11 +85,15 @@ class PairPipeline:
     @staticmethod
     def pin(featA, featB, kpsA, kpsB):
         """numpy -> pinned host tensors (do this once per pair, outside any timed region)."""
+        from .hostutil import numa_local
+
         def p(a, dt):
             t = torch.empty(a.shape, dtype=dt, pin_memory=True)
             t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
             return t
-        return (p(featA, torch.float32), p(featB, torch.float32), p(kpsA, torch.float64), p(kpsB, torch.float64))
+        # allocate (and first-touch) on the memory node next to the GPU: the H2D DMA of 77 MB per pair reads it from there
+        with numa_local(torch.cuda.current_device() if torch.cuda.is_available() else 0):
+            return (p(featA, torch.float32), p(featB, torch.float32), p(kpsA, torch.float64), p(kpsB, torch.float64))
 
     def register_pinned(self, fa_pin, fb_pin, ka_pin, kb_pin):
         """Pinned host tensors in -> numpy transforms out.  The four H2D copies run on a side stream; PartI of fragment A
