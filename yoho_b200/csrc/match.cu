@@ -30,24 +30,35 @@ __global__ void __launch_bounds__(256) nn_tile_kernel(const float* __restrict__ 
     }
     __syncthreads();
     const int ta = t >> 4, tb = t & 15;   // 16 x 16 threads, 4 x 4 distances each
-    float d2[4][4];
+    // Packed FP32 (sub.f32x2 / fma.rn.f32x2, sm_100): the two lanes of a packed register are two NEIGHBOURING COLUMNS of the
+    // tile, so every distance is still one subtraction and one FMA per channel in ascending channel order (bit-identical to
+    // the scalar loop) at half the instruction count — this kernel is issue bound.
+    unsigned long long acc2[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d2[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i) { acc2[i][0] = 0ull; acc2[i][1] = 0ull; }
 #pragma unroll 8
     for (int f = 0; f < YF; ++f) {
         const float4 av = *reinterpret_cast<const float4*>(&As[f][ta * 4]);
         const float4 bv = *reinterpret_cast<const float4*>(&Bs[f][tb * 4]);
         const float a[4] = {av.x, av.y, av.z, av.w};
-        const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+        unsigned long long b01, b23;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(b01) : "f"(bv.x), "f"(bv.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(b23) : "f"(bv.z), "f"(bv.w));
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            unsigned long long aa, d01, d23;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
+            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(aa), "l"(b01));
+            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(aa), "l"(b23));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc2[i][0]) : "l"(d01));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc2[i][1]) : "l"(d23));
+        }
+    }
+    float d2[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float df = __fsub_rn(a[i], b[j]);
-                d2[i][j] = __fmaf_rn(df, df, d2[i][j]);
-            }
+    for (int i = 0; i < 4; ++i) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(d2[i][0]), "=f"(d2[i][1]) : "l"(acc2[i][0]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(d2[i][2]), "=f"(d2[i][3]) : "l"(acc2[i][1]));
     }
     unsigned long long rkey[4], ckey[4];
 #pragma unroll
