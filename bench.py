@@ -240,7 +240,7 @@ def run_ours(args):
     ev0.record()
     Ms = []
     for i in range(args.steps):
-        r = pipe.register(*sets_d[i % N_SETS])
+        r = pipe.register(*sets_d[i % N_SETS], lean=True)      # the two transforms + M (no per-stage tensor views on the host)
         Ms.append(r["M"])
     ev1.record()
     barrier()

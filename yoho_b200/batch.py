@@ -62,8 +62,11 @@ def register_scene(pipe: PairPipeline, fragments, pair_ids, timing=None):
         fa, ka, ea, da = cache[a]
         fb, kb, eb, db = cache[b]
         # the hypothesis draws are seeded by the pair's position, so the result does not depend on the sharding
-        r = pipe.register(fa, fb, ka, kb, eqvA=ea, eqvB=eb, descA=da, descB=db, seed=pipe.seed + 1 + pi)
-        out[n, 0], out[n, 1] = r["T_c"], r["T_o"]
+        r = pipe.register(fa, fb, ka, kb, eqvA=ea, eqvB=eb, descA=da, descB=db, seed=pipe.seed + 1 + pi, lean=pipe.fused)
+        if "T_co" in r:
+            out[n] = r["T_co"]
+        else:
+            out[n, 0], out[n, 1] = r["T_c"], r["T_o"]
     if ev:
         ev[2].record()
         torch.cuda.synchronize()

@@ -21,6 +21,24 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class PairBuffers:
+    """Outputs of one `yoho_register_pair` call: one device allocation + a name -> (offset, bytes, shape, dtype) table.
+    `out[name]` builds the tensor view on demand; `out.M` is the match count."""
+
+    def __init__(self, buf, ent, ext, M, keep):
+        self.buf, self.ent, self.ext, self.M, self._keep = buf, ent, ext, M, keep
+
+    def __getitem__(self, name):
+        if name in self.ext:
+            return self.ext[name]
+        if name == "T_c":
+            return self["T_co"][0]
+        if name == "T_o":
+            return self["T_co"][1]
+        o, n, shape, dt = self.ent[name]
+        return self.buf[o:o + n].view(dt).view(shape)
+
+
 class Engine:
     def __init__(self, device=None, so3_dir=None):
         if not torch.cuda.is_available():
@@ -283,50 +301,66 @@ class Engine:
         return p, re, te
 
     # ---- the whole pair in one call (csrc/pair.cu) ---------------------------------------------------------
+    _ESIZE = {torch.float32: 4, torch.float64: 8, torch.int64: 8, torch.int32: 4, torch.uint8: 1}
+    _PAIR_PTRS = ("eqvA", "eqvB", "descA", "descB", "pairs", "n_pairs", "dr_index", "k0", "k1", "hyp", "c_status", "T_c",
+                  "c_best", "c_inl", "c_mask", "quat", "trans", "order", "T_o", "o_best", "o_inl", "o_mask")
+
+    def _pair_layout(self, Ka, Kb, c_iters, have):
+        """Offsets of the per-pair outputs inside ONE allocation (cached per shape: the host cost of a pair is part of its time)."""
+        key = (Ka, Kb, c_iters, have)
+        cache = self.__dict__.setdefault("_pair_layouts", {})
+        lay = cache.get(key)
+        if lay is None:
+            cap = max(1, min(Ka, Kb))
+            # T_co holds the two results back to back (T_c = T_co[0], T_o = T_co[1]): one D2H copy for both
+            spec = [("T_co", (2, 3, 4), torch.float64), ("pairs", (cap, 2), torch.int64), ("n_pairs", (1,), torch.int32),
+                    ("dr_index", (cap,), torch.int64), ("k0", (cap, 3), torch.float64), ("k1", (cap, 3), torch.float64),
+                    ("hyp", (max(1, c_iters), 3), torch.int32), ("c_status", (1,), torch.int32), ("c_best", (1,), torch.int32),
+                    ("c_inl", (1,), torch.int32), ("c_mask", (cap,), torch.uint8), ("quat", (cap, 4), torch.float32),
+                    ("trans", (cap, 3, 4), torch.float64), ("order", (cap,), torch.int32), ("o_best", (1,), torch.int32),
+                    ("o_inl", (1,), torch.int32), ("o_mask", (cap,), torch.uint8)]
+            if not have:
+                spec += [("eqvA", (Ka, 32, 60), torch.float32), ("eqvB", (Kb, 32, 60), torch.float32),
+                         ("descA", (Ka, 32), torch.float32), ("descB", (Kb, 32), torch.float32)]
+            ent, total = {}, 0
+            for name, shape, dt in spec:
+                n = int(np.prod(shape)) * self._ESIZE[dt]
+                ent[name] = (total, n, shape, dt)
+                total += (n + 255) // 256 * 256
+            lay = cache[key] = (ent, max(total, 256))
+        return lay
+
     def register_pair(self, featA, featB, kpsA, kpsB, c_iters, o_iters, c_dist, o_dist, seed, eqvA=None, eqvB=None,
                       descA=None, descB=None):
         """yoho_register_pair: PartI x2 (unless eqv/desc are given), mutual matching, rotation index, YOHO-C, PartII, YOHO-O with
-        ONE host round trip.  All M-sized results are views (first M rows) of one allocation sized for min(Ka, Kb) matches."""
+        ONE host round trip.  Returns a `PairBuffers`: every output lives in one allocation sized for min(Ka, Kb) matches and is
+        materialised as a tensor view only when asked for (`out["quat"]`), so the throughput path pays for two views."""
         fa, fb, ka, kb = self._f32(featA), self._f32(featB), self._f64(kpsA), self._f64(kpsB)
         Ka, Kb = fa.shape[0], fb.shape[0]
-        cap = max(1, min(Ka, Kb))
         have = eqvA is not None
+        ent, total = self._pair_layout(Ka, Kb, int(c_iters), have)
+        buf = torch.empty((total,), dtype=torch.uint8, device=self.device)
+        base = buf.data_ptr()
+        ext = {}
         if have:
-            eqvA, eqvB, descA, descB = self._f32(eqvA), self._f32(eqvB), self._f32(descA), self._f32(descB)
-        spec = [("pairs", (cap, 2), torch.int64), ("n_pairs", (1,), torch.int32), ("dr_index", (cap,), torch.int64),
-                ("k0", (cap, 3), torch.float64), ("k1", (cap, 3), torch.float64), ("hyp", (max(1, c_iters), 3), torch.int32),
-                ("c_status", (1,), torch.int32), ("T_c", (3, 4), torch.float64), ("c_best", (1,), torch.int32),
-                ("c_inl", (1,), torch.int32), ("c_mask", (cap,), torch.uint8), ("quat", (cap, 4), torch.float32),
-                ("trans", (cap, 3, 4), torch.float64), ("order", (cap,), torch.int32), ("T_o", (3, 4), torch.float64),
-                ("o_best", (1,), torch.int32), ("o_inl", (1,), torch.int32), ("o_mask", (cap,), torch.uint8)]
-        if not have:
-            spec += [("eqvA", (Ka, 32, 60), torch.float32), ("eqvB", (Kb, 32, 60), torch.float32),
-                     ("descA", (Ka, 32), torch.float32), ("descB", (Kb, 32), torch.float32)]
-        offs, total = [], 0
-        for _, shape, dt in spec:
-            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
-            offs.append(total)
-            total += (n + 255) // 256 * 256
-        buf = torch.empty((max(total, 256),), dtype=torch.uint8, device=self.device)
-        t = {}
-        for (name, shape, dt), o in zip(spec, offs):
-            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
-            t[name] = buf[o:o + n].view(dt).view(shape)
-        if have:
-            t.update(eqvA=eqvA, eqvB=eqvB, descA=descA, descB=descB)
+            ext = dict(eqvA=self._f32(eqvA), eqvB=self._f32(eqvB), descA=self._f32(descA), descB=self._f32(descB))
         io = _lib.yoho_pair_io()
-        dummy = buf.data_ptr()                       # an empty fragment has no storage: any valid pointer will do (never read)
-        io.featA, io.featB, io.kpsA, io.kpsB = (x.data_ptr() or dummy for x in (fa, fb, ka, kb))
+        io.featA, io.featB, io.kpsA, io.kpsB = (x.data_ptr() or base for x in (fa, fb, ka, kb))   # empty fragment: any valid pointer
         io.Ka, io.Kb, io.have_part1 = Ka, Kb, int(have)
         io.c_iters, io.o_iters, io.c_dist, io.o_dist, io.seed = int(c_iters), int(o_iters), float(c_dist), float(o_dist), int(seed)
-        for name in ("eqvA", "eqvB", "descA", "descB", "pairs", "n_pairs", "dr_index", "k0", "k1", "hyp", "c_status", "T_c",
-                     "c_best", "c_inl", "c_mask", "quat", "trans", "order", "T_o", "o_best", "o_inl", "o_mask"):
-            setattr(io, name, t[name].data_ptr() or dummy)
+        for name in self._PAIR_PTRS:
+            if name in ext:
+                ptr = ext[name].data_ptr() or base
+            elif name == "T_c":
+                ptr = base + ent["T_co"][0]
+            elif name == "T_o":
+                ptr = base + ent["T_co"][0] + 96
+            else:
+                ptr = base + ent[name][0]
+            setattr(io, name, ptr)
         M = ctypes.c_int32(0)
         _lib.check(self.lib.yoho_register_pair(self.h, ctypes.byref(io), ctypes.byref(M), _stream()))
-        t["M"] = int(M.value)
-        t["_keep"] = (fa, fb, ka, kb)
-        return t
+        return PairBuffers(buf, ent, ext, int(M.value), (fa, fb, ka, kb))
 
     # ---- E: estimators -----------------------------------------------------------------------------
     def gather_kps(self, kps0, kps1, pairs):

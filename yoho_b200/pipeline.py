@@ -28,9 +28,11 @@ class PairPipeline:
         self._copy_stream = None
 
     # ---- device-resident pair ------------------------------------------------------------------------
-    def register(self, featA, featB, kpsA, kpsB, eqvA=None, eqvB=None, descA=None, descB=None, seed=None):
+    def register(self, featA, featB, kpsA, kpsB, eqvA=None, eqvB=None, descA=None, descB=None, seed=None, lean=False):
         """All inputs CUDA tensors: feat [K,32,60] f32, kps [K,3] f64.  Pass precomputed eqv/desc to skip PartI
-        (the amortised regime: one PartI pass per fragment per dataset, tests/extractor.py:46-47)."""
+        (the amortised regime: one PartI pass per fragment per dataset, tests/extractor.py:46-47).
+        lean=True (fused path only) returns just `M` and `T_co` ([2,3,4]: YOHO-C, YOHO-O) — the throughput callers' form, which
+        skips building the per-stage tensor views on the host."""
         e = self.eng
         if self.fused:
             if seed is None:
@@ -38,7 +40,9 @@ class PairPipeline:
                 seed = self.seed
             t = e.register_pair(featA, featB, kpsA, kpsB, self.c_iters, self.o_iters, self.c_dist, self.o_dist, seed,
                                 eqvA=eqvA, eqvB=eqvB, descA=descA, descB=descB)
-            M = t["M"]
+            M = t.M
+            if lean:                                  # throughput path: the two transforms (one contiguous [2,3,4] block) and M
+                return PairResult(M=M, T_co=t["T_co"], _buffers=t)
             out = PairResult(M=M, pairs=t["pairs"][:M], eqvA=t["eqvA"], eqvB=t["eqvB"], T_c=t["T_c"], T_o=t["T_o"])
             if M == 0:
                 out.update(dr_index=t["dr_index"][:0], c_best=-1, o_best=-1)
@@ -174,14 +178,14 @@ class PairPipeline:
             except StopIteration:
                 nxt = None
             main.wait_event(ev)
-            r = self.register(fa, fb, ka, kb)
+            r = self.register(fa, fb, ka, kb, lean=self.fused)
             free = torch.cuda.Event()
             free.record(main)                           # every kernel reading this input set has been queued
             self._in_free[n & 1] = free
             if not hasattr(self, "_res_pin"):
                 self._res_pin = [torch.empty((2, 3, 4), dtype=torch.float64, pin_memory=True) for _ in range(2)]
             host = self._res_pin[n & 1]
-            host.copy_(torch.stack([r["T_c"], r["T_o"]]), non_blocking=True)
+            host.copy_(r["T_co"] if "T_co" in r else torch.stack([r["T_c"], r["T_o"]]), non_blocking=True)
             dv = torch.cuda.Event()
             dv.record(main)
             if pending is not None:
