@@ -40,6 +40,7 @@ def register_scene(pipe: PairPipeline, fragments, pair_ids, timing=None):
             loc[fid] = (o["eqv"], o["desc"])
         eqvs = ydist.allgather_sharded([loc[f][0] for f in my_f], len(needed))
         descs = ydist.allgather_sharded([loc[f][1] for f in my_f], len(needed))
+        del loc                                   # the gathered copies are the ones phase 2 uses
         mine_f = {fid for pi in mine for fid in pair_ids[pi]}
         for i, fid in enumerate(needed):
             if fid in mine_f:
