@@ -166,8 +166,12 @@ def run_reference(args):
         return
     vals = []
     cores, sample = 0, ""
+    # bounded sample per step, sized so that the whole run stays within a few minutes whatever --steps asks for (the PartI
+    # sample dominates a step's wall time and its cost per keypoint is linear in the sample)
+    skp = 900 if args.steps <= 8 else 450 if args.steps <= 20 else 300
     for i in range(args.warmup + args.steps):
-        sec, cores, sample, _ = cpu_pair_seconds(args.kpts, sample_kp=300 if i < args.warmup else 900)
+        sec, cores, sample, _ = cpu_pair_seconds(args.kpts, sample_kp=300 if i < args.warmup else skp,
+                                                 sample_matches=256 if args.steps <= 20 else 128)
         if i >= args.warmup:
             vals.append(args.kpts / sec)
     v = float(np.mean(vals))
