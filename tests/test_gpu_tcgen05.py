@@ -177,6 +177,8 @@ def test_fourier_transform_kernels_agree(engine, tables):
         g = engine.part1(x)
         engine.set_tuning(0, 3 | 256 | 512)  # tcgen05 transform kernel, layers 1 and 4 as direct convolutions
         h = engine.part1(x)
+        engine.set_tuning(0, 3 | 256 | 2048)  # all-Fourier with the output side (inverse transform, norms, pools) on tensor cores
+        k2 = engine.part1(x)
         torch.cuda.synchronize()
     finally:
         engine.set_tuning(0, engine.DEFAULT_TUNING)
@@ -192,5 +194,10 @@ def test_fourier_transform_kernels_agree(engine, tables):
     e6, _ = _report("tcgen05-xf (layers 2+3) vs oracle", _np(h["eqv"]), ref["eqv"].numpy())
     assert e1 <= DESC_TOL and e2 <= DESC_TOL and e3 <= DESC_TOL and e4 <= 2e-5 and e5 <= DESC_TOL and e6 <= DESC_TOL
     assert float(np.abs(_np(g["inv"]) - ref["inv"].numpy()).max()) <= DESC_TOL
+    e7, _ = _report("all-Fourier, tensor-core output side vs oracle", _np(k2["eqv"]), ref["eqv"].numpy())
+    e8, _ = _report("all-Fourier, tensor-core output side vs SIMT output side", _np(k2["eqv"]), _np(g["eqv"]))
+    assert e7 <= DESC_TOL and e8 <= 2e-5
+    assert float(np.abs(_np(k2["inv"]) - ref["inv"].numpy()).max()) <= DESC_TOL
+    assert float(np.abs(_np(k2["desc"]) - _np(g["desc"])).max()) <= 2e-5
     assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], c2["eqv"]) and torch.equal(a["eqv"], d["eqv"])
     assert torch.equal(a["eqv"], e["eqv"]) and torch.equal(a["eqv"], f["eqv"])

@@ -17,6 +17,8 @@ passes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 eng = get_engine()
 eng.set_gconv_impl(os.environ.get("YOHO_B200_GCONV", "tcgen05_fourier"))
 eng.load_part1(synth.synth_state_dict("PartI", 2))
+if os.environ.get("YOHO_B200_TUNING"):
+    eng.set_tuning(0, int(os.environ["YOHO_B200_TUNING"]))
 x, _ = synth.make_fragment(K, 7)
 xd = torch.from_numpy(x).to(eng.device)
 eng.profile(True)

@@ -349,6 +349,187 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_transform_tc_kernel(const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Output side of the all-Fourier PartI on the same machinery (tuning flag 2048; the FP32 SIMT twin is part1_finalize_fourier_kernel):
+//     e[c][g] = bias4[c] + sum_m F[m][g] Y4[m][c] + x[c][g] ;  eqv = e / max(||e[:, g]||, 1e-4) ;  inv, desc as in part1.cu
+// Y4 arrives as a bf16 hi/lo pair [B][60][32].  A tile is FOUR keypoints x 32 channels = the 128 lanes of the UMMA M axis, so an
+// epilogue warp (TMEM lane quadrant q) holds one keypoint with one channel per lane and the 60 group elements as 60 columns:
+// the channel norms are warp-shuffle sums, the pools over the group axis are per-thread sums over registers, and every thread
+// reads / writes the 60 contiguous floats of its (keypoint, channel) row of x / eqv.  One product (inverse transform), same
+// producer / issuer / alternating epilogue sets as the one-product transform kernel.
+struct FinArgs {
+    const unsigned short* in_hi;      // [B][60][32] bf16 hi/lo of the layer-4 Fourier coefficients
+    const unsigned short* in_lo;
+    const unsigned short* m1_hi;      // inverse transform, [64 g][64 m] bf16 hi/lo
+    const unsigned short* m1_lo;
+    const float* bias4;               // [32]
+    const float* x;                   // [B][32][60] PartI input (the outer residual)
+    float* eqv;                       // [B][32][60]
+    float* inv;                       // [B][32] or nullptr
+    float* desc;                      // [B][32] or nullptr
+    int B, tiles;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(XT_THREADS, 1) group_finalize_tc_kernel(const FinArgs p) {
+    constexpr int NST = 3;
+    constexpr int STAGE = 2 * D_TILE;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* mats = smem;
+    uint8_t* stages = mats + 2 * M_IMG;
+    XtBars* bars = (XtBars*)(stages + NST * STAGE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 8; i += XT_THREADS) {
+        const int r = i >> 3, j = i & 7;
+        const uint32_t o = r * 128 + ((j ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(mats + o) = reinterpret_cast<const uint4*>(p.m1_hi)[i];
+        *reinterpret_cast<uint4*>(mats + M_IMG + o) = reinterpret_cast<const uint4*>(p.m1_lo)[i];
+    }
+    for (int i = threadIdx.x; i < NST * 2 * 2 * 32; i += XT_THREADS) {          // k rows 60..63 stay zero
+        const int img = i / 64, rem = i % 64, nb = rem / 32, q = rem % 32;
+        *reinterpret_cast<uint4*>(stages + (img / 2) * STAGE + (img % 2) * D_TILE + (nb * 8 + 7) * 1024 + 512 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&bars->full[s], 128); mbar_init(&bars->empty[s], 1); }
+        for (int e = 0; e < 2; ++e) { mbar_init(&bars->acc1_full[e], 1); mbar_init(&bars->acc1_empty[e], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp < 4) {
+        // producers: tile = keypoints 4*tile .. 4*tile+3; 16-byte chunk j16 of coefficient row k holds channels 8*(j16 % 4).. of
+        // keypoint j16 / 4 (missing keypoints of the last tile are zero filled)
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            uint8_t* st = stages + stage * STAGE;
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int item = threadIdx.x + 128 * i;               // 60 rows x 16 chunks
+                if (item < YG * 16) {
+                    const int k = item >> 4, j16 = item & 15, nb = j16 >> 3, j = j16 & 7;
+                    const uint32_t o = (nb * 8 + (k >> 3)) * 1024 + (k & 7) * 128 + ((j ^ (k & 7)) << 4);
+                    const int b = tile * 4 + (j16 >> 2);
+                    const bool ok = b < p.B;
+                    const size_t g = ((size_t)(ok ? b : 0) * YG + k) * YF + (j16 & 3) * 8;
+                    cp_async16(st + o, p.in_hi + g, ok);
+                    cp_async16(st + D_TILE + o, p.in_lo + g, ok);
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bars->full[stage])) : "memory");
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 12) {
+        if (lane == 0) {
+            const uint64_t b1h = umma_desc(mats), b1l = umma_desc(mats + M_IMG);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                const int a = it & 1;
+                mbar_wait(&bars->acc1_empty[a], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                mbar_wait(&bars->full[stage], phase);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                tc_fence_after();
+                const uint8_t* st = stages + stage * STAGE;
+                const uint64_t ah = umma_desc_mn(st, 8192u, 1024u), al = umma_desc_mn(st + D_TILE, 8192u, 1024u);
+                const uint32_t d = tmem_base + a * 64;
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks) {
+                    const uint64_t aadv = (uint64_t)(ks * 128), badv = (uint64_t)(ks * 2);
+                    tc_mma(d, ah + aadv, b1h + badv, IDESC_MN, ks ? 1u : 0u);
+                    tc_mma(d, al + aadv, b1h + badv, IDESC_MN, 1u);
+                    tc_mma(d, ah + aadv, b1l + badv, IDESC_MN, 1u);
+                }
+                tc_commit(&bars->empty[stage]);
+                tc_commit(&bars->acc1_full[a]);
+                if (++stage == NST) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 12) {
+        const int e = (warp - 4) >> 2;                       // epilogue set: even / odd local tiles
+        const int q = warp & 3;                              // TMEM lane quadrant = keypoint of the tile; lane = channel
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float b4 = __ldg(p.bias4 + lane);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            if ((it & 1) != e) continue;
+            const int b = tile * 4 + q;
+            const bool ok = b < p.B;                         // warp-uniform
+            mbar_wait(&bars->acc1_full[e], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[64];
+            tmem_ld32_nowait(tmem_base + e * 64 + lane_off, v);
+            tmem_ld32_nowait(tmem_base + e * 64 + 32 + lane_off, v + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&bars->acc1_empty[e]);
+            if (!ok) continue;
+            const size_t row = ((size_t)b * YF + lane) * YG;              // this thread's 60 contiguous floats of x / eqv
+            float ev[YG];
+#pragma unroll
+            for (int g4 = 0; g4 < YG / 4; ++g4) {
+                const float4 xv = *reinterpret_cast<const float4*>(p.x + row + 4 * g4);
+                ev[4 * g4 + 0] = (__uint_as_float(v[4 * g4 + 0]) + b4) + xv.x;
+                ev[4 * g4 + 1] = (__uint_as_float(v[4 * g4 + 1]) + b4) + xv.y;
+                ev[4 * g4 + 2] = (__uint_as_float(v[4 * g4 + 2]) + b4) + xv.z;
+                ev[4 * g4 + 3] = (__uint_as_float(v[4 * g4 + 3]) + b4) + xv.w;
+            }
+            // invariant pooling uses the UN-normalised e (utils/network.py:99 precedes :102)
+            if (p.inv) {
+                float sum = 0.f;
+#pragma unroll
+                for (int g = 0; g < YG; ++g) sum += ev[g];
+                const float mean = sum / 60.0f;
+                const float ss = warp_sum(mean * mean);
+                p.inv[(size_t)b * YF + lane] = mean / fmaxf(sqrtf(ss), 1e-4f);
+            }
+#pragma unroll
+            for (int g = 0; g < YG; ++g) {
+                const float ss = warp_sum(ev[g] * ev[g]);                  // sum over the 32 channels of this keypoint
+                ev[g] = ev[g] / fmaxf(sqrtf(ss), 1e-4f);                    // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
+            }
+#pragma unroll
+            for (int g4 = 0; g4 < YG / 4; ++g4)
+                *reinterpret_cast<float4*>(p.eqv + row + 4 * g4) = make_float4(ev[4 * g4], ev[4 * g4 + 1], ev[4 * g4 + 2], ev[4 * g4 + 3]);
+            if (p.desc) {
+                // numpy's float32 pairwise mean of 60 contiguous values (np.mean(feats, axis=-1), tests/matcher.py:35)
+                float r8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r8[j] = ev[j];
+#pragma unroll
+                for (int i = 8; i < 56; i += 8)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r8[j] = __fadd_rn(r8[j], ev[i + j]);
+                float res = __fadd_rn(__fadd_rn(__fadd_rn(r8[0], r8[1]), __fadd_rn(r8[2], r8[3])),
+                                      __fadd_rn(__fadd_rn(r8[4], r8[5]), __fadd_rn(r8[6], r8[7])));
+#pragma unroll
+                for (int i = 56; i < 60; ++i) res = __fadd_rn(res, ev[i]);
+                p.desc[(size_t)b * YF + lane] = __fdiv_rn(res, 60.0f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
 template <bool TWO, bool RES, bool FS>
 constexpr size_t xt_smem() { return 1024 + (size_t)(TWO ? 4 : 2) * M_IMG + (size_t)(FS ? 2 : TWO ? 4 : 3) * StageBytes<RES, FS>::value + (TWO ? 2 * 2 * A2_TILE : 0) + sizeof(XtBars) + 64; }
 static_assert(xt_smem<true, false, true>() <= 232448 && xt_smem<true, false, false>() <= 232448 && xt_smem<false, true, false>() <= 232448, "227 KB per CTA");
@@ -386,4 +567,19 @@ int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int 
     }
     if (resid) return xt_launch<false, true, false, 256>(ctx, p, st);
     return xt_launch<false, false, false, 256>(ctx, p, st);
+}
+
+// PartI output side on tensor cores (tuning flag 2048): see group_finalize_tc_kernel.
+int group_finalize_tc(yoho_ctx* ctx, const void* y4_hi, const void* y4_lo, int B, const void* minv_hi, const void* minv_lo, const float* bias4,
+                      const float* x, float* eqv, float* inv, float* desc, cudaStream_t st) {
+    YARG(B > 0 && y4_hi && y4_lo && minv_hi && minv_lo && bias4 && x && eqv);
+    FinArgs p{(const unsigned short*)y4_hi, (const unsigned short*)y4_lo, (const unsigned short*)minv_hi, (const unsigned short*)minv_lo,
+              bias4, x, eqv, inv, desc, B, (B + 3) / 4};
+    constexpr size_t smem = 1024 + 2 * M_IMG + 3 * 2 * D_TILE + sizeof(XtBars) + 64;
+    YCHECK(cudaFuncSetAttribute(group_finalize_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.tiles < ctx->num_sms ? p.tiles : ctx->num_sms;
+    group_finalize_tc_kernel<<<grid, XT_THREADS, smem, st>>>(p);
+    ctx->launches++;
+    YCHECK(cudaGetLastError());
+    return YOHO_OK;
 }

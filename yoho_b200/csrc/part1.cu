@@ -20,6 +20,8 @@ int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int 
                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                        void* out_hi, void* out_lo, cudaStream_t st, const void* in2_hi, const void* in2_lo);
 int gconv_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st);
+int group_finalize_tc(yoho_ctx* ctx, const void* y4_hi, const void* y4_lo, int B, const void* minv_hi, const void* minv_lo, const float* bias4,
+                      const float* x, float* eqv, float* inv, float* desc, cudaStream_t st);
 void yoho_prof_begin(yoho_ctx* ctx, int cls, double flops, cudaStream_t st);
 void yoho_prof_end(yoho_ctx* ctx, cudaStream_t st);
 
@@ -358,12 +360,22 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             if (int rc = group_transform_tc(ctx, Y3h, Y3l, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->d_p1_bias31, nullptr,
                                             ctx->p1_bn_out.scale, ctx->p1_bn_out.shift, X3h, X3l, st, Y1h, Y1l)) return rc;
             yoho_prof_end(ctx, st);
-            // layer 4 (256 -> 32): Fourier coefficients of y4, FP32 [n][60][32]
+            // layer 4 (256 -> 32): Fourier coefficients of y4 [n][60][32], then the output side (inverse transform, residual, norms,
+            // pools).  Tuning flag 2048: coefficients as a bf16 hi/lo pair and the output side on tensor cores (fourier_tc.cu).
+            if (ctx->tc_flags & 2048) {
+                unsigned short* Y4h = (unsigned short*)Y4;
+                unsigned short* Y4l = Y4h + R * 32;
+                if (int rc = layer(ctx->p1f_out, X3h, X3l, Y4h, Y4l, nullptr, 32, true)) return rc;
+                if (int rc = group_finalize_tc(ctx, Y4h, Y4l, n, ctx->d_inv_hi, ctx->d_inv_lo, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+                                               inv ? inv + (size_t)s * YF : nullptr, desc_mean ? desc_mean + (size_t)s * YF : nullptr, st)) return rc;
+            } else {
             if (int rc = layer(ctx->p1f_out, X3h, X3l, nullptr, nullptr, Y4, 32, true)) return rc;
-            part1_finalize_fourier_kernel<<<n < 6 * ctx->num_sms ? n : 6 * ctx->num_sms, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
-                                                            inv ? inv + (size_t)s * YF : nullptr,
-                                                            desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
+            const int fgrid = n < 6 * ctx->num_sms ? n : 6 * ctx->num_sms;
+            part1_finalize_fourier_kernel<<<fgrid, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+                                                                  inv ? inv + (size_t)s * YF : nullptr,
+                                                                  desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
             ctx->launches++;
+            }
             continue;
         }
         transpose_in_kernel<<<n, 128, 0, st>>>(xs, xt, tc ? xt_hi : nullptr, tc ? xt_lo : nullptr, n);
