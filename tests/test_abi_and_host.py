@@ -165,3 +165,38 @@ def test_make_scene_plants_consistent_pairwise_transforms():
         cor = np.array([(fi * fj[:, :, P[r]]).sum() for r in range(60)])
         r = int(cor.argmax())
         assert cor[r] > 0.9 * len(a) * 60 and np.sort(cor)[-2] < 0.5 * cor[r]
+
+
+def test_numa_local_restores_affinity():
+    """hostutil.numa_local is a best-effort context manager: whatever NVML answers (or fails to), the affinity is back afterwards."""
+    import os
+    from yoho_b200.hostutil import numa_local
+    before = os.sched_getaffinity(0)
+    with numa_local(0):
+        assert len(os.sched_getaffinity(0)) >= 1
+    assert os.sched_getaffinity(0) == before
+    try:
+        with numa_local(0):
+            raise KeyError("x")
+    except KeyError:
+        pass
+    assert os.sched_getaffinity(0) == before
+
+
+def test_pair_output_layout_is_aligned_and_disjoint():
+    """Engine._pair_layout (the single allocation behind yoho_register_pair's outputs): 256-byte aligned, non-overlapping
+    entries, T_c / T_o back to back in one [2,3,4] block, PartI outputs only when they are not supplied."""
+    import types
+    import torch
+    from yoho_b200.engine import Engine
+    me = types.SimpleNamespace(_ESIZE=Engine._ESIZE)
+    for Ka, Kb, iters, have in [(5000, 4000, 1000, False), (300, 300, 0, True), (0, 7, 10, False)]:
+        ent, total = Engine._pair_layout(me, Ka, Kb, iters, have)
+        spans = sorted((o, o + n) for (o, n, _, _) in ent.values())
+        assert all(o % 256 == 0 for o, _ in spans) and spans[-1][1] <= total
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+        assert ent["T_co"][2] == (2, 3, 4) and ent["T_co"][3] == torch.float64 and ent["T_co"][1] == 192
+        cap = max(1, min(Ka, Kb))
+        assert ent["pairs"][2] == (cap, 2) and ent["trans"][2] == (cap, 3, 4)
+        assert ("eqvA" in ent) == (not have)
+    assert Engine._pair_layout(me, 300, 300, 0, True) is Engine._pair_layout(me, 300, 300, 0, True)      # cached
