@@ -376,6 +376,10 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// STAGED (tuning flag 4096 on top of 2048, NOT yet run on hardware): the x / eqv rows of a keypoint (7680 contiguous bytes) pass
+// through a per-warp shared-memory tile, so the global accesses are lane-contiguous 16-byte pieces instead of 32 rows x 16 bytes
+// per warp instruction (the measured bound of the unstaged variant: 68 us against a 20 us HBM floor).
+template <bool STAGED>
 __global__ void __launch_bounds__(XT_THREADS, 1) group_finalize_tc_kernel(const FinArgs p) {
     constexpr int NST = 3;
     constexpr int STAGE = 2 * D_TILE;
@@ -383,7 +387,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_finalize_tc_kernel(const 
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* mats = smem;
     uint8_t* stages = mats + 2 * M_IMG;
-    XtBars* bars = (XtBars*)(stages + NST * STAGE);
+    uint8_t* xtiles = stages + NST * STAGE;                  // STAGED: 8 x 7680 B, one [32][60] FP32 tile per epilogue warp
+    XtBars* bars = (XtBars*)(xtiles + (STAGED ? 8 * YF * YG * 4 : 0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 64 * 8; i += XT_THREADS) {
         const int r = i >> 3, j = i & 7;
@@ -469,6 +474,13 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_finalize_tc_kernel(const 
             if ((it & 1) != e) continue;
             const int b = tile * 4 + q;
             const bool ok = b < p.B;                         // warp-uniform
+            float* sx = reinterpret_cast<float*>(xtiles) + (warp - 4) * (YF * YG);
+            if (STAGED && ok) {                              // this keypoint's x tile, lane-contiguous, while the product is still running
+                const float4* gx = reinterpret_cast<const float4*>(p.x + (size_t)b * YF * YG);
+#pragma unroll
+                for (int t4 = 0; t4 < YF * YG / 4 / 32; ++t4) reinterpret_cast<float4*>(sx)[t4 * 32 + lane] = gx[t4 * 32 + lane];
+                __syncwarp();
+            }
             mbar_wait(&bars->acc1_full[e], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             uint32_t v[64];
@@ -482,7 +494,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_finalize_tc_kernel(const 
             float ev[YG];
 #pragma unroll
             for (int g4 = 0; g4 < YG / 4; ++g4) {
-                const float4 xv = *reinterpret_cast<const float4*>(p.x + row + 4 * g4);
+                const float4 xv = STAGED ? *reinterpret_cast<const float4*>(sx + lane * YG + 4 * g4)
+                                         : *reinterpret_cast<const float4*>(p.x + row + 4 * g4);
                 ev[4 * g4 + 0] = (__uint_as_float(v[4 * g4 + 0]) + b4) + xv.x;
                 ev[4 * g4 + 1] = (__uint_as_float(v[4 * g4 + 1]) + b4) + xv.y;
                 ev[4 * g4 + 2] = (__uint_as_float(v[4 * g4 + 2]) + b4) + xv.z;
@@ -502,9 +515,21 @@ __global__ void __launch_bounds__(XT_THREADS, 1) group_finalize_tc_kernel(const 
                 const float ss = warp_sum(ev[g] * ev[g]);                  // sum over the 32 channels of this keypoint
                 ev[g] = ev[g] / fmaxf(sqrtf(ss), 1e-4f);                    // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
             }
+            if (STAGED) {
+                __syncwarp();                                // every lane has read its x row
 #pragma unroll
-            for (int g4 = 0; g4 < YG / 4; ++g4)
-                *reinterpret_cast<float4*>(p.eqv + row + 4 * g4) = make_float4(ev[4 * g4], ev[4 * g4 + 1], ev[4 * g4 + 2], ev[4 * g4 + 3]);
+                for (int g4 = 0; g4 < YG / 4; ++g4)
+                    *reinterpret_cast<float4*>(sx + lane * YG + 4 * g4) = make_float4(ev[4 * g4], ev[4 * g4 + 1], ev[4 * g4 + 2], ev[4 * g4 + 3]);
+                __syncwarp();
+                float4* ge = reinterpret_cast<float4*>(p.eqv + (size_t)b * YF * YG);
+#pragma unroll
+                for (int t4 = 0; t4 < YF * YG / 4 / 32; ++t4) ge[t4 * 32 + lane] = reinterpret_cast<const float4*>(sx)[t4 * 32 + lane];
+                __syncwarp();                                // the tile is free for this warp's next keypoint
+            } else {
+#pragma unroll
+                for (int g4 = 0; g4 < YG / 4; ++g4)
+                    *reinterpret_cast<float4*>(p.eqv + row + 4 * g4) = make_float4(ev[4 * g4], ev[4 * g4 + 1], ev[4 * g4 + 2], ev[4 * g4 + 3]);
+            }
             if (p.desc) {
                 // numpy's float32 pairwise mean of 60 contiguous values (np.mean(feats, axis=-1), tests/matcher.py:35)
                 float r8[8];
@@ -569,16 +594,22 @@ int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int 
     return xt_launch<false, false, false, 256>(ctx, p, st);
 }
 
-// PartI output side on tensor cores (tuning flag 2048): see group_finalize_tc_kernel.
+// PartI output side on tensor cores (tuning flag 2048; + 4096: shared-memory staged row accesses): see group_finalize_tc_kernel.
 int group_finalize_tc(yoho_ctx* ctx, const void* y4_hi, const void* y4_lo, int B, const void* minv_hi, const void* minv_lo, const float* bias4,
                       const float* x, float* eqv, float* inv, float* desc, cudaStream_t st) {
     YARG(B > 0 && y4_hi && y4_lo && minv_hi && minv_lo && bias4 && x && eqv);
     FinArgs p{(const unsigned short*)y4_hi, (const unsigned short*)y4_lo, (const unsigned short*)minv_hi, (const unsigned short*)minv_lo,
               bias4, x, eqv, inv, desc, B, (B + 3) / 4};
-    constexpr size_t smem = 1024 + 2 * M_IMG + 3 * 2 * D_TILE + sizeof(XtBars) + 64;
-    YCHECK(cudaFuncSetAttribute(group_finalize_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool staged = (ctx->tc_flags & 4096) != 0;
+    const size_t smem = 1024 + 2 * M_IMG + 3 * 2 * D_TILE + (staged ? 8 * YF * YG * 4 : 0) + sizeof(XtBars) + 64;
     const int grid = p.tiles < ctx->num_sms ? p.tiles : ctx->num_sms;
-    group_finalize_tc_kernel<<<grid, XT_THREADS, smem, st>>>(p);
+    if (staged) {
+        YCHECK(cudaFuncSetAttribute(group_finalize_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_finalize_tc_kernel<true><<<grid, XT_THREADS, smem, st>>>(p);
+    } else {
+        YCHECK(cudaFuncSetAttribute(group_finalize_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_finalize_tc_kernel<false><<<grid, XT_THREADS, smem, st>>>(p);
+    }
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
