@@ -124,7 +124,8 @@ int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
  * tensor-core GEMM; 4, 8, 32, 64, 128 = older transform kernels (FP32 SIMT, block-tiled / single-buffered warp-MMA); 16 = one
  * launch per irrep; 256 = tcgen05 transform kernel (default on); 512 = keep PartI layers 1 and 4 as direct convolutions;
  * 1024 = PartII last group convolution as one GEMM instead of five tap-split partial GEMMs; 2048 = PartI output side (inverse
- * transform of the layer-4 coefficients, residual, norms, pools) on the tcgen05 transform machinery (experimental, default off). */
+ * transform of the layer-4 coefficients, residual, norms, pools) on the tcgen05 transform machinery, 4096 = the same with
+ * shared-memory staged row accesses (both experimental, parity-green, not faster yet: default off). */
 int yoho_set_tuning(yoho_ctx* ctx, int key, int value);
 
 /* A1-A6 — PartI_test.forward (utils/network.py:86-105,140-147) on B keypoints.
