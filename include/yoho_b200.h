@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YOHO_ABI_VERSION 2
+#define YOHO_ABI_VERSION 3
 #define YOHO_G 60      /* group order */
 #define YOHO_TAPS 13   /* group-convolution kernel support */
 #define YOHO_F 32      /* descriptor channels */
@@ -183,12 +183,16 @@ int yoho_c_draw(yoho_ctx* ctx, const int64_t* dr_index, int M, int iters, uint64
 
 /* E2-E4 — yohoc.ransac inner loop over a pre-drawn hypothesis list (tests/estimator.py:55-70,119-137).
  * k0/k1 float64 [M,3] matched keypoints; hyp int32 [iters,3] match ids; signs int8[iters] or NULL
- * (0 = sign rule of DESIGN.md, +1/-1 = forced determinant of the null-space completion).
+ * (0 = sign rule of DESIGN.md, +1/-1 = forced determinant of the null-space completion, 2 = take the caller's transform
+ * fixed[h] for this hypothesis); fixed float64 [iters,3,4] or NULL.  The reference's R = V U^T depends on LAPACK's
+ * arbitrary sign for the null-space singular pair of the rank-2 cross-covariance (and on its arbitrary completion of a
+ * rank-1 one, when a match was drawn twice): a reference-identical run passes sign(det(V U^T)) of np.linalg.svd per
+ * hypothesis and LAPACK's transform for the rank-deficient triplets (yoho_b200/estimator.py does).
  * Outputs (device): T float64[12] ([I|0] if nothing scores), best_iter int32 (0-based, -1 if none),
  * n_inl int32, mask uint8[M] (inliers of the winner), counts int32[iters] (may be NULL). */
 int yoho_c_ransac(yoho_ctx* ctx, const double* k0, const double* k1, int M, const int32_t* hyp,
-                  const int8_t* signs, int iters, double inlier_dist, double* T, int32_t* best_iter,
-                  int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream);
+                  const int8_t* signs, const double* fixed, int iters, double inlier_dist, double* T,
+                  int32_t* best_iter, int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream);
 
 /* Device-side random evaluation order for YOHO-O (np.random.shuffle(index), tests/estimator.py:321-323). */
 int yoho_o_order(yoho_ctx* ctx, int M, uint64_t seed, int32_t* order, void* stream);

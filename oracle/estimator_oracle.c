@@ -164,10 +164,11 @@ int32_t yoho_oracle_count_inliers(const double* k0, const double* k1, int32_t M,
     return n;
 }
 
-/* E4 over a pre-drawn hypothesis list.  signs may be NULL (rule) or int8[iters] in {-1,0,+1}.
+/* E4 over a pre-drawn hypothesis list.  signs may be NULL (rule) or int8[iters] in {-1,0,+1,2}; 2 = take the caller's
+ * transform fixed[it] (float64 [iters,12]) for that hypothesis instead of the Kabsch solve.
  * counts/degen may be NULL.  best_iter = -1 and T = [I|0] when no hypothesis has an inlier. */
 void yoho_oracle_yohoc(const double* k0, const double* k1, int32_t M, const int32_t* hyp, int32_t iters,
-                       const int8_t* signs, double dist, double T_best[12], int32_t* best_iter,
+                       const int8_t* signs, const double* fixed, double dist, double T_best[12], int32_t* best_iter,
                        int32_t* n_inl, uint8_t* mask, int32_t* counts, uint8_t* degen) {
     double thr2 = dist * dist;
     int32_t best = 0, bi = -1;
@@ -175,6 +176,7 @@ void yoho_oracle_yohoc(const double* k0, const double* k1, int32_t M, const int3
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) T_best[4 * r + c] = (r == c) ? 1.0 : 0.0;
     for (int32_t it = 0; it < iters; ++it) {
         int dg = yoho_oracle_kabsch3(k0, k1, hyp + 3 * it, signs ? signs[it] : 0, T);
+        if (signs && fixed && signs[it] == 2) memcpy(T, fixed + 12 * (size_t)it, sizeof(T));
         int32_t n = yoho_oracle_count_inliers(k0, k1, M, T, thr2, 0);
         if (counts) counts[it] = n;
         if (degen) degen[it] = (uint8_t)dg;

@@ -27,7 +27,7 @@ def lib():
         L.yoho_oracle_kabsch3.restype = ctypes.c_int
         L.yoho_oracle_count_inliers.argtypes = [d, d, ctypes.c_int32, d, ctypes.c_double, u8]
         L.yoho_oracle_count_inliers.restype = ctypes.c_int32
-        L.yoho_oracle_yohoc.argtypes = [d, d, ctypes.c_int32, i32, ctypes.c_int32, i8, ctypes.c_double,
+        L.yoho_oracle_yohoc.argtypes = [d, d, ctypes.c_int32, i32, ctypes.c_int32, i8, d, ctypes.c_double,
                                         d, i32, i32, u8, i32, u8]
         L.yoho_oracle_yohoc.restype = None
         L.yoho_oracle_yohoo.argtypes = [d, d, ctypes.c_int32, d, ctypes.c_int32, ctypes.c_double,
@@ -59,16 +59,17 @@ def count_inliers(k0, k1, T, dist):
     return int(n), mask
 
 
-def yohoc(k0, k1, hyp, dist, signs=None):
+def yohoc(k0, k1, hyp, dist, signs=None, fixed=None):
     """Returns dict(T[3,4], best_iter, n_inl, mask[M], counts[iters], degenerate[iters])."""
     k0 = np.ascontiguousarray(k0, np.float64); k1 = np.ascontiguousarray(k1, np.float64)
     hyp = np.ascontiguousarray(hyp, np.int32).reshape(-1, 3)
     M, iters = k0.shape[0], hyp.shape[0]
     sg = None if signs is None else np.ascontiguousarray(signs, np.int8)
+    fx = None if fixed is None else np.ascontiguousarray(fixed, np.float64).reshape(-1)
     T = np.zeros(12); bi = np.zeros(1, np.int32); ni = np.zeros(1, np.int32)
     mask = np.zeros(M, np.uint8); counts = np.zeros(iters, np.int32); dg = np.zeros(iters, np.uint8)
     lib().yoho_oracle_yohoc(_p(k0, ctypes.c_double), _p(k1, ctypes.c_double), M, _p(hyp, ctypes.c_int32), iters,
-                            _p(sg, ctypes.c_int8), float(dist), _p(T, ctypes.c_double), _p(bi, ctypes.c_int32),
+                            _p(sg, ctypes.c_int8), _p(fx, ctypes.c_double), float(dist), _p(T, ctypes.c_double), _p(bi, ctypes.c_int32),
                             _p(ni, ctypes.c_int32), _p(mask, ctypes.c_uint8), _p(counts, ctypes.c_int32),
                             _p(dg, ctypes.c_uint8))
     return dict(T=T.reshape(3, 4), best_iter=int(bi[0]), n_inl=int(ni[0]), mask=mask, counts=counts,

@@ -7,7 +7,8 @@ Outputs (tests/golden/):
   pipeline_synth.npz     the reference's whole file-based pipeline on one synthetic 128-keypoint pair with the
                          seeded synthetic weights of yoho_b200.synth (regenerable anywhere from the seed):
                          Extract -> match -> PartI_Rindex -> yohoc.ransac -> PartII_R_pre -> yohoo.ransac,
-                         plus the per-iteration triplets / SVD signs / scores the reference's yohoc loop saw.
+                         plus the per-iteration triplets / SVD signs / scores the reference's yohoc loop saw, the
+                         `center` array of its YOHO_C npz and the bytes of both `pre.log` files.
   stages_synth.npz       stage-level vectors on other seeds: PartI (eqv, inv), KNN both ways, rotation
                          correlation, PartII quaternion.
   pipeline_realckpt.npz  same as pipeline_synth with the reference's shipped checkpoints (the test that uses it
@@ -125,7 +126,12 @@ def run_pipeline(ref, tmp, sdI, sdII, pair, seed, max_iter=1000):
     m = os.path.join(base, 'Match')
     c = np.load(os.path.join(m, 'YOHO_C', f'{max_iter}iters', '0-1.npz'), allow_pickle=True)
     o = np.load(os.path.join(m, 'YOHO_O', f'{max_iter}iters', '0-1.npz'), allow_pickle=True)
+    def _bytes(fn):
+        with open(fn, 'rb') as f:
+            return np.frombuffer(f.read(), dtype=np.uint8).copy()
     out = dict(
+        c_center=np.asarray(c['center']), c_prelog=_bytes(os.path.join(m, 'YOHO_C', f'{max_iter}iters', 'pre.log')),
+        o_prelog=_bytes(os.path.join(m, 'YOHO_O', f'{max_iter}iters', 'pre.log')),
         eqv0=np.load(os.path.join(base, 'YOHO_Output_Group_feature', '0.npy')),
         eqv1=np.load(os.path.join(base, 'YOHO_Output_Group_feature', '1.npy')),
         matches=np.load(os.path.join(m, '0-1.npy')),

@@ -296,9 +296,16 @@ def test_c_ransac_golden_replay(engine):
         ok = ~want["degenerate"]
         ref_counts = np.rint(g["c_overlap"] * m.shape[0]).astype(np.int64)
         assert np.array_equal(_np(res["counts"])[ok], ref_counts[ok])
-        if ok[: int(g["c_recalltime"])].all():
-            assert int(res["best_iter"].item()) + 1 == int(g["c_recalltime"])
-            assert np.abs(_np(res["T"]) - g["c_trans"][:3]).max() <= 1e-9
+        # full replay: rank-deficient triplets take LAPACK's (arbitrary) transform as recorded from the reference, so
+        # EVERY per-hypothesis count, the winner and the transform are the reference's
+        signs = g["c_sign"].copy()
+        signs[~ok] = 2
+        res = engine.c_ransac(k0, k1, g["c_hyp"], float(g["c_dist"]), signs=signs, fixed=g["c_hyp_trans"], want_counts=True)
+        want = E.yohoc(k0, k1, g["c_hyp"], float(g["c_dist"]), signs=signs, fixed=g["c_hyp_trans"])
+        assert np.array_equal(_np(res["counts"]), ref_counts) and np.array_equal(want["counts"], ref_counts)
+        assert int(res["best_iter"].item()) + 1 == int(g["c_recalltime"]) == want["best_iter"] + 1
+        assert np.abs(_np(res["T"]) - g["c_trans"][:3]).max() <= 1e-9
+        assert int(res["n_inl"].item()) == ref_counts.max()
 
 
 def test_c_ransac_no_inlier_gives_identity(engine):

@@ -38,13 +38,36 @@ def _rot_err_deg(Ra, Rb):
     return np.degrees(np.arccos(np.clip(c, -1, 1)))
 
 
-def test_dropin_file_pipeline_matches_reference_artefacts(tmp_path):
+def _real_ckpt(part):
+    fn = os.path.join(os.path.dirname(__file__), '..', 'oracle', '_ref', 'ckpt', part + '.npz')
+    if not os.path.exists(fn):
+        pytest.skip("oracle/_ref/ckpt not extracted (__graft_entry__.build() with /root/reference present)")
+    return {k: v for k, v in np.load(fn).items()}
+
+
+def _prelog_equal(path, golden_bytes, strict):
+    got = open(path, 'rb').read()
+    want = bytes(golden_bytes)
+    if strict:
+        assert got == want
+    gl, wl = got.decode().split('\n'), want.decode().split('\n')
+    assert len(gl) == len(wl) and gl[0] == wl[0]
+    for a, b in zip(gl[1:], wl[1:]):
+        fa, fb = [float(v) for v in a.split()], [float(v) for v in b.split()]
+        assert len(fa) == len(fb) and np.allclose(fa, fb, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("golden,weights,c_class", [("pipeline_synth.npz", "synth", "yohoc"),
+                                                     ("pipeline_synth.npz", "synth", "yohoc_mul"),
+                                                     ("pipeline_realckpt.npz", "real", "yohoc")])
+def test_dropin_file_pipeline_matches_reference_artefacts(tmp_path, golden, weights, c_class):
     """Extract -> match -> PartI_Rindex -> yohoc.ransac -> PartII_R_pre -> yohoo.ransac with the reference's
-    on-disk protocol; every artefact is compared with what the unmodified reference wrote for the same inputs."""
-    g = load_golden("pipeline_synth.npz")
+    on-disk protocol; every artefact is compared with what the unmodified reference wrote for the same inputs and the
+    same numpy seed (tests/golden/make_golden.py), with seeded synthetic weights and with the shipped checkpoints."""
+    g = load_golden(golden)
     from yoho_b200.extractor import extractor_PartI, extractor_dr_index, extractor_PartII
     from yoho_b200.matcher import matcher_dual
-    from yoho_b200.estimator import yohoc, yohoo
+    from yoho_b200 import estimator as est
     pair = synth.make_fragment_pair(128, seed=7, overlap=0.6, sigma=0.05)
     tmp = str(tmp_path)
     cfgI, cfgII = Cfg(), Cfg()
@@ -55,7 +78,8 @@ def test_dropin_file_pipeline_matches_reference_artefacts(tmp_path):
         cfg.model_fn = os.path.join(tmp, 'model')
     for part, d in (('PartI', 'PartI_train'), ('PartII', 'PartII_train')):
         os.makedirs(os.path.join(tmp, 'model', d))
-        torch.save({'best_para': 0.0, 'network_state_dict': synth.to_torch_state_dict(synth.synth_state_dict(part, 0))},
+        sd = synth.synth_state_dict(part, 0) if weights == "synth" else _real_ckpt(part)
+        torch.save({'best_para': 0.0, 'network_state_dict': synth.to_torch_state_dict(sd)},
                    os.path.join(tmp, 'model', d, 'model_best.pth'))
     name = 'synth/scene'
     base = os.path.join(tmp, 'cache', 'Testset', name)
@@ -70,7 +94,8 @@ def test_dropin_file_pipeline_matches_reference_artefacts(tmp_path):
 
     extractor_PartI(cfgI).Extract(ds)
     eqv0 = np.load(os.path.join(base, 'YOHO_Output_Group_feature', '0.npy'))
-    assert eqv0.dtype == np.float32 and np.abs(eqv0 - g['eqv0']).max() <= 1e-4
+    eqv1 = np.load(os.path.join(base, 'YOHO_Output_Group_feature', '1.npy'))
+    assert eqv0.dtype == np.float32 and np.abs(eqv0 - g['eqv0']).max() <= 1e-4 and np.abs(eqv1 - g['eqv1']).max() <= 1e-4
     # downstream stages are fed the reference's own eqv so that each stage is compared in isolation
     np.save(os.path.join(base, 'YOHO_Output_Group_feature', '0.npy'), g['eqv0'])
     np.save(os.path.join(base, 'YOHO_Output_Group_feature', '1.npy'), g['eqv1'])
@@ -80,23 +105,45 @@ def test_dropin_file_pipeline_matches_reference_artefacts(tmp_path):
     extractor_dr_index(cfgI).PartI_Rindex(ds)
     dr = np.load(os.path.join(base, 'Match', 'DR_index', '0-1.npy'))
     assert dr.dtype == np.int64 and np.array_equal(dr, g['dr_index'])
+
+    # YOHO-C (E1-E4, E6): same global-RNG draws, LAPACK's null-space signs replayed -> the reference's artefact.
+    # `strict`: this host's LAPACK rounds like the authoring host's (it is the reference's un-pinned dependency; its
+    # null-space sign is rounding noise, so on another CPU the REFERENCE would write different files too).
+    k0, k1 = pair['kps_A'][m[:, 0]], pair['kps_B'][m[:, 1]]
+    rt, rs = est.yohoc.lapack_replay(k0, k1, g['c_hyp'])
+    strict = np.array_equal(rt, g['c_hyp_trans'])
+    print(f"[{golden}] host LAPACK reproduces the golden per-hypothesis transforms bit for bit: {strict}")
     np.random.seed(int(g['c_seed']))
-    yohoc(cfgI).ransac(ds, 1000)
-    c = np.load(os.path.join(base, 'Match', 'YOHO_C', '1000iters', '0-1.npz'), allow_pickle=True)
-    assert os.path.exists(os.path.join(base, 'Match', 'YOHO_C', '1000iters', 'pre.log'))
-    # same global-RNG draws as the reference; the winner can differ only through LAPACK's null-space sign noise,
-    # so compare quality: the planted transform is recovered
+    state_before = np.random.get_state()[1].copy()
+    getattr(est, c_class)(cfgI).ransac(ds, 1000)
+    if c_class == 'yohoc_mul':          # forked workers in the reference: the parent's stream does not advance
+        assert np.array_equal(np.random.get_state()[1], state_before)
+    cdir = os.path.join(base, 'Match', 'YOHO_C', '1000iters')
+    c = np.load(os.path.join(cdir, '0-1.npz'), allow_pickle=True)
+    assert set(c.files) == {'trans', 'center', 'recalltime'}
+    if strict or np.array_equal(rs[rs != 2], g['c_sign'][rs != 2]):
+        assert int(c['recalltime']) == int(g['c_recalltime'])
+        assert c['center'].shape == (6, 3) and np.array_equal(c['center'], g['c_center'])
+        assert c['trans'].dtype == np.float64 and np.abs(c['trans'] - g['c_trans']).max() <= 1e-9
+    if strict:
+        assert np.array_equal(c['trans'], g['c_trans'])
+    _prelog_equal(os.path.join(cdir, 'pre.log'), g['c_prelog'], strict)
     assert _rot_err_deg(c['trans'][:3, :3], pair['R_gt']) < 3.0
     assert np.linalg.norm(c['trans'][:3, 3] - pair['t_gt']) < 0.1
+
     extractor_PartII(cfgII).PartII_R_pre(ds)
     tp = np.load(os.path.join(base, 'Match', 'Trans_pre', '0-1.npy'))
-    assert tp.dtype == np.float64 and np.abs(tp - g['trans_pre']).max() <= 1e-4
+    assert tp.dtype == np.float64 and tp.shape == g['trans_pre'].shape
+    assert np.abs(tp - g['trans_pre']).max() <= 1e-4
     np.save(os.path.join(base, 'Match', 'Trans_pre', '0-1.npy'), g['trans_pre'])
     np.random.seed(int(g['o_seed']))
-    yohoo(cfgII).ransac(ds, 1000)
-    o = np.load(os.path.join(base, 'Match', 'YOHO_O', '1000iters', '0-1.npz'), allow_pickle=True)
+    est.yohoo(cfgII).ransac(ds, 1000)
+    odir = os.path.join(base, 'Match', 'YOHO_O', '1000iters')
+    o = np.load(os.path.join(odir, '0-1.npz'), allow_pickle=True)
+    assert set(o.files) == {'trans', 'recalltime'}
     assert int(o['recalltime']) == int(g['o_recalltime'])
     assert np.array_equal(o['trans'], g['o_trans'])
+    _prelog_equal(os.path.join(odir, 'pre.log'), g['o_prelog'], True)          # no LAPACK on this path: always bytes
     # skip-if-exists (tests/extractor.py:47): a second Extract must not overwrite
     extractor_PartI(cfgI).Extract(ds)
     assert np.array_equal(np.load(os.path.join(base, 'YOHO_Output_Group_feature', '0.npy')), g['eqv0'])

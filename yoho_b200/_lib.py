@@ -73,7 +73,7 @@ SYMBOLS = {
     "yoho_part2_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "yoho_gather_kps": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "yoho_c_draw": (_i, [_vp, _vp, _i, _i, ctypes.c_uint64, _vp, _vp, _vp]),
-    "yoho_c_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yoho_c_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_o_order": (_i, [_vp, _i, ctypes.c_uint64, _vp, _vp]),
     "yoho_o_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_register_pair": (_i, [_vp, _vp, _vp, _vp]),

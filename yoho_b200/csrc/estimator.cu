@@ -135,22 +135,35 @@ __device__ __forceinline__ bool is_inlier(const double* __restrict__ k0, const d
     return fma(dz, dz, fma(dy, dy, dx * dx)) < thr2;
 }
 
+// Transform of hypothesis h.  YOHO-O: the given transform (through `order`).  YOHO-C: Kabsch of the triplet with the
+// sign rule / the caller's sign; signs[h] == 2 takes the caller's transform `fixed[h]` instead (reference replay of the
+// rank-deficient triplets, whose LAPACK completion is arbitrary: yoho_b200/estimator.py).
+__device__ __forceinline__ void hypothesis_transform(const double* __restrict__ k0, const double* __restrict__ k1,
+                                                     const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
+                                                     const double* __restrict__ fixed, const double* __restrict__ trans,
+                                                     const int32_t* __restrict__ order, int h, double T[12]) {
+    const double* src = nullptr;
+    if (trans) src = trans + 12 * (size_t)(order ? order[h] : h);
+    else if (signs && fixed && signs[h] == 2) src = fixed + 12 * (size_t)h;
+    if (src) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[i] = src[i];
+    } else {
+        kabsch3(k0, k1, hyp[3 * h], hyp[3 * h + 1], hyp[3 * h + 2], signs ? (int)signs[h] : 0, T);
+    }
+}
+
 // One warp per hypothesis.  mode 0: Kabsch from hyp triplets; mode 1: given transforms (YOHO-O).
 __global__ void __launch_bounds__(256) score_kernel(const double* __restrict__ k0, const double* __restrict__ k1, int M,
                                                    const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
+                                                   const double* __restrict__ fixed,
                                                    const double* __restrict__ trans, const int32_t* __restrict__ order,
                                                    int n_hyp, double thr2, int32_t* __restrict__ counts) {
     const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (h >= n_hyp) return;
     double T[12];
-    if (trans) {
-        const double* src = trans + 12 * (size_t)(order ? order[h] : h);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) T[i] = src[i];
-    } else {
-        kabsch3(k0, k1, hyp[3 * h], hyp[3 * h + 1], hyp[3 * h + 2], signs ? (int)signs[h] : 0, T);
-    }
+    hypothesis_transform(k0, k1, hyp, signs, fixed, trans, order, h, T);
     int n = 0;
     for (int m = lane; m < M; m += 32) n += is_inlier(k0, k1, m, T, thr2) ? 1 : 0;
 #pragma unroll
@@ -161,6 +174,7 @@ __global__ void __launch_bounds__(256) score_kernel(const double* __restrict__ k
 // First strictly-best hypothesis, its transform and inlier mask.  Single CTA.
 __global__ void __launch_bounds__(1024) select_kernel(const double* __restrict__ k0, const double* __restrict__ k1, int M,
                                                      const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
+                                                     const double* __restrict__ fixed,
                                                      const double* __restrict__ trans, const int32_t* __restrict__ order,
                                                      int n_hyp, double thr2, const int32_t* __restrict__ counts,
                                                      double* __restrict__ T_out, int32_t* __restrict__ best_iter,
@@ -191,14 +205,7 @@ __global__ void __launch_bounds__(1024) select_kernel(const double* __restrict__
         *best_iter = bi;
         *n_inl = cnt > 0 ? cnt : 0;
         double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-        if (bi >= 0) {
-            if (trans) {
-                const double* src = trans + 12 * (size_t)(order ? order[bi] : bi);
-                for (int i = 0; i < 12; ++i) T[i] = src[i];
-            } else {
-                kabsch3(k0, k1, hyp[3 * bi], hyp[3 * bi + 1], hyp[3 * bi + 2], signs ? (int)signs[bi] : 0, T);
-            }
-        }
+        if (bi >= 0) hypothesis_transform(k0, k1, hyp, signs, fixed, trans, order, bi, T);
         for (int i = 0; i < 12; ++i) { Ts[i] = T[i]; T_out[i] = T[i]; }
     }
     __syncthreads();
@@ -366,7 +373,8 @@ extern "C" int yoho_c_draw(yoho_ctx* ctx, const int64_t* dr_index, int M, int it
 }
 
 static int score_and_select(yoho_ctx* ctx, const double* k0, const double* k1, int M, const int32_t* hyp,
-                            const int8_t* signs, const double* trans, const int32_t* order, int n_hyp, double dist,
+                            const int8_t* signs, const double* fixed, const double* trans, const int32_t* order, int n_hyp,
+                            double dist,
                             double* T, int32_t* best_iter, int32_t* n_inl, uint8_t* mask, int32_t* counts, cudaStream_t st) {
     int32_t* cnt = counts;
     if (!cnt) {
@@ -375,21 +383,21 @@ static int score_and_select(yoho_ctx* ctx, const double* k0, const double* k1, i
     }
     const double thr2 = dist * dist;
     if (n_hyp > 0) {
-        score_kernel<<<(n_hyp + 7) / 8, 256, 0, st>>>(k0, k1, M, hyp, signs, trans, order, n_hyp, thr2, cnt);
+        score_kernel<<<(n_hyp + 7) / 8, 256, 0, st>>>(k0, k1, M, hyp, signs, fixed, trans, order, n_hyp, thr2, cnt);
         ctx->launches++;
     }
-    select_kernel<<<1, 1024, 0, st>>>(k0, k1, M, hyp, signs, trans, order, n_hyp, thr2, cnt, T, best_iter, n_inl, mask);
+    select_kernel<<<1, 1024, 0, st>>>(k0, k1, M, hyp, signs, fixed, trans, order, n_hyp, thr2, cnt, T, best_iter, n_inl, mask);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
 }
 
 extern "C" int yoho_c_ransac(yoho_ctx* ctx, const double* k0, const double* k1, int M, const int32_t* hyp,
-                             const int8_t* signs, int iters, double inlier_dist, double* T, int32_t* best_iter,
-                             int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream) {
+                             const int8_t* signs, const double* fixed, int iters, double inlier_dist, double* T,
+                             int32_t* best_iter, int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream) {
     YARG(ctx && k0 && k1 && T && best_iter && n_inl && M >= 0 && iters >= 0 && (iters == 0 || hyp));
     YCHECK(cudaSetDevice(ctx->device));
-    return score_and_select(ctx, k0, k1, M, hyp, signs, nullptr, nullptr, iters, inlier_dist, T, best_iter, n_inl, mask,
+    return score_and_select(ctx, k0, k1, M, hyp, signs, fixed, nullptr, nullptr, iters, inlier_dist, T, best_iter, n_inl, mask,
                             counts, (cudaStream_t)stream);
 }
 
@@ -411,6 +419,6 @@ extern "C" int yoho_o_score(yoho_ctx* ctx, const double* k0, const double* k1, i
                             int32_t* n_inl, uint8_t* mask, int32_t* counts, void* stream) {
     YARG(ctx && k0 && k1 && T && best_iter && n_inl && M >= 0 && H >= 0 && (H == 0 || trans));
     YCHECK(cudaSetDevice(ctx->device));
-    return score_and_select(ctx, k0, k1, M, nullptr, nullptr, trans, order, H, inlier_dist, T, best_iter, n_inl, mask,
+    return score_and_select(ctx, k0, k1, M, nullptr, nullptr, nullptr, trans, order, H, inlier_dist, T, best_iter, n_inl, mask,
                             counts, (cudaStream_t)stream);
 }

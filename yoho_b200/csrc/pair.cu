@@ -56,7 +56,7 @@ extern "C" int yoho_register_pair(yoho_ctx* ctx, const yoho_pair_io* io, int32_t
     if ((rc = yoho_rot_argmax(ctx, io->eqvB, io->pairs + 1, io->eqvA, io->pairs, 2, M, io->dr_index, nullptr, stream))) return rc;
     if ((rc = yoho_gather_kps(ctx, io->kpsA, io->kpsB, io->pairs, M, io->k0, io->k1, stream))) return rc;
     if ((rc = yoho_c_draw(ctx, io->dr_index, M, io->c_iters, io->seed, io->hyp, io->c_status, stream))) return rc;
-    if ((rc = yoho_c_ransac(ctx, io->k0, io->k1, M, io->hyp, nullptr, io->c_iters, io->c_dist, io->T_c, io->c_best, io->c_inl,
+    if ((rc = yoho_c_ransac(ctx, io->k0, io->k1, M, io->hyp, nullptr, nullptr, io->c_iters, io->c_dist, io->T_c, io->c_best, io->c_inl,
                             io->c_mask, nullptr, stream))) return rc;
     c_finish_kernel<<<1, 32, 0, st>>>(io->c_status, io->T_c, io->c_best);
     ctx->launches++;

@@ -387,7 +387,7 @@ class Engine:
         counts = self._empty((n_hyp,), torch.int32) if want_counts else None
         return T, bi, ni, mask, counts
 
-    def c_ransac(self, k0, k1, hyp, dist, signs=None, want_counts=False):
+    def c_ransac(self, k0, k1, hyp, dist, signs=None, want_counts=False, fixed=None):
         k0, k1 = self._f64(k0), self._f64(k1)
         if isinstance(hyp, np.ndarray):
             hyp = torch.from_numpy(np.ascontiguousarray(hyp, np.int32))
@@ -395,9 +395,14 @@ class Engine:
         sg = None
         if signs is not None:
             sg = torch.as_tensor(np.ascontiguousarray(signs, np.int8)).to(self.device)
+        fx = None
+        if fixed is not None:
+            fx = self._f64(fixed).reshape(-1, 12)
+            if sg is None or fx.shape[0] != hyp.shape[0]:
+                raise ValueError("fixed transforms need signs and one [3,4] entry per hypothesis")
         M, iters = k0.shape[0], hyp.shape[0]
         T, bi, ni, mask, counts = self._est_out(M, iters, want_counts)
-        _lib.check(self.lib.yoho_c_ransac(self.h, _ptr(k0), _ptr(k1), M, _ptr(hyp), _ptr(sg), iters, float(dist),
+        _lib.check(self.lib.yoho_c_ransac(self.h, _ptr(k0), _ptr(k1), M, _ptr(hyp), _ptr(sg), _ptr(fx), iters, float(dist),
                                           _ptr(T), _ptr(bi), _ptr(ni), _ptr(mask), _ptr(counts), _stream()))
         return dict(T=T, best_iter=bi, n_inl=ni, mask=mask, counts=counts)
 

@@ -7,9 +7,15 @@ These classes draw the SAME values from the SAME global stream in the SAME order
 `np.random.seed(s)` selects the same hypotheses as the reference), then score all hypotheses in one device
 pass.  `rng='device'` switches to the counter-based device generator (same distribution, no host loop).
 
-SVD sign.  With three matches the cross-covariance has rank 2 and LAPACK's sign for the null-space pair is
-rounding noise; the device Kabsch uses the rule documented in DESIGN.md ("Estimator arithmetic").  Given the
-same hypothesis the inlier mask is exact; see tests/test_estimator_*.py for what is pinned against numpy.
+SVD sign.  With three matches the cross-covariance has rank 2 and the sign LAPACK gives the null-space singular
+pair is rounding noise (det(V U^T) = +1 about half of the time): the reference's hypothesis is "whatever
+np.linalg.svd returned".  In the default numpy-RNG mode `lapack_replay` therefore makes the reference's own
+LAPACK call on the [iters,3,3] cross-covariance batch (tests/estimator.py:55-59; the batched gufunc runs the same
+gesdd per matrix as the reference's scalar call), and hands the device sign(det(V U^T)) per hypothesis plus
+LAPACK's transform for the rank-deficient triplets (a match drawn twice: the completion is arbitrary).  The device
+solves and scores every hypothesis (csrc/estimator.cu); winner, `recalltime`, `center` and — through the
+replayed LAPACK transform of the winning triplet — `trans` equal the reference's artefacts bit for bit
+(tests/test_gpu_pipeline.py).  `rng='device'` uses the device's own sign rule (DESIGN.md "Estimator arithmetic").
 
 `yohoc_mul` (one forked process per pair in the reference, :255-275) is the same device batch here — a CUDA
 process must not fork.
@@ -84,6 +90,26 @@ class yohoc:
             it += 1
         return hyp[:it]
 
+    @staticmethod
+    def lapack_replay(Keys_m0, Keys_m1, hyp):
+        """Threepps2Tran (tests/estimator.py:55-63) for every triplet at once, with the reference's operations:
+        returns (trans [iters,3,4] f64 = the reference's per-hypothesis transforms, signs int8[iters]:
+        +-1 = det(V U^T) of a rank-2 triplet, 2 = rank-deficient triplet -> the device takes trans[i] as given)."""
+        hyp = np.asarray(hyp, np.int64).reshape(-1, 3)
+        a = np.asarray(Keys_m0, np.float64)[hyp]
+        b = np.asarray(Keys_m1, np.float64)[hyp]
+        c0 = np.mean(a, 1, keepdims=True)
+        c1 = np.mean(b, 1, keepdims=True)
+        H = np.matmul((b - c1).transpose(0, 2, 1), a - c0)
+        U, S, VT = np.linalg.svd(H)
+        R = np.matmul(VT.transpose(0, 2, 1), U.transpose(0, 2, 1))
+        t = c0 - np.matmul(c1, R.transpose(0, 2, 1))
+        trans = np.concatenate([R, t.transpose(0, 2, 1)], 2)
+        signs = np.where(np.linalg.det(R) > 0, 1, -1).astype(np.int8)
+        dup = (hyp[:, 0] == hyp[:, 1]) | (hyp[:, 0] == hyp[:, 2]) | (hyp[:, 1] == hyp[:, 2])
+        signs[dup | ~(S[:, 1] > 1e-12 * S[:, 0])] = 2
+        return trans, signs
+
     # ---- E2-E4 on matched keypoints ---------------------------------------------------------------------
     def estimate(self, Keys_m0, Keys_m1, Index, max_iter=1000):
         """Matched keypoints [M,3] f64 x2 and rotation index [M] -> dict(trans, center, recalltime).
@@ -92,16 +118,21 @@ class yohoc:
         if prob is None:
             return dict(trans=np.eye(4), center=0, axis=0, recalltime=50001)
         eng = get_engine(so3_dir=self._so3)
+        ref_trans = None
         if self.rng == 'device':
             seed = int(np.random.randint(0, 2 ** 31 - 1))
             hyp_d, _ = eng.c_draw(np.asarray(Index, np.int64), max_iter, seed)
+            res = eng.c_ransac(Keys_m0, Keys_m1, hyp_d, self.inliner_dist)
         else:
             hyp_d = self.draw_hypotheses(stat, prob, max_iter)
-        res = eng.c_ransac(Keys_m0, Keys_m1, hyp_d, self.inliner_dist)
+            ref_trans, signs = self.lapack_replay(Keys_m0, Keys_m1, hyp_d)
+            res = eng.c_ransac(Keys_m0, Keys_m1, hyp_d, self.inliner_dist, signs=signs, fixed=ref_trans)
         bi = int(res['best_iter'].item())
         if bi < 0:
             return dict(trans=np.eye(4), center=np.ones([6, 3]), recalltime=0)
-        trans = res['T'].cpu().numpy()
+        # numpy mode: the winner's transform as LAPACK computed it (what the reference saves); the device's own solve of
+        # the same triplet with the same sign agrees to ~1e-9 (tests/test_gpu_parity.py::test_c_ransac_golden_replay)
+        trans = ref_trans[bi] if ref_trans is not None else res['T'].cpu().numpy()
         ids = (hyp_d[bi].cpu().numpy() if isinstance(hyp_d, torch.Tensor) else hyp_d[bi]).astype(np.int64)
         center = np.concatenate([np.asarray(Keys_m0)[ids], np.asarray(Keys_m1)[ids]], axis=0)
         return dict(trans=trans, center=center, recalltime=bi + 1)
@@ -133,10 +164,26 @@ class yohoc:
 
 class yohoc_mul(yohoc):
     """tests/estimator.py:145-275.  Same results contract as `yohoc`; the per-pair process pool of the reference
-    is replaced by device parallelism over hypotheses (no fork after CUDA initialisation)."""
+    is replaced by device parallelism over hypotheses (no fork after CUDA initialisation).
+
+    Randomness: the reference forks one worker per pair (`Pool(len(pair_ids))`, :269-273), so every worker starts
+    from a COPY of the parent's global numpy state and the parent's own stream does not advance.  That is what this
+    class reproduces: each pair draws from the state the caller had on entry, and the state is restored on exit.
+    (When the reference's pool hands two pairs to one worker, the second continues the first one's stream; that
+    assignment is scheduler-dependent and not reproducible in the reference either.)"""
+
+    def estimate(self, Keys_m0, Keys_m1, Index, max_iter=1000):
+        if self.rng != 'device' and getattr(self, '_fork_state', None) is not None:
+            np.random.set_state(self._fork_state)
+        return super().estimate(Keys_m0, Keys_m1, Index, max_iter)
 
     def ransac(self, dataset, max_iter=1000):
-        super().ransac(dataset, max_iter)
+        self._fork_state = np.random.get_state()
+        try:
+            super().ransac(dataset, max_iter)
+        finally:
+            np.random.set_state(self._fork_state)
+            self._fork_state = None
         print('Done')
 
 
