@@ -16,7 +16,36 @@ import sys
 import types
 import contextlib
 
-REF_ROOT = os.environ.get("YOHO_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the authoring container; on the GPU box the git-ignored copy of the hot-path .py files that
+# `__graft_entry__.build()` makes under oracle/_ref/src (never committed; travels with the gpurun snapshot like the checkpoints)
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")
+REF_ROOT = os.environ.get("YOHO_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/utils/network.py") else _LOCAL_COPY)
+
+# what build() copies: the path's own modules + what they import at module level (none of it is product source)
+HOT_PATH_FILES = [
+    "utils/__init__.py", "utils/network.py", "utils/knn_search.py", "utils/r_eval.py", "utils/utils.py", "utils/dataset.py",
+    "utils/RR_cal.py", "utils/misc.py", "utils/utils_o3d.py",
+    "tests/__init__.py", "tests/extractor.py", "tests/matcher.py", "tests/estimator.py", "tests/evaluator.py",
+    "parses/parses_partI.py", "parses/parses_partII.py", "train/loss_val.py",
+    "group_related/Rotation.npy", "group_related/60_60.npy", "group_related/Nei_Index_in_SO3_ordered_13.npy",
+]
+
+
+def export_hot_path(src_root="/root/reference", dst_root=_LOCAL_COPY):
+    """Copy the reference's hot-path files verbatim into oracle/_ref/src (git-ignored).  Called by build() only."""
+    import shutil
+    n = 0
+    for rel in HOT_PATH_FILES:
+        s = os.path.join(src_root, rel)
+        if not os.path.isfile(s):
+            continue
+        d = os.path.join(dst_root, rel)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        if not os.path.exists(d) or os.path.getmtime(d) < os.path.getmtime(s):
+            shutil.copyfile(s, d)
+        n += 1
+    return n
 
 
 def available() -> bool:

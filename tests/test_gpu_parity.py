@@ -309,14 +309,18 @@ def test_c_ransac_golden_replay(engine):
 
 
 def test_c_ransac_no_inlier_gives_identity(engine):
-    k0 = np.zeros((5, 3)); k1 = np.arange(15.0).reshape(5, 3) * 100 + 50
-    k0[:, 0] = [1e3, -1e3, 5e3, 7e3, -9e3]
-    hyp = np.array([[0, 0, 0]], np.int32)
-    res = engine.c_ransac(k0, k1, hyp, 1e-6)
-    if int(res["n_inl"].item()) == 0:
-        assert int(res["best_iter"].item()) == -1
-        assert np.array_equal(_np(res["T"]), np.eye(4)[:3])
-        assert not _np(res["mask"]).any()
+    """No hypothesis has an inlier -> eye(4), recalltime 0 (tests/estimator.py:111-117: best_overlap stays 0).  The triplet's
+    two triangles differ in scale by 1000, so even its own three points miss by hundreds of metres; the other matches are far."""
+    k1 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [50, 50, 50], [60, 60, 60]], np.float64)
+    k0 = np.array([[0, 0, 0], [1000, 0, 0], [0, 1000, 0], [1e5, -1e5, 3e5], [-2e5, 7e5, 1e5]], np.float64)
+    hyp = np.array([[0, 1, 2], [2, 1, 0], [0, 2, 1]], np.int32)
+    res = engine.c_ransac(k0, k1, hyp, 0.07, want_counts=True)
+    assert np.array_equal(_np(res["counts"]), [0, 0, 0]) and int(res["n_inl"].item()) == 0
+    assert int(res["best_iter"].item()) == -1
+    assert np.array_equal(_np(res["T"]), np.eye(4)[:3])
+    assert not _np(res["mask"]).any()
+    want = E.yohoc(k0, k1, hyp, 0.07)
+    assert want["best_iter"] == -1 and np.array_equal(want["T"], np.eye(4)[:3])
 
 
 @pytest.mark.parametrize("M,H", [(1, 1), (87, 87), (1000, 1000), (2000, 500)])
