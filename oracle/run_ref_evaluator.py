@@ -41,63 +41,65 @@ class StubDataset:
         return self._kps[int(i)]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--backend", choices=["yoho_b200", "reference"], required=True)
-    ap.add_argument("--device", choices=["cpu", "cuda"], default="cuda")
-    ap.add_argument("--work", required=True)
-    ap.add_argument("--weights", choices=["synth", "real"], default="synth")
-    ap.add_argument("--K", type=int, default=128)
-    ap.add_argument("--pair-seed", type=int, default=7)
-    ap.add_argument("--overlap", type=float, default=0.6)
-    ap.add_argument("--c-seed", type=int, default=123)
-    ap.add_argument("--o-seed", type=int, default=124)
-    ap.add_argument("--max-iter", type=int, default=1000)
-    ap.add_argument("--tf32", type=int, default=-1, help="reference on cuda: 0/1 force torch's TF32 switches, -1 = torch defaults")
-    a = ap.parse_args()
-    sys.argv = [sys.argv[0]]                      # parses/*.py parse sys.argv at import time
-
-    import numpy as np
+def setup(backend, device="cuda", tf32=-1):
+    """Import the reference's evaluator stack (unmodified) with the chosen backend underneath.  Returns a namespace
+    (ev = the reference's tests.evaluator module, cfgI, cfgII, ref_root, extractor_file)."""
+    import types
+    import importlib
     import torch
     import ref_shim
-    if a.backend == "reference" and a.device == "cpu":
-        os.environ["CUDA_VISIBLE_DEVICES"] = ""
-    if a.backend == "reference" and a.device == "cuda" and a.tf32 >= 0:
-        torch.backends.cudnn.allow_tf32 = bool(a.tf32)
-        torch.backends.cuda.matmul.allow_tf32 = bool(a.tf32)
+    if backend == "reference" and device == "cpu":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""           # before CUDA is initialised: the reference's .cuda() calls become no-ops
+    if backend == "reference" and device == "cuda" and tf32 >= 0:
+        torch.backends.cudnn.allow_tf32 = bool(tf32)
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     ref_shim.install()
-    if a.backend == "yoho_b200":
+    if backend == "yoho_b200":
         import yoho_b200.dropin as dropin
         dropin.install()
-    import importlib
-    pI = importlib.import_module("parses.parses_partI")
-    pII = importlib.import_module("parses.parses_partII")
-    cfgI, _ = pI.get_config()
-    cfgII, _ = pII.get_config()
-    ev = importlib.import_module("tests.evaluator")           # the reference's module, whatever the backend
+    argv, sys.argv = sys.argv, [sys.argv[0]]              # parses/*.py parse sys.argv at import time
+    try:
+        pI = importlib.import_module("parses.parses_partI")
+        pII = importlib.import_module("parses.parses_partII")
+        cfgI, _ = pI.get_config()
+        cfgII, _ = pII.get_config()
+    finally:
+        sys.argv = argv
+    ev = importlib.import_module("tests.evaluator")       # the reference's module, whatever the backend
     assert os.path.abspath(ev.__file__).startswith(os.path.abspath(ref_shim.REF_ROOT)), ev.__file__
     ext = sys.modules["tests.extractor"]
     backend_file = getattr(ext, "__file__", "")
-    if a.backend == "yoho_b200":
+    if backend == "yoho_b200":
         assert "yoho_b200" in backend_file, backend_file
         assert ev.name2extractor is ext.name2extractor
+    else:
+        assert os.path.abspath(backend_file).startswith(os.path.abspath(ref_shim.REF_ROOT)), backend_file
+    return types.SimpleNamespace(ev=ev, cfgI=cfgI, cfgII=cfgII, ref_root=ref_shim.REF_ROOT, extractor_file=backend_file,
+                                 backend=backend, device=device if backend == "reference" else "cuda")
 
+
+def run_pair(ns, work, K=128, pair_seed=7, overlap=0.6, c_seed=123, o_seed=124, max_iter=1000, weights="synth", fmr=True):
+    """One synthetic K-keypoint pair through Evaluator_PartI.run_onescene + Evaluator_PartII.run_onescene in directory `work`
+    (the reference's on-disk protocol).  Returns wall-clock seconds per evaluator and bookkeeping."""
+    import numpy as np
+    import torch
     from yoho_b200 import synth
-    tmp = a.work
+    ev, cfgI, cfgII = ns.ev, ns.cfgI, ns.cfgII
+    tmp = work
     for cfg in (cfgI, cfgII):
         cfg.output_cache_fn = os.path.join(tmp, 'cache')
         cfg.origin_data_dir = os.path.join(tmp, 'origin')
         cfg.model_fn = os.path.join(tmp, 'model')
-        cfg.SO3_related_files = os.path.join(ref_shim.REF_ROOT, 'group_related')
+        cfg.SO3_related_files = os.path.join(ns.ref_root, 'group_related')
     for part, d in (('PartI', 'PartI_train'), ('PartII', 'PartII_train')):
         os.makedirs(os.path.join(tmp, 'model', d), exist_ok=True)
-        if a.weights == "synth":
+        if weights == "synth":
             sd = synth.synth_state_dict(part, 0)
         else:
             sd = dict(np.load(os.path.join(HERE, '_ref', 'ckpt', part + '.npz')))
         torch.save({'best_para': 0.0, 'step': 0, 'network_state_dict': synth.to_torch_state_dict(sd)},
                    os.path.join(tmp, 'model', d, 'model_best.pth'))
-    pair = synth.make_fragment_pair(a.K, seed=a.pair_seed, overlap=a.overlap, sigma=0.05)
+    pair = synth.make_fragment_pair(K, seed=pair_seed, overlap=overlap, sigma=0.05)
     name = 'synth/scene'
     base = os.path.join(tmp, 'cache', 'Testset', name)
     os.makedirs(os.path.join(base, 'FCGF_Input_Group_feature'), exist_ok=True)
@@ -111,26 +113,64 @@ def main():
     ds = StubDataset(name, [pair['kps_A'], pair['kps_B']], gt)
     cfgI.ok_match_dist_threshold = cfgII.ok_match_dist_threshold = 0.1
 
+    def sync():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     times = {}
+    sync()
     t0 = time.perf_counter()
-    e1 = ev.Evaluator_PartI(cfgI, max_iter=a.max_iter)        # Test.py:54 -> name2evaluator['PartI']
-    np.random.seed(a.c_seed)
+    e1 = ev.Evaluator_PartI(cfgI, max_iter=max_iter)          # Test.py:54 -> name2evaluator['PartI']
+    np.random.seed(c_seed)
     e1.run_onescene(ds)
-    if torch.cuda.is_available():
-        torch.cuda.synchronize()
+    sync()
     times['partI_s'] = time.perf_counter() - t0
-    fmr, pair_fmrs = e1.Feature_match_Recall(ds, ratio=0.05)
+    out = dict(K=K, weights=weights)
+    if fmr:
+        f, pair_fmrs = e1.Feature_match_Recall(ds, ratio=0.05)
+        out.update(fmr=float(f), pair_fmr=[float(v) for v in pair_fmrs])
+    sync()
     t0 = time.perf_counter()
-    e2 = ev.Evaluator_PartII(cfgII, max_iter=a.max_iter)      # Test.py:64
-    np.random.seed(a.o_seed)
+    e2 = ev.Evaluator_PartII(cfgII, max_iter=max_iter)        # Test.py:64
+    np.random.seed(o_seed)
     e2.run_onescene(ds)
-    if torch.cuda.is_available():
-        torch.cuda.synchronize()
+    sync()
     times['partII_s'] = time.perf_counter() - t0
-    info = dict(backend=a.backend, device=a.device if a.backend == "reference" else "cuda", evaluator_file=ev.__file__,
-                extractor_file=backend_file, estimator_class=type(e1.estimator).__module__ + "." + type(e1.estimator).__name__,
-                fmr=float(fmr), pair_fmr=[float(v) for v in pair_fmrs], K=a.K, weights=a.weights, **times)
-    with open(os.path.join(tmp, 'run_info.json'), 'w') as f:
+    m = np.load(os.path.join(base, 'Match', '0-1.npy'))
+    c = np.load(os.path.join(base, 'Match', 'YOHO_C', f'{max_iter}iters', '0-1.npz'), allow_pickle=True)
+    R = c['trans'][:3, :3]
+    rot_err = float(np.degrees(np.arccos(np.clip((np.trace(R.T @ pair['R_gt']) - 1) / 2, -1, 1))))
+    out.update(times, seconds=times['partI_s'] + times['partII_s'], M=int(m.shape[0]), c_rot_err_deg=rot_err,
+               estimator_class=type(e1.estimator).__module__ + "." + type(e1.estimator).__name__)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", choices=["yoho_b200", "reference"], required=True)
+    ap.add_argument("--device", choices=["cpu", "cuda"], default="cuda")
+    ap.add_argument("--work", required=True)
+    ap.add_argument("--weights", choices=["synth", "real"], default="synth")
+    ap.add_argument("--K", type=int, default=128)
+    ap.add_argument("--pair-seed", type=int, default=7)
+    ap.add_argument("--overlap", type=float, default=0.6)
+    ap.add_argument("--c-seed", type=int, default=123)
+    ap.add_argument("--o-seed", type=int, default=124)
+    ap.add_argument("--max-iter", type=int, default=1000)
+    ap.add_argument("--tf32", type=int, default=-1, help="reference on cuda: 0/1 force torch's TF32 switches, -1 = torch defaults")
+    ap.add_argument("--warmup-K", type=int, default=0, help="run a pair of this size first (untimed; model load, cuDNN selection)")
+    ap.add_argument("--threads", type=int, default=0)
+    a = ap.parse_args()
+    import torch
+    if a.threads > 0:
+        torch.set_num_threads(a.threads)
+    ns = setup(a.backend, a.device, a.tf32)
+    if a.warmup_K > 0:
+        run_pair(ns, os.path.join(a.work, 'warmup'), K=a.warmup_K, weights=a.weights, fmr=False)
+    r = run_pair(ns, a.work, a.K, a.pair_seed, a.overlap, a.c_seed, a.o_seed, a.max_iter, a.weights)
+    info = dict(backend=ns.backend, device=ns.device, evaluator_file=ns.ev.__file__, extractor_file=ns.extractor_file,
+                threads=torch.get_num_threads(), tf32=a.tf32, **r)
+    with open(os.path.join(a.work, 'run_info.json'), 'w') as f:
         json.dump(info, f)
     print(json.dumps(info))
 

@@ -125,12 +125,17 @@ class PairPipeline:
         res = torch.stack([r["T_c"], r["T_o"]]).cpu().numpy()          # D2H of the result (synchronises)
         return dict(T_c=res[0], T_o=res[1], M=r["M"])
 
-    def register_stream(self, pinned_pairs):
+    def register_stream(self, pinned_pairs, stats=None):
         """Throughput form of `register_pinned` for a sequence of pairs (the way a dataset is processed, tests/evaluator.py:41-47):
         generator over `(fa_pin, fb_pin, ka_pin, kb_pin)` tuples yielding one `dict(T_c, T_o, M)` per pair, in order.  The H2D
         copies of pair i+1 run on the side stream while pair i computes, and the D2H of pair i's transforms (into a pinned
         buffer) is awaited only when pair i+1 has been queued, so neither copy sits on the critical path.  Every pair's inputs
-        still cross PCIe from host memory and every result is read back to the host."""
+        still cross PCIe from host memory and every result is read back to the host.
+        `stats` (a dict) switches on per-pair accounting with CUDA events on the main stream and host clocks; on return it holds
+        lists (ms per pair): copy_wait = main stream stalled on the upload of ITS pair, compute = first to last kernel of the pair,
+        gap = device idle between the end of the previous pair and this pair's wait (the host was late queueing), and the host
+        times upload_host / call_host / d2h_wait_host spent in the three host-side steps."""
+        import time as _time
         dev = self.eng.device
         main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
@@ -160,9 +165,14 @@ class PairPipeline:
 
         def finish(pend):
             host, ev, M = pend
+            t0 = _time.perf_counter()
             ev.synchronize()
+            if stats is not None:
+                stats.setdefault("d2h_wait_host", []).append(1e3 * (_time.perf_counter() - t0))
             res = host.numpy().copy()
             return dict(T_c=res[0], T_o=res[1], M=M)
+
+        marks = []          # per pair: (before wait, after wait, end) events on the main stream
 
         it = iter(pinned_pairs)
         try:
@@ -173,14 +183,25 @@ class PairPipeline:
         n = 0
         while nxt is not None:
             (fa, fb, ka, kb), ev = nxt
+            t0 = _time.perf_counter()
             try:
                 nxt = upload(next(it), (n + 1) & 1)     # prefetch: overlaps this pair's PartI
             except StopIteration:
                 nxt = None
+            t1 = _time.perf_counter()
+            if stats is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(main)
             main.wait_event(ev)
+            if stats is not None:
+                e1.record(main)
             r = self.register(fa, fb, ka, kb, lean=self.fused)
-            free = torch.cuda.Event()
+            free = torch.cuda.Event(enable_timing=stats is not None)
             free.record(main)                           # every kernel reading this input set has been queued
+            if stats is not None:
+                marks.append((e0, e1, free))
+                stats.setdefault("upload_host", []).append(1e3 * (t1 - t0))
+                stats.setdefault("call_host", []).append(1e3 * (_time.perf_counter() - t1))
             self._in_free[n & 1] = free
             if not hasattr(self, "_res_pin"):
                 self._res_pin = [torch.empty((2, 3, 4), dtype=torch.float64, pin_memory=True) for _ in range(2)]
@@ -194,6 +215,11 @@ class PairPipeline:
             n += 1
         if pending is not None:
             yield finish(pending)
+        if stats is not None and marks:
+            torch.cuda.synchronize()
+            stats["copy_wait"] = [a.elapsed_time(b) for a, b, _ in marks]
+            stats["compute"] = [b.elapsed_time(c) for _, b, c in marks]
+            stats["gap"] = [0.0] + [marks[i - 1][2].elapsed_time(marks[i][0]) for i in range(1, len(marks))]
 
     def register_host(self, featA, featB, kpsA, kpsB):
         """numpy in (feat [K,32,60] f32, kps [K,3] f64) -> numpy transforms out; staging + H2D + D2H inside."""
