@@ -10,9 +10,11 @@ value = n_gpus * steps * kpts / seconds, inputs resident in HBM, timed with CUDA
 e2e   = the same through the host-facing call (pinned host buffers -> H2D -> pipeline -> D2H of the transforms).
 Ranks are independent (pairs shard with no data-path collective): scaling is weak, one pair per rank per step.
 
---impl reference times the reference's CPU implementation of the same path (the oracle port: the same torch CPU
-operators in the reference's order, BN/ReLU on the 13x-inflated tensor like utils/network.py:15-19) on this box's
-host cores, on a bounded sample per step, rank 0 only.
+--impl reference times the reference's CPU implementation of the same path on this box's host cores, rank 0 only: the
+UNMODIFIED reference (its own evaluator, tests/evaluator.py:41-47,112-117, from /root/reference or the git-ignored copy
+oracle/_ref/src that build() exports) — the first timed step is one full, un-extrapolated cold pair, the other steps are
+bounded samples (a smaller pair through the same code, scaled by the keypoint ratio).  Without the reference sources it
+falls back to the oracle port (kind "port").
 """
 import argparse
 import json
@@ -108,18 +110,7 @@ def cpu_pair_seconds(kpts, sample_kp=900, sample_matches=256, threads=None):
     import yoho_oracle as O
     import estimator_oracle as E
     from yoho_b200 import synth
-    # one thread per PHYSICAL core this process may use: torch's own default and its fastest setting (measured on the
-    # box: 64 threads 89 keypoint-pairs/s, 128 hyper-threads 41).  torchrun exports OMP_NUM_THREADS=1, so set it explicitly.
-    try:
-        import psutil
-        phys = psutil.cpu_count(logical=False) or 1
-    except Exception:
-        phys = max(1, (os.cpu_count() or 2) // 2)
-    try:
-        phys = min(phys, len(os.sched_getaffinity(0)))
-    except Exception:
-        pass
-    torch.set_num_threads(threads or phys)
+    torch.set_num_threads(threads or host_threads())
     cores = torch.get_num_threads()
     R, P, N = O.load_tables()
     sdI, sdII = synth.synth_state_dict("PartI", 0), synth.synth_state_dict("PartII", 0)
@@ -160,14 +151,85 @@ def cpu_pair_seconds(kpts, sample_kp=900, sample_matches=256, threads=None):
     return total, cores, sample, t
 
 
+def host_threads():
+    """One thread per PHYSICAL core this process may use (torch's fastest setting on the box: 64 threads 89 keypoint-pairs/s,
+    128 hyper-threads 41).  torchrun exports OMP_NUM_THREADS=1, so it is set explicitly."""
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or 1
+    except Exception:
+        phys = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        phys = min(phys, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, phys)
+
+
+def reference_sources_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    return ref_shim.available()
+
+
+def shm_dir():
+    import tempfile
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    return tempfile.mkdtemp(prefix="yoho_ref_", dir=base)          # RAM-backed: the reference's .npy round trips are memory copies
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    import shutil
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    K = args.kpts
+    weights = pick_weights(args)
+    cfg = {"workload": f"configs[1]: one cold {K}-keypoint 3DMatch-shaped pair, PartI+PartII + matching + YOHO-C/O", "kpts": K,
+           "weights": weights_note(weights)}
+    if reference_sources_available():
+        import run_ref_evaluator as RE
+        ns = RE.setup("reference", "cpu")
+        work = shm_dir()
+        try:
+            sk = 500 if args.steps <= 25 else 300
+            for i in range(args.warmup):                            # untimed: imports, checkpoint parsing, thread pools
+                RE.run_pair(ns, os.path.join(work, f"w{i}"), K=200, pair_seed=i, overlap=0.5, weights=weights, fmr=False)
+                shutil.rmtree(os.path.join(work, f"w{i}"), ignore_errors=True)
+            steps, walls = [], []
+            for i in range(args.steps):
+                k = K if i == 0 else sk                             # step 0: the full, un-extrapolated cold pair
+                t0 = time.perf_counter()
+                r = RE.run_pair(ns, os.path.join(work, f"s{i}"), K=k, pair_seed=100 + i, overlap=0.5, weights=weights, fmr=False)
+                walls.append(time.perf_counter() - t0)
+                shutil.rmtree(os.path.join(work, f"s{i}"), ignore_errors=True)
+                steps.append(dict(kpts=k, seconds=r["seconds"], partI_s=r["partI_s"], partII_s=r["partII_s"], M=r["M"],
+                                  value=k / r["seconds"]))
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        full = steps[0]
+        v = full["value"]
+        rest = [st["value"] for st in steps[1:]]
+        sample = (f"step 0 = one FULL cold {K}-keypoint pair through the unmodified reference (Evaluator_PartI.run_onescene + "
+                  f"Evaluator_PartII.run_onescene, file protocol on /dev/shm, torch CPU {threads} threads): {full['seconds']:.1f} s, "
+                  f"M={full['M']}; steps 1..{args.steps - 1} = {sk}-keypoint pairs through the same code (their keypoint-pairs/s is "
+                  f"reported in sampled_steps, not in value)")
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                                 "seconds_per_cold_pair": full["seconds"], "same_config": True},
+                "sampled_steps": {"kpts": sk, "value_mean": float(np.mean(rest)) if rest else None,
+                                  "value_min": float(np.min(rest)) if rest else None, "value_max": float(np.max(rest)) if rest else None},
+                "ms_per_step_note": "wall time per timed step as executed (step 0 a full pair, the rest bounded samples); value is step 0",
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    # fallback: the oracle port, bounded sample extrapolated (no reference sources on this box)
     vals = []
     cores, sample = 0, ""
-    # bounded sample per step, sized so that the whole run stays within a few minutes whatever --steps asks for (the PartI
-    # sample dominates a step's wall time and its cost per keypoint is linear in the sample)
     skp = 900 if args.steps <= 8 else 450 if args.steps <= 20 else 300
     for i in range(args.warmup + args.steps):
         sec, cores, sample, _ = cpu_pair_seconds(args.kpts, sample_kp=300 if i < args.warmup else skp,
@@ -177,12 +239,55 @@ def run_reference(args):
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * args.kpts / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: one cold {args.kpts}-keypoint 3DMatch-shaped pair, PartI+PartII + matching + YOHO-C/O",
-                       "kpts": args.kpts},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def real_weights_available():
+    ck = os.path.join(ROOT, "oracle", "_ref", "ckpt")
+    return os.path.exists(os.path.join(ck, "PartI.npz")) and os.path.exists(os.path.join(ck, "PartII.npz"))
+
+
+def pick_weights(args):
+    if args.weights == "auto":
+        return "real" if real_weights_available() else "synth"
+    return args.weights
+
+
+def weights_note(w):
+    return ("the reference's shipped checkpoints (model/PartI_train, model/PartII_train; extracted to oracle/_ref/ckpt by build())"
+            if w == "real" else "seeded synthetic (yoho_b200.synth), reference architecture")
+
+
+def load_weights(w):
+    from yoho_b200 import synth
+    if w == "real":
+        ck = os.path.join(ROOT, "oracle", "_ref", "ckpt")
+        return dict(np.load(os.path.join(ck, "PartI.npz"))), dict(np.load(os.path.join(ck, "PartII.npz")))
+    return synth.synth_state_dict("PartI", 0), synth.synth_state_dict("PartII", 0)
+
+
+def reference_subprocess(device, K, weights, tf32=-1, threads=0, warmup_k=500, timeout=900):
+    """The unmodified reference on `device` in a process of its own (oracle/run_ref_evaluator.py).  Returns its info dict or
+    {'unavailable': why}."""
+    import shutil
+    work = shm_dir()
+    try:
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_ref_evaluator.py"), "--backend", "reference", "--device", device,
+               "--work", work, "--K", str(K), "--overlap", "0.5", "--pair-seed", "0", "--weights", weights, "--warmup-K", str(warmup_k),
+               "--tf32", str(tf32), "--threads", str(threads)]
+        env = dict(os.environ)
+        env.pop("OMP_NUM_THREADS", None)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if r.returncode != 0:
+            return {"unavailable": (r.stderr.strip().splitlines() or ["failed"])[-1][:300]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -203,8 +308,10 @@ def run_ours(args):
     eng = get_engine(local_rank)
     if args.gconv:
         eng.set_gconv_impl(args.gconv)
-    eng.load_part1(synth.synth_state_dict("PartI", 0))
-    eng.load_part2(synth.synth_state_dict("PartII", 0))
+    weights = pick_weights(args)
+    sdI, sdII = load_weights(weights)
+    eng.load_part1(sdI)
+    eng.load_part2(sdII)
     dev = eng.device
     K = args.kpts
     sets_h, sets_d, sets_p = [], [], []
@@ -243,9 +350,17 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     Ms = []
-    for i in range(args.steps):
-        r = pipe.register(*sets_d[i % N_SETS], lean=True)      # the two transforms + M (no per-stage tensor views on the host)
-        Ms.append(r["M"])
+    if args.per_pair_sync:
+        for i in range(args.steps):
+            r = pipe.register(*sets_d[i % N_SETS], lean=True)  # one pair at a time: the host waits for each pair's match count
+            Ms.append(r["M"])
+    else:
+        # the dataset form (a step = one cold pair; pairs are processed as a sequence): pair i+1's PartI is queued before the
+        # host waits for pair i's match count, so that wait never idles the device.  Same kernels, same results, same seeds.
+        keep = []
+        for r in pipe.register_many(sets_d[i % N_SETS] for i in range(args.steps)):
+            Ms.append(r["M"])
+            keep.append(r["T_co"])
     ev1.record()
     barrier()
     launches = eng.launch_count() - l0
@@ -265,6 +380,15 @@ def run_ours(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()                      # samples of both timed regions (device-resident and end-to-end)
+    # the same loop once more with per-pair accounting (events around upload-wait / compute, host clocks) — diagnostic, untimed
+    st = {}
+    for out in pipe.register_stream((sets_p[i % N_SETS] for i in range(args.steps)), stats=st):
+        pass
+    med = lambda v: float(statistics.median(v)) if v else None
+    e2e_diag = {"copy_wait_ms": med(st.get("copy_wait")), "period_ms": med(st.get("period")),
+                "upload_host_ms": med(st.get("upload_host")), "begin_host_ms": med(st.get("begin_host")),
+                "end_host_ms": med(st.get("end_host")), "d2h_wait_host_ms": med(st.get("d2h_wait_host")),
+                "numa": getattr(PairPipeline, "numa_note", None)}
     # raw H2D rate of one pinned fragment on this box (diagnostic next to e2e: 77 MB per pair must cross this link)
     h2d_gbs = None
     try:
@@ -292,7 +416,15 @@ def run_ours(args):
     if fourier:     # algorithmic FLOPs of the two layers (13 taps x 60 group elements), whatever formulation executes them
         dfl = args.steps * 2 * K * 60 * 13 * 256 * 512 * 2 * 2.0
     achieved = dfl / (dms / 1000.0) / 1e12 if dms > 0 else 0.0
-    peak = pk["bf16_sustained"]
+    # burst peak for a timed region shorter than a second (the sustained figure was measured over 4 s at 1200 MHz), else sustained
+    burst = ms < 1000.0
+    peak = pk["bf16"] if burst else pk["bf16_sustained"]
+    # executed bf16 FLOPs of the same launches: the per-irrep GEMMs execute 244/780 of the MACs, x3 bf16 products each; the
+    # transforms 2 products of 60x64 (padded) x 3 bf16 products per channel per keypoint
+    gemm = [p for p in prof if p["name"] in ("p1_L2_256x512", "p1_L3_512x256")]
+    gemm_ms = sum(p["ms"] for p in gemm)
+    gemm_exec = (sum(p["flops"] for p in gemm) * 3.0) if fourier else (sum(p["flops"] for p in gemm) * 3.0)
+    executed_tflops = gemm_exec / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
@@ -304,7 +436,11 @@ def run_ours(args):
     gconv_ms = sum(p["ms"] for p in prof)
     roofline = {"bound": "tensor", "kernel": "gather-GEMM group convolution, PartI layers 2+3 (256->512->256, 13 taps)" + (" in the group-Fourier domain: per-irrep GEMMs + transforms" if fourier else ""),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "peak_source": pk["src"] + (", burst bf16 (timed region %.2f s < 1 s)" % (ms / 1000.0) if burst
+                                            else ", sustained bf16 (timed region %.1f s)" % (ms / 1000.0)),
+                "executed_tflops": executed_tflops, "executed_frac": executed_tflops / peak if (executed_tflops and peak) else None,
+                "executed_note": "bf16 FLOPs the tensor cores actually execute in the layer-2/3 GEMM launches (3 bf16 products per "
+                                 "MAC; Fourier form: 244/780 of the algorithmic MACs) over those launches' own time (transforms excluded)",
                 "launches": dln, "avg_launch_ms": dms / dln if dln else None,
                 "algorithmic_flops_per_launch": dfl / dln if dln else None,
                 "share_of_step": dms / ms if ms else None, "all_gconv_share_of_step": gconv_ms / ms if ms else None,
@@ -316,10 +452,37 @@ def run_ours(args):
     line = None
     if rank == 0:
         cpu = None
+        gpu_ref = None
         if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N=1 only
-            sec, cores, sample, _ = cpu_pair_seconds(K)
-            cpu = {"value": K / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                   "seconds_per_cold_pair": sec}
+            have_ref = reference_sources_available()
+            r = None
+            if have_ref:
+                # bounded sample: a 1250-keypoint pair through the UNMODIFIED reference on the host cores, scaled by the
+                # keypoint ratio (PartI, rotation index, PartII are linear in K; the 1-NN search is quadratic but < 3 % of a pair,
+                # so the scaling favours the reference).  `--impl reference` runs the full pair.
+                ks = min(K, 1250)
+                r = reference_subprocess("cpu", ks, weights, threads=host_threads(), warmup_k=200)
+            if r and "unavailable" not in r:
+                sec = r["seconds"] * K / ks
+                cpu = {"value": K / sec, "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                       "sample": f"one {ks}-keypoint pair through the unmodified reference evaluator (file protocol on /dev/shm, torch CPU "
+                                 f"{r['threads']} threads): {r['seconds']:.1f} s, M={r['M']}; scaled x{K / ks:.1f} to {K} keypoints",
+                       "seconds_per_cold_pair": sec}
+            else:
+                sec, cores, sample, _ = cpu_pair_seconds(K)
+                cpu = {"value": K / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                       "seconds_per_cold_pair": sec}
+            if have_ref and not args.no_gpu_reference:
+                # same-box competitor: the unmodified reference on THIS GPU through its own .cuda() path
+                # (torch/cuDNN FP32 conv on the 13x-gathered tensors, host loops, .npy round trips on /dev/shm), full pair
+                gpu_ref = {}
+                for name, tf in (("tf32_torch_default", -1), ("tf32_off", 0)):
+                    g = reference_subprocess("cuda", K, weights, tf32=tf, threads=host_threads(), warmup_k=900)
+                    gpu_ref[name] = ({"value": K / g["seconds"], "unit": UNIT, "seconds_per_cold_pair": g["seconds"],
+                                      "partI_evaluator_s": g["partI_s"], "partII_evaluator_s": g["partII_s"], "M": g["M"]}
+                                     if "unavailable" not in g else g)
+                gpu_ref["kind"] = ("unmodified reference (tests/evaluator.py run_onescene x2) on cuda:0 with torch %s; not the "
+                                   "headline arm (the driver's reference arm is the CPU path)" % torch.__version__)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if eng.impl_name == "simt" else "f32 via bf16x3 split products, f32 accumulate (tcgen05" + (", group-Fourier layers 2+3)" if fourier else ")"),
@@ -327,16 +490,20 @@ def run_ours(args):
                 "config": {"workload": f"configs[1]: one cold {K}-keypoint 3DMatch-shaped pair per rank per step: PartI x2, "
                                        "mutual 1-NN, rotation argmax, YOHO-C 1000 iters, PartII, YOHO-O",
                            "kpts": K, "pairs_per_step_per_gpu": 1, "matches_per_pair": int(np.mean(Ms)),
+                           "call": ("PairPipeline.register (blocking per pair)" if args.per_pair_sync else
+                                    "PairPipeline.register_many (split-phase yoho_register_pair_begin/_end over the step sequence)"),
                            "parallelism": f"dp{world} (independent pairs, no data-path collective)",
                            "l2": f"inputs rotate over {N_SETS} distinct pairs ({N_SETS * 2 * K * 7680 / 1e6:.0f} MB) > 126 MB L2",
-                           "weights": "seeded synthetic (yoho_b200.synth), reference architecture"},
+                           "weights": weights_note(weights)},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": PairPipeline.h2d_bytes(K), "d2h_bytes_per_step": PairPipeline.d2h_bytes(),
-                        "h2d_link_gbs": h2d_gbs},
+                        "h2d_link_gbs": h2d_gbs, **e2e_diag},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "layers": prof}
         if cpu:
             line["cpu_baseline"] = cpu
+        if gpu_ref:
+            line["gpu_reference_baseline"] = gpu_ref
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -352,6 +519,11 @@ def main():
     ap.add_argument("--kpts", type=int, default=5000)
     ap.add_argument("--gconv", default=None, choices=[None, "simt", "tcgen05", "tcgen05_split", "tcgen05_fourier"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-pair-sync", action="store_true", help="device-resident region: one blocking pair call per step "
+                    "(latency form) instead of the split-phase sequence call")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the unmodified-reference-on-cuda legs (N=1 only)")
+    ap.add_argument("--weights", default="auto", choices=["auto", "real", "synth"],
+                    help="auto = the reference's shipped checkpoints when oracle/_ref/ckpt exists, else seeded synthetic")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -233,6 +233,15 @@ typedef struct {
 } yoho_pair_io;
 int yoho_register_pair(yoho_ctx* ctx, const yoho_pair_io* io, int32_t* M_host, void* stream);
 
+/* The same pair in two phases, for a SEQUENCE of pairs (a dataset: tests/evaluator.py:41-47 loops over dataset.pair_ids).
+ * _begin queues PartI x2 + the mutual matching and starts the match count on its way to the host, without waiting;
+ * _end(io of the OLDEST begun pair) waits for that count and queues the rest.  Calling begin(i+1) before end(i) puts ~4 ms of
+ * device work between a pair's matching and the moment the host needs its count, so the single host synchronisation of a pair
+ * no longer idles the device (yoho_register_pair = begin + end back to back; results are identical).  FIFO order, at most 8
+ * pairs in flight, every pair with its own output buffers; one stream. */
+int yoho_register_pair_begin(yoho_ctx* ctx, const yoho_pair_io* io, void* stream);
+int yoho_register_pair_end(yoho_ctx* ctx, const yoho_pair_io* io, int32_t* M_host, void* stream);
+
 /* "Next" row — the tail of the group-feature lift, YOHO_testset.py:153-166: for every group rotation g,
  * rotate the keypoints (Keys @ R_g^T, float64), 1-NN of each into that rotation's down-sampled cloud (float64 distances
  * against float32 points, first minimal index), gather the 32-d backbone feature: out[k,:,g] = feats[offsets[g] + nn, :].

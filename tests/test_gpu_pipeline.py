@@ -282,6 +282,31 @@ def test_register_stream_equals_per_pair_calls(engine):
     assert list(PairPipeline(engine, seed=0).register_stream(iter([]))) == []
 
 
+def test_register_many_equals_per_pair_calls(engine):
+    """Split-phase sequence call (yoho_register_pair_begin / _end, pair i+1 begun before pair i ends) == blocking per-pair
+    calls, bit for bit, for ragged sizes, an empty fragment in the middle and lookahead 1 and 3."""
+    from yoho_b200.pipeline import PairPipeline
+    engine.load_part1(synth.synth_state_dict('PartI', 0))
+    engine.load_part2(synth.synth_state_dict('PartII', 0))
+    dev = engine.device
+    t = lambda v: torch.from_numpy(v).to(dev)
+    ps = [synth.make_fragment_pair(200 + 70 * i, seed=40 + i, overlap=0.6) for i in range(5)]
+    args = [(t(p['feat_A']), t(p['feat_B']), t(p['kps_A']), t(p['kps_B'])) for p in ps]
+    z = (torch.zeros((0, 32, 60), device=dev), args[0][1], torch.zeros((0, 3), dtype=torch.float64, device=dev), args[0][3])
+    args.insert(2, z)
+    one = [PairPipeline(engine, seed=5 + i).register(*a, lean=True) for i, a in enumerate(args)]
+    for la in (1, 3):
+        got = list(PairPipeline(engine, seed=5).register_many(iter(args), lookahead=la))
+        assert len(got) == len(args)
+        for g, o in zip(got, one):
+            assert g['M'] == o['M'] and torch.equal(g['T_co'], o['T_co'])
+    assert got[2]['M'] == 0 and np.array_equal(got[2]['T_co'][0].cpu().numpy(), np.eye(4)[:3])
+    # protocol errors are reported, not silently mis-ordered
+    from yoho_b200._lib import YohoError
+    with pytest.raises(YohoError):
+        engine.register_pair_end(engine._pair_io(*args[0], 10, 10, 0.07, 0.09, 1))
+
+
 def test_pipeline_degenerate_statistics_gives_identity(engine):
     """DR_statictic returns None when sum_bins n(n-.01)(n-.02), n = count/100, is below 1e-4, and the reference then writes
     the identity with recalltime 50001 (tests/estimator.py:41-51,107-108).  Five keypoints per fragment force it: at least one

@@ -77,6 +77,8 @@ SYMBOLS = {
     "yoho_o_order": (_i, [_vp, _i, ctypes.c_uint64, _vp, _vp]),
     "yoho_o_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_register_pair": (_i, [_vp, _vp, _vp, _vp]),
+    "yoho_register_pair_begin": (_i, [_vp, _vp, _vp]),
+    "yoho_register_pair_end": (_i, [_vp, _vp, _vp, _vp]),
     "yoho_lift_group_features": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_fmr_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_double, _vp, _vp]),
     "yoho_registration_errors": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

@@ -133,6 +133,10 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     for (GLayer* l : layers) free_layer(*l);
     GBn* bns[] = {&c->p1_bn_a, &c->p1_bn_b, &c->p1_bn_out, &c->p2_bn_init, &c->p2_bn_a, &c->p2_bn_b, &c->p2_bn1, &c->p2_bn2};
     for (GBn* b : bns) free_bn(*b);
+    if (c->pair_M_pinned) {
+        cudaFreeHost(c->pair_M_pinned);
+        for (int i = 0; i < yoho_ctx::kPairRing; ++i) cudaEventDestroy(c->pair_ev[i]);
+    }
     cudaFree(c->d_rot); cudaFree(c->d_rot32); cudaFree(c->d_perm); cudaFree(c->d_perm_t);
     cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one); cudaFree(c->d_idx_ident);
     for (int r = 0; r < 8; ++r) {

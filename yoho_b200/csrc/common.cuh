@@ -96,6 +96,11 @@ struct yoho_ctx {
     GLayer p2_init, p2_a, p2_b, p2_fc1, p2_fc2, p2_fc3;
     GLayer p2_b_split[5];           // p2_b cut along its 13 taps (3,3,3,2,2): five partial GEMMs in one launch (only 22 row tiles at M = 2800)
     GBn p2_bn_init, p2_bn_a, p2_bn_b, p2_bn1, p2_bn2;
+    // split-phase pair calls (pair.cu): FIFO of match counts in flight — pinned host slot + event per begun pair
+    static constexpr int kPairRing = 8;
+    int32_t* pair_M_pinned = nullptr;           // [kPairRing] cudaHostAlloc
+    cudaEvent_t pair_ev[kPairRing] = {nullptr};
+    int pair_head = 0, pair_tail = 0;            // begin pushes at head, end pops at tail
     // grow-only workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;

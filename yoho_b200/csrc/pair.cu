@@ -25,26 +25,62 @@ __global__ void identity_kernel(double* __restrict__ Tc, double* __restrict__ To
 
 }  // namespace
 
-extern "C" int yoho_register_pair(yoho_ctx* ctx, const yoho_pair_io* io, int32_t* M_host, void* stream) {
-    YARG(ctx && io && M_host && io->featA && io->featB && io->kpsA && io->kpsB && io->Ka >= 0 && io->Kb >= 0);
+static int pair_check(yoho_ctx* ctx, const yoho_pair_io* io) {
+    YARG(ctx && io && io->featA && io->featB && io->kpsA && io->kpsB && io->Ka >= 0 && io->Kb >= 0);
     YARG(io->eqvA && io->eqvB && io->descA && io->descB && io->pairs && io->n_pairs && io->dr_index && io->k0 && io->k1);
     YARG(io->hyp && io->c_status && io->T_c && io->c_best && io->c_inl && io->c_mask && io->quat && io->trans && io->order);
     YARG(io->T_o && io->o_best && io->o_inl && io->o_mask && io->c_iters >= 0 && io->o_iters >= 0);
+    return YOHO_OK;
+}
+
+// Front half of a pair: PartI on both fragments (unless given), the mutual matching, and the match count on its way to a pinned
+// host slot (asynchronous; the event marks its arrival).  Nothing here waits for the device.
+extern "C" int yoho_register_pair_begin(yoho_ctx* ctx, const yoho_pair_io* io, void* stream) {
+    if (int rc = pair_check(ctx, io)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
+    if (ctx->pair_head - ctx->pair_tail >= yoho_ctx::kPairRing) {
+        yoho_set_error("yoho_register_pair_begin: %d pairs already in flight (call yoho_register_pair_end)", yoho_ctx::kPairRing);
+        return YOHO_ERR_ARG;
+    }
+    if (!ctx->pair_M_pinned) {
+        YCHECK(cudaHostAlloc((void**)&ctx->pair_M_pinned, sizeof(int32_t) * yoho_ctx::kPairRing, cudaHostAllocDefault));
+        for (int i = 0; i < yoho_ctx::kPairRing; ++i) YCHECK(cudaEventCreateWithFlags(&ctx->pair_ev[i], cudaEventDisableTiming));
+    }
     int rc;
     if (!io->have_part1) {
         if ((rc = yoho_part1_forward(ctx, io->featA, io->Ka, io->eqvA, nullptr, io->descA, stream))) return rc;
         if ((rc = yoho_part1_forward(ctx, io->featB, io->Kb, io->eqvB, nullptr, io->descB, stream))) return rc;
     }
-    int M = 0;
+    const int slot = ctx->pair_head % yoho_ctx::kPairRing;
     if (io->Ka > 0 && io->Kb > 0) {
         if ((rc = yoho_mutual_nn(ctx, io->descA, io->Ka, io->descB, io->Kb, io->pairs, io->n_pairs, nullptr, nullptr, stream))) return rc;
-        YCHECK(cudaMemcpyAsync(&M, io->n_pairs, sizeof(int), cudaMemcpyDeviceToHost, st));
-        YCHECK(cudaStreamSynchronize(st));                       // the one host synchronisation of the pair
     } else {
         YCHECK(cudaMemsetAsync(io->n_pairs, 0, sizeof(int), st));
     }
+    YCHECK(cudaMemcpyAsync(ctx->pair_M_pinned + slot, io->n_pairs, sizeof(int), cudaMemcpyDeviceToHost, st));
+    YCHECK(cudaEventRecord(ctx->pair_ev[slot], st));
+    ctx->pair_head++;
+    return YOHO_OK;
+}
+
+// Back half of the OLDEST begun pair (`io` must be the structure passed to its begin call): waits for that pair's match count —
+// the one host synchronisation of a pair; when other pairs were begun in between it has long arrived and the device never idles —
+// then queues rotation index, YOHO-C, PartII and YOHO-O.
+extern "C" int yoho_register_pair_end(yoho_ctx* ctx, const yoho_pair_io* io, int32_t* M_host, void* stream) {
+    if (int rc = pair_check(ctx, io)) return rc;
+    YARG(M_host);
+    cudaStream_t st = (cudaStream_t)stream;
+    YCHECK(cudaSetDevice(ctx->device));
+    if (ctx->pair_head == ctx->pair_tail) {
+        yoho_set_error("yoho_register_pair_end without a matching yoho_register_pair_begin");
+        return YOHO_ERR_ARG;
+    }
+    const int slot = ctx->pair_tail % yoho_ctx::kPairRing;
+    ctx->pair_tail++;
+    YCHECK(cudaEventSynchronize(ctx->pair_ev[slot]));
+    const int M = ctx->pair_M_pinned[slot];
+    int rc;
     *M_host = M;
     if (M == 0) {
         identity_kernel<<<1, 32, 0, st>>>(io->T_c, io->T_o, io->c_best, io->o_best, io->c_inl, io->o_inl);
@@ -68,4 +104,14 @@ extern "C" int yoho_register_pair(yoho_ctx* ctx, const yoho_pair_io* io, int32_t
                            nullptr, stream))) return rc;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
+}
+
+extern "C" int yoho_register_pair(yoho_ctx* ctx, const yoho_pair_io* io, int32_t* M_host, void* stream) {
+    YARG(M_host);
+    if (ctx && ctx->pair_head != ctx->pair_tail) {
+        yoho_set_error("yoho_register_pair while split-phase pairs are in flight");
+        return YOHO_ERR_ARG;
+    }
+    if (int rc = yoho_register_pair_begin(ctx, io, stream)) return rc;
+    return yoho_register_pair_end(ctx, io, M_host, stream);
 }

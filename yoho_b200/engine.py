@@ -330,11 +330,11 @@ class Engine:
             lay = cache[key] = (ent, max(total, 256))
         return lay
 
-    def register_pair(self, featA, featB, kpsA, kpsB, c_iters, o_iters, c_dist, o_dist, seed, eqvA=None, eqvB=None,
-                      descA=None, descB=None):
-        """yoho_register_pair: PartI x2 (unless eqv/desc are given), mutual matching, rotation index, YOHO-C, PartII, YOHO-O with
-        ONE host round trip.  Returns a `PairBuffers`: every output lives in one allocation sized for min(Ka, Kb) matches and is
-        materialised as a tensor view only when asked for (`out["quat"]`), so the throughput path pays for two views."""
+    def _pair_io(self, featA, featB, kpsA, kpsB, c_iters, o_iters, c_dist, o_dist, seed, eqvA=None, eqvB=None, descA=None,
+                 descB=None):
+        """Builds the yoho_pair_io of one pair: every output lives in ONE allocation sized for min(Ka, Kb) matches."""
+        if (eqvA is None) != (descA is None) or (eqvB is None) != (descB is None) or (eqvA is None) != (eqvB is None):
+            raise ValueError("precomputed PartI outputs must be given together: eqvA, eqvB, descA, descB")
         fa, fb, ka, kb = self._f32(featA), self._f32(featB), self._f64(kpsA), self._f64(kpsB)
         Ka, Kb = fa.shape[0], fb.shape[0]
         have = eqvA is not None
@@ -358,9 +358,31 @@ class Engine:
             else:
                 ptr = base + ent[name][0]
             setattr(io, name, ptr)
+        return io, buf, ent, ext, (fa, fb, ka, kb)
+
+    def register_pair(self, featA, featB, kpsA, kpsB, c_iters, o_iters, c_dist, o_dist, seed, eqvA=None, eqvB=None,
+                      descA=None, descB=None):
+        """yoho_register_pair: PartI x2 (unless eqv/desc are given), mutual matching, rotation index, YOHO-C, PartII, YOHO-O with
+        ONE host round trip.  Returns a `PairBuffers`: every output lives in one allocation sized for min(Ka, Kb) matches and is
+        materialised as a tensor view only when asked for (`out["quat"]`), so the throughput path pays for two views."""
+        io, buf, ent, ext, keep = self._pair_io(featA, featB, kpsA, kpsB, c_iters, o_iters, c_dist, o_dist, seed, eqvA, eqvB,
+                                                descA, descB)
         M = ctypes.c_int32(0)
         _lib.check(self.lib.yoho_register_pair(self.h, ctypes.byref(io), ctypes.byref(M), _stream()))
-        return PairBuffers(buf, ent, ext, int(M.value), (fa, fb, ka, kb))
+        return PairBuffers(buf, ent, ext, int(M.value), keep)
+
+    def register_pair_begin(self, *args, **kw):
+        """First phase of `register_pair` (yoho_register_pair_begin): queues PartI x2 + matching, does not wait.  Returns the
+        token to hand to `register_pair_end` (pairs end in the order they were begun)."""
+        tok = self._pair_io(*args, **kw)
+        _lib.check(self.lib.yoho_register_pair_begin(self.h, ctypes.byref(tok[0]), _stream()))
+        return tok
+
+    def register_pair_end(self, tok):
+        io, buf, ent, ext, keep = tok
+        M = ctypes.c_int32(0)
+        _lib.check(self.lib.yoho_register_pair_end(self.h, ctypes.byref(io), ctypes.byref(M), _stream()))
+        return PairBuffers(buf, ent, ext, int(M.value), keep)
 
     # ---- E: estimators -----------------------------------------------------------------------------
     def gather_kps(self, kps0, kps1, pairs):

@@ -64,7 +64,7 @@ class numa_local:
     GPU's PCIe root hangs off, which is what the H2D DMA reads fastest.  A no-op when NVML or the affinity call is missing."""
 
     def __init__(self, index=0):
-        self.index, self.prev = int(index), None
+        self.index, self.prev, self.note = int(index), None, "not attempted"
 
     def __enter__(self):
         try:
@@ -79,8 +79,12 @@ class numa_local:
             if cpus and cpus != allowed:
                 self.prev = allowed
                 os.sched_setaffinity(0, cpus)
-        except Exception:
+                self.note = f"pinned-buffer first touch bound to {len(cpus)} GPU-local CPUs of {len(allowed)} allowed"
+            else:
+                self.note = f"no binding needed: NVML's affinity for GPU {self.index} covers all {len(allowed)} allowed CPUs"
+        except Exception as e:  # noqa: BLE001
             self.prev = None
+            self.note = f"no-op ({type(e).__name__})"
         return self
 
     def __exit__(self, *exc):

@@ -85,6 +85,24 @@ class PairPipeline:
                    o_best=ro["best_iter"], o_inl=ro["n_inl"], o_mask=ro["mask"])
         return out
 
+    def register_many(self, inputs, lookahead=1):
+        """Throughput form of `register` for a SEQUENCE of device-resident pairs (a dataset's pair list): generator over
+        `(featA, featB, kpsA, kpsB)` tuples yielding one lean result (`M`, `T_co` [2,3,4]) per pair, in order.  Pair i+1's PartI
+        and matching are queued BEFORE the host waits for pair i's match count (yoho_register_pair_begin / _end), so the one
+        host synchronisation of a pair never idles the device.  Same seeds, same results as calling `register` pair by pair."""
+        e = self.eng
+        assert self.fused, "register_many needs the fused pair call"
+        pend = []
+        for args in inputs:
+            self.seed += 1
+            pend.append(e.register_pair_begin(*args, self.c_iters, self.o_iters, self.c_dist, self.o_dist, self.seed))
+            if len(pend) > lookahead:
+                t = e.register_pair_end(pend.pop(0))
+                yield PairResult(M=t.M, T_co=t["T_co"], _buffers=t)
+        while pend:
+            t = e.register_pair_end(pend.pop(0))
+            yield PairResult(M=t.M, T_co=t["T_co"], _buffers=t)
+
     # ---- host-facing calls (the e2e path: host buffers in, host transforms out) -----------------------------
     @staticmethod
     def pin(featA, featB, kpsA, kpsB):
@@ -96,8 +114,10 @@ class PairPipeline:
             t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
             return t
         # allocate (and first-touch) on the memory node next to the GPU: the H2D DMA of 77 MB per pair reads it from there
-        with numa_local(torch.cuda.current_device() if torch.cuda.is_available() else 0):
-            return (p(featA, torch.float32), p(featB, torch.float32), p(kpsA, torch.float64), p(kpsB, torch.float64))
+        with numa_local(torch.cuda.current_device() if torch.cuda.is_available() else 0) as nl:
+            out = (p(featA, torch.float32), p(featB, torch.float32), p(kpsA, torch.float64), p(kpsB, torch.float64))
+        PairPipeline.numa_note = nl.note
+        return out
 
     def register_pinned(self, fa_pin, fb_pin, ka_pin, kb_pin):
         """Pinned host tensors in -> numpy transforms out.  The four H2D copies run on a side stream; PartI of fragment A
@@ -127,28 +147,37 @@ class PairPipeline:
 
     def register_stream(self, pinned_pairs, stats=None):
         """Throughput form of `register_pinned` for a sequence of pairs (the way a dataset is processed, tests/evaluator.py:41-47):
-        generator over `(fa_pin, fb_pin, ka_pin, kb_pin)` tuples yielding one `dict(T_c, T_o, M)` per pair, in order.  The H2D
-        copies of pair i+1 run on the side stream while pair i computes, and the D2H of pair i's transforms (into a pinned
-        buffer) is awaited only when pair i+1 has been queued, so neither copy sits on the critical path.  Every pair's inputs
-        still cross PCIe from host memory and every result is read back to the host.
-        `stats` (a dict) switches on per-pair accounting with CUDA events on the main stream and host clocks; on return it holds
-        lists (ms per pair): copy_wait = main stream stalled on the upload of ITS pair, compute = first to last kernel of the pair,
-        gap = device idle between the end of the previous pair and this pair's wait (the host was late queueing), and the host
-        times upload_host / call_host / d2h_wait_host spent in the three host-side steps."""
+        generator over `(fa_pin, fb_pin, ka_pin, kb_pin)` tuples yielding one `dict(T_c, T_o, M)` per pair, in order.
+        Software pipeline over three persistent device input sets: while pair n's rotation index / estimators / PartII run, pair
+        n+1's PartI has already been queued behind them (split-phase pair call: the host never idles the device waiting for a
+        match count) and pair n+2's inputs are crossing PCIe on the side stream; the D2H of pair n's transforms (into a pinned
+        buffer) is awaited only after pair n+1 has been queued.  Every pair's inputs still come from host memory and every
+        result is read back to the host.
+        `stats` (a dict) switches on accounting with CUDA events on the main stream and host clocks; on return it holds lists
+        (ms per pair): copy_wait = main stream stalled on the upload of a pair, period = time between the last kernels of
+        consecutive pairs, and the host times upload_host / begin_host / end_host / d2h_wait_host of the four host-side steps."""
         import time as _time
-        dev = self.eng.device
+        e = self.eng
+        dev = e.device
         main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
+        NS = 3
+        # persistent sets of device input buffers (no allocator traffic in steady state): pair n uses set n % 3; the copy of pair
+        # n + 3 into the same set waits for the event recorded after pair n's last kernel was queued
+        if not hasattr(self, "_in_sets") or len(self._in_sets) != NS:
+            self._in_sets = [None] * NS
+            self._in_free = [None] * NS
+            self._res_pin = [torch.empty((2, 3, 4), dtype=torch.float64, pin_memory=True) for _ in range(NS)]
+        timing = stats is not None
 
-        # two persistent sets of device input buffers (no allocator traffic in steady state): pair n uses set n % 2; the copy of
-        # pair n + 2 into the same set waits for the event recorded after pair n's last kernel was queued
-        if not hasattr(self, "_in_sets"):
-            self._in_sets = [None, None]
-            self._in_free = [None, None]
+        def note(key, t0):
+            if timing:
+                stats.setdefault(key, []).append(1e3 * (_time.perf_counter() - t0))
 
         def upload(pp, slot):
+            t0 = _time.perf_counter()
             cur = self._in_sets[slot]
             if cur is None or any(c.shape != t.shape or c.dtype != t.dtype for c, t in zip(cur, pp)):
                 cur = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in pp]
@@ -161,65 +190,84 @@ class PairPipeline:
                     c.copy_(t, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
+            note("upload_host", t0)
             return cur, ev
+
+        waits, ends = [], []
+
+        def begin(up):
+            (fa, fb, ka, kb), ev = up
+            t0 = _time.perf_counter()
+            if timing:
+                w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                w0.record(main)
+            main.wait_event(ev)
+            if timing:
+                w1.record(main)
+                waits.append((w0, w1))
+            self.seed += 1
+            tok = e.register_pair_begin(fa, fb, ka, kb, self.c_iters, self.o_iters, self.c_dist, self.o_dist, self.seed)
+            note("begin_host", t0)
+            return tok
+
+        def end(tok, n):
+            t0 = _time.perf_counter()
+            t = e.register_pair_end(tok)
+            free = torch.cuda.Event(enable_timing=timing)
+            free.record(main)                           # every kernel reading this input set has been queued
+            self._in_free[n % NS] = free
+            if timing:
+                ends.append(free)
+            host = self._res_pin[n % NS]
+            host.copy_(t["T_co"], non_blocking=True)
+            dv = torch.cuda.Event()
+            dv.record(main)
+            note("end_host", t0)
+            return host, dv, t.M
 
         def finish(pend):
             host, ev, M = pend
             t0 = _time.perf_counter()
             ev.synchronize()
-            if stats is not None:
-                stats.setdefault("d2h_wait_host", []).append(1e3 * (_time.perf_counter() - t0))
+            note("d2h_wait_host", t0)
             res = host.numpy().copy()
             return dict(T_c=res[0], T_o=res[1], M=M)
 
-        marks = []          # per pair: (before wait, after wait, end) events on the main stream
-
+        if not self.fused:
+            raise RuntimeError("register_stream needs the fused pair call")
         it = iter(pinned_pairs)
-        try:
-            nxt = upload(next(it), 0)
-        except StopIteration:
+        ups = []                                        # uploaded, not yet begun (at most 2)
+        n_up = 0
+        for _ in range(2):
+            try:
+                ups.append(upload(next(it), n_up % NS))
+                n_up += 1
+            except StopIteration:
+                break
+        if not ups:
             return
+        toks = [begin(ups.pop(0))]                      # begun, not yet ended (at most 2)
         pending = None
         n = 0
-        while nxt is not None:
-            (fa, fb, ka, kb), ev = nxt
-            t0 = _time.perf_counter()
+        while toks:
             try:
-                nxt = upload(next(it), (n + 1) & 1)     # prefetch: overlaps this pair's PartI
+                ups.append(upload(next(it), n_up % NS))     # pair n + 2: crosses PCIe during pair n + 1's PartI
+                n_up += 1
             except StopIteration:
-                nxt = None
-            t1 = _time.perf_counter()
-            if stats is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(main)
-            main.wait_event(ev)
-            if stats is not None:
-                e1.record(main)
-            r = self.register(fa, fb, ka, kb, lean=self.fused)
-            free = torch.cuda.Event(enable_timing=stats is not None)
-            free.record(main)                           # every kernel reading this input set has been queued
-            if stats is not None:
-                marks.append((e0, e1, free))
-                stats.setdefault("upload_host", []).append(1e3 * (t1 - t0))
-                stats.setdefault("call_host", []).append(1e3 * (_time.perf_counter() - t1))
-            self._in_free[n & 1] = free
-            if not hasattr(self, "_res_pin"):
-                self._res_pin = [torch.empty((2, 3, 4), dtype=torch.float64, pin_memory=True) for _ in range(2)]
-            host = self._res_pin[n & 1]
-            host.copy_(r["T_co"] if "T_co" in r else torch.stack([r["T_c"], r["T_o"]]), non_blocking=True)
-            dv = torch.cuda.Event()
-            dv.record(main)
+                pass
+            if ups:
+                toks.append(begin(ups.pop(0)))          # pair n + 1's PartI + matching queued before we wait for pair n's count
+            cur = end(toks.pop(0), n)
             if pending is not None:
                 yield finish(pending)
-            pending = (host, dv, r["M"])
+            pending = cur
             n += 1
         if pending is not None:
             yield finish(pending)
-        if stats is not None and marks:
+        if timing and ends:
             torch.cuda.synchronize()
-            stats["copy_wait"] = [a.elapsed_time(b) for a, b, _ in marks]
-            stats["compute"] = [b.elapsed_time(c) for _, b, c in marks]
-            stats["gap"] = [0.0] + [marks[i - 1][2].elapsed_time(marks[i][0]) for i in range(1, len(marks))]
+            stats["copy_wait"] = [a.elapsed_time(b) for a, b in waits]
+            stats["period"] = [ends[i - 1].elapsed_time(ends[i]) for i in range(1, len(ends))]
 
     def register_host(self, featA, featB, kpsA, kpsB):
         """numpy in (feat [K,32,60] f32, kps [K,3] f64) -> numpy transforms out; staging + H2D + D2H inside."""
