@@ -357,10 +357,10 @@ def run_ours(args):
     else:
         # the dataset form (a step = one cold pair; pairs are processed as a sequence): pair i+1's PartI is queued before the
         # host waits for pair i's match count, so that wait never idles the device.  Same kernels, same results, same seeds.
-        keep = []
+        # (results are dropped as they arrive: a kept T_co view would pin its pair's whole 80 MB output block, and fresh
+        # cudaMallocs inside the loop synchronise the device)
         for r in pipe.register_many(sets_d[i % N_SETS] for i in range(args.steps)):
             Ms.append(r["M"])
-            keep.append(r["T_co"])
     ev1.record()
     barrier()
     launches = eng.launch_count() - l0
