@@ -406,6 +406,23 @@ def run_ours(args):
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
     e2e = world * args.steps * K / (ms_e2e / 1000.0)
 
+    # ---- dataset-shaped jobs, STRONG scaling (BASELINE.json configs 3-5): one fixed set of fragments / pairs over all ranks ----
+    scene = None
+    if args.scene != "off":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import scene_bench as SB
+        scale = {"full": 1.0, "small": 0.15}[args.scene]
+        scene = {}
+        for key in ("c3", "c4"):
+            barrier()
+            scene[key] = SB.run_scene(eng, key, K, scale)
+            torch.cuda.empty_cache()
+        barrier()
+        scene["c5"] = SB.run_config5(eng, 2 * K)
+        scene["note"] = ("strong scaling: the same job at every N; keypoint_pairs_per_s = pairs * kpts / seconds with PartI run once "
+                         "per fragment (the amortised regime of tests/extractor.py:46-47), so it is not comparable with `value` "
+                         "(cold pairs: PartI twice per pair)")
+
     # ---- roofline of the dominant kernel: the 256<->512 group convolutions of PartI ---------------------------
     pk = peaks()
     fourier = eng.impl_name == "tcgen05_fourier"
@@ -504,6 +521,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if gpu_ref:
             line["gpu_reference_baseline"] = gpu_ref
+        if scene:
+            line["scene"] = scene
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -519,6 +538,8 @@ def main():
     ap.add_argument("--kpts", type=int, default=5000)
     ap.add_argument("--gconv", default=None, choices=[None, "simt", "tcgen05", "tcgen05_split", "tcgen05_fourier"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scene", default="full", choices=["full", "small", "off"],
+                    help="dataset-shaped strong-scaling legs (configs 3-5): full = 433 fragments / 1623 + 1781 pairs, small = 15 %% of it")
     ap.add_argument("--per-pair-sync", action="store_true", help="device-resident region: one blocking pair call per step "
                     "(latency form) instead of the split-phase sequence call")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the unmodified-reference-on-cuda legs (N=1 only)")

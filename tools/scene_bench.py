@@ -1,82 +1,154 @@
-"""Scene-level throughput (BASELINE.json configs 3-4, amortised regime): PartI once per FRAGMENT, then matching, rotation
-index, YOHO-C, PartII and YOHO-O once per PAIR from the cached descriptors (`yoho_b200.batch.register_scene`), pairs sharded
-over the ranks.  Prints one JSON line per configuration with the amortised keypoint-pairs/s and the YOHO-C success rate
-against the planted transforms.
+"""Scene-set throughput (BASELINE.json configs 3-5), STRONG scaling: one fixed dataset-shaped job, all ranks together.
 
-    python tools/scene_bench.py [--fragments 64] [--kpts 5000] [--config c3|c4|both]
-    python -m torch.distributed.run --nproc-per-node N ... tools/scene_bench.py      # pairs sharded over N ranks
+  c3  configs[2]: 3DMatch-test-shaped set — 433 fragments in 8 scenes of [60,60,60,55,57,37,66,38] (utils/dataset.py:167),
+      1623 pairs, pair overlap ~U[0.3,0.9], PartI once per fragment, YOHO-C (1000 iterations) + PartII + YOHO-O per pair
+  c4  configs[3]: 3DLoMatch-shaped set — same fragments, 1781 low-overlap pairs (~U[0.1,0.3]), YOHO-O 1000 hypotheses
+  c5  configs[4]: one 10 000-keypoint pair, fragment-1 descriptors sharded over the ranks, cross-rank mutual 1-NN
+
+`yoho_b200.batch.register_scene` does the work: scene-aware cut of the fragment list over the ranks, PartI on the owner,
+send/recv of the PartI outputs of the fragments that straddle a cut, split-phase pair loop, one gather of the transforms.
+Importable (`run_scene`, `run_config5`: bench.py's `scene` object) and a CLI:
+
+    python tools/scene_bench.py [--config c3|c4|c5|all] [--scale 1.0] [--kpts 5000]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 ... tools/scene_bench.py
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 import numpy as np                                 # noqa: E402
 import torch                                       # noqa: E402
-from yoho_b200 import synth, dist as ydist         # noqa: E402
-from yoho_b200.engine import get_engine            # noqa: E402
-from yoho_b200.pipeline import PairPipeline        # noqa: E402
-from yoho_b200.batch import register_scene         # noqa: E402
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--fragments", type=int, default=64)
-ap.add_argument("--kpts", type=int, default=5000)
-ap.add_argument("--config", default="both", choices=["c3", "c4", "both"])
-ap.add_argument("--repeat", type=int, default=2, help="timed passes per configuration (the best is reported)")
-args = ap.parse_args()
+CFG = {"c3": dict(name="configs[2] shape: 3DMatch-test-like set, YOHO-C 1000 iterations (+ PartII, YOHO-O)", pairs=1623, lo=0.55, hi=0.95),
+       "c4": dict(name="configs[3] shape: 3DLoMatch-like low-overlap set, YOHO-O 1000 hypotheses (+ YOHO-C)", pairs=1781, lo=0.32, hi=0.55)}
 
-rank, local_rank, world = ydist.init_from_env()
-torch.cuda.set_device(local_rank)
-eng = get_engine(local_rank)
-eng.load_part1(synth.synth_state_dict("PartI", 0))
-eng.load_part2(synth.synth_state_dict("PartII", 0))
-dev = eng.device
-CFG = {"c3": dict(name="configs[2] shape: 3DMatch-like scene, pair overlap ~U[0.3,0.9], YOHO-C 1000 iterations + YOHO-O", lo=0.55, hi=0.95),
-       "c4": dict(name="configs[3] shape: 3DLoMatch-like scene, pair overlap ~U[0.1,0.3], YOHO-C + YOHO-O 1000 hypotheses", lo=0.32, hi=0.55)}
-for key in (["c3", "c4"] if args.config == "both" else [args.config]):
+
+def _max_over_ranks(v, dev):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return v
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(v, dev):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return v
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def run_scene(eng, key, K=5000, scale=1.0, seed=7):
+    """One timed pass of config `key` over all ranks.  scale < 1 shrinks every scene (and the pair count) proportionally.
+    Returns the result dict (identical on every rank)."""
+    from yoho_b200 import synth, dist as ydist
+    from yoho_b200.pipeline import PairPipeline
+    from yoho_b200.batch import register_scene, plan_scene
     c = CFG[key]
-    t0 = time.time()
-    frags, pair_ids, gts = synth.make_scene(args.fragments, args.kpts, seed=7, overlap_lo=c["lo"], overlap_hi=c["hi"])
-    gen_s = time.time() - t0
-    dfr = {k: (torch.from_numpy(f).to(dev), torch.from_numpy(p).to(dev)) for k, (f, p) in frags.items()}
-    pipe = PairPipeline(eng, seed=1)
-    register_scene(pipe, {k: dfr[k] for k in list(dfr)[:8]}, pair_ids[:8])          # warm-up (one cluster)
+    dev = eng.device
+    sizes = [max(4, int(round(n * scale))) for n in synth.THREEDMATCH_SCENE_SIZES]
+    n_pairs = int(round(c["pairs"] * sum(sizes) / sum(synth.THREEDMATCH_SCENE_SIZES)))
+    S = synth.SceneSet(sizes, n_pairs, K, seed=seed, overlap_lo=c["lo"], overlap_hi=c["hi"])
+    w, rk = ydist.world(), ydist.rank()
+    plan = plan_scene(S.frag_ids, S.pair_ids, w, scene_of=S.scene_of)
+    # this rank's inputs, resident in HBM before the clock starts (generated on the device, seeded per fragment)
+    need = list(dict.fromkeys(plan.frags_of(rk) + [f for i in plan.pairs_of(rk) for f in S.pair_ids[i]]))
+    frs = {f: S.fragment_torch(f, dev) for f in need}
+    # warm-up (no collectives): one cold pair of this rank's own list grows the workspace / allocator pools
+    mine = plan.pairs_of(rk)
+    if mine:
+        a0, b0 = S.pair_ids[mine[0]]
+        PairPipeline(eng, seed=1).register(frs[a0][0], frs[b0][0], frs[a0][1], frs[b0][1], lean=True)
     torch.cuda.synchronize()
+    tim = {}
+    res = register_scene(PairPipeline(eng, seed=1), frs, S.pair_ids, timing=tim, frag_ids=S.frag_ids, scene_of=S.scene_of, plan=plan)
+    ms = _max_over_ranks(tim["total_ms"], dev)
+    T = res.cpu().numpy()
+    ok_c = [S.success(p, T[n, 0]) for n, p in enumerate(S.pair_ids)]
+    ok_o = [S.success(p, T[n, 1]) for n, p in enumerate(S.pair_ids)]
+    out = {"config": c["name"], "n_gpus": w, "fragments": len(S.frag_ids), "scenes": len(sizes), "pairs": len(S.pair_ids), "kpts": K,
+           "seconds": ms / 1e3, "ms_per_pair": ms / len(S.pair_ids),
+           "keypoint_pairs_per_s": len(S.pair_ids) * K / (ms / 1e3), "pairs_per_s": len(S.pair_ids) / (ms / 1e3),
+           "yoho_c_success_rate": float(np.mean(ok_c)), "yoho_o_success_rate": float(np.mean(ok_o)),
+           "plan_balance": plan.balance, "transfers": len(plan.transfers),
+           "exchange": {"collective": "batched NCCL send/recv of (eqv [K,32,60], desc [K,32]) for fragments straddling a cut",
+                        "bytes_total": _sum_over_ranks(float(tim["exchange_bytes_received"]), dev),
+                        "ms_max_rank": _max_over_ranks(tim["exchange_ms"], dev)},
+           "phase_ms_max_rank": {"part1": _max_over_ranks(tim["part1_ms"], dev), "pairs": _max_over_ranks(tim["pairs_ms"], dev)},
+           "scaling": "strong", "data": "synthetic (yoho_b200.synth.SceneSet, generated on the device per fragment)"}
+    return out
+
+
+def run_config5(eng, K=10000, seed=3):
+    """configs[4]: one K-keypoint pair; PartI descriptors of fragment 1 sharded over the ranks, cross-rank mutual 1-NN with one
+    all-gather of packed (distance, index) keys (yoho_b200.dist.sharded_mutual_nn).  Times the matching step on the device."""
+    from yoho_b200 import dist as ydist
+    dev = eng.device
+    w, rk = ydist.world(), ydist.rank()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    dA = torch.randn((K, 32), generator=g, device=dev) * 0.1
+    dB = torch.randn((K, 32), generator=g, device=dev) * 0.1
+    n = int(0.4 * K)
+    perm = torch.randperm(K, generator=g, device=dev)[:n]
+    dB[:n] = dA[perm] + torch.randn((n, 32), generator=g, device=dev) * 0.01
+    bounds = np.linspace(0, K, w + 1).astype(int)
+    lo, hi = int(bounds[rk]), int(bounds[rk + 1])
+    dBl = dB[lo:hi].contiguous()
+    ydist.sharded_mutual_nn(dA, dBl, lo, K, eng.nn1)                # warm-up
+    torch.cuda.synchronize()
+    if w > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        got = ydist.sharded_mutual_nn(dA, dBl, lo, K, eng.nn1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / reps, dev)
+    pairs, cnt = eng.mutual_nn(dA, dB)
+    want = pairs[: int(cnt.item())]
+    return {"config": "configs[4] shape: one %d-keypoint pair, fragment-1 descriptors sharded over the ranks, cross-rank mutual 1-NN" % K,
+            "n_gpus": w, "kpts": K, "matches": int(got.shape[0]), "equals_single_gpu_result": bool(torch.equal(got, want)),
+            "ms_per_match_step": ms, "keypoint_pairs_per_s_matching_only": K / (ms / 1e3),
+            "collective": "all_gather of [Ka] int64 packed (dist,idx) keys (%d B per rank) + all_reduce(MAX) of [Kb] int64" % (8 * K)}
+
+
+def main():
+    from yoho_b200 import synth, dist as ydist
+    from yoho_b200.engine import get_engine
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="all", choices=["c3", "c4", "c5", "all"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--kpts", type=int, default=5000)
+    ap.add_argument("--weights", default="synth", choices=["synth", "real"])
+    args = ap.parse_args()
+    rank, local_rank, world = ydist.init_from_env()
+    torch.cuda.set_device(local_rank)
+    eng = get_engine(local_rank)
+    if args.weights == "real":
+        ck = os.path.join(ROOT, "oracle", "_ref", "ckpt")
+        eng.load_part1(dict(np.load(os.path.join(ck, "PartI.npz"))))
+        eng.load_part2(dict(np.load(os.path.join(ck, "PartII.npz"))))
+    else:
+        eng.load_part1(synth.synth_state_dict("PartI", 0))
+        eng.load_part2(synth.synth_state_dict("PartII", 0))
+    for key in (["c3", "c4", "c5"] if args.config == "all" else [args.config]):
+        r = run_config5(eng, 2 * args.kpts) if key == "c5" else run_scene(eng, key, args.kpts, args.scale)
+        if rank == 0:
+            print(json.dumps(r), flush=True)
     if world > 1:
         torch.distributed.barrier()
-    best = None
-    for rep in range(args.repeat):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tim = {}
-        e0.record()
-        res = register_scene(PairPipeline(eng, seed=1), dfr, pair_ids, timing=tim)
-        e1.record()
-        torch.cuda.synchronize()
-        if best is None or e0.elapsed_time(e1) < best[0]:
-            best = (e0.elapsed_time(e1), tim)
-    ms, tim = best
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
-    T = res.cpu().numpy()
-    ok_c = []
-    for n, pid in enumerate(pair_ids):
-        R, t = gts[pid]
-        cosang = np.clip((np.trace(T[n, 0][:, :3].T @ R) - 1) / 2, -1, 1)
-        ok_c.append(bool(np.degrees(np.arccos(cosang)) < 5.0 and np.linalg.norm(T[n, 0][:, 3] - t) < 0.3))
-    if rank == 0:
-        print(json.dumps({"config": c["name"], "n_gpus": world, "fragments": args.fragments, "pairs": len(pair_ids), "kpts": args.kpts,
-                          "seconds": ms / 1e3, "ms_per_pair": ms / len(pair_ids),
-                          "keypoint_pairs_per_s": len(pair_ids) * args.kpts / (ms / 1e3),
-                          "pairs_per_s": len(pair_ids) / (ms / 1e3),
-                          "yoho_c_success_rate": float(np.mean(ok_c)), "rank0_phases": tim, "timed_passes": args.repeat,
-                          "extrapolated_full_set_seconds": {"3dmatch_433_fragments_1623_pairs" if key == "c3" else "3dlomatch_433_fragments_1781_pairs":
-                                                            ms / 1e3 * ((1623 if key == "c3" else 1781) / len(pair_ids))},
-                          "host_generation_seconds": gen_s, "data": "synthetic (yoho_b200.synth.make_scene)"}), flush=True)
-if world > 1:
-    torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,37 @@ def gather_transforms(T_local):
     return torch.stack(rows) if rows else T_local
 
 
+def gather_rows(rows_local, index_local, n_total):
+    """rows_local [n_local, C] on this rank, index_local = the global row number of each -> [n_total, C] on every rank
+    (the scene driver's result gather: pairs are owned by arbitrary ranks).  Two small all-gathers (padded rows + indices)."""
+    w = world()
+    dev, dt = rows_local.device, rows_local.dtype
+    C = rows_local.shape[1]
+    idx = torch.as_tensor(list(index_local), dtype=torch.int64, device=dev)
+    out = torch.zeros((n_total, C), dtype=dt, device=dev)
+    if w == 1:
+        if idx.numel():
+            out[idx] = rows_local
+        return out
+    n = torch.tensor([idx.numel()], device=dev, dtype=torch.int64)
+    ns = [torch.zeros_like(n) for _ in range(w)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    cap = max(max(ns), 1)
+    buf = torch.zeros((cap, C), device=dev, dtype=dt)
+    ibuf = torch.full((cap,), -1, device=dev, dtype=torch.int64)
+    buf[: idx.numel()] = rows_local
+    ibuf[: idx.numel()] = idx
+    bufs = [torch.zeros_like(buf) for _ in range(w)]
+    ibufs = [torch.zeros_like(ibuf) for _ in range(w)]
+    dist.all_gather(bufs, buf)
+    dist.all_gather(ibufs, ibuf)
+    for r in range(w):
+        if ns[r]:
+            out[ibufs[r][: ns[r]]] = bufs[r][: ns[r]]
+    return out
+
+
 def allgather_sharded(items_local, n_total):
     """Every rank holds the tensors of items r, r+w, r+2w, ... (the `shard` order) of a list of n_total equally shaped
     tensors; returns the full list, in item order, on every rank.  ONE all-gather of the stacked (zero-padded) shards — used

@@ -182,3 +182,102 @@ def make_scene(n_fragments, K, seed=0, cluster=8, overlap_lo=0.55, overlap_hi=0.
                 gts[(fid + i, fid + j)] = (Rij, ti - Rij @ tj)
         fid += n_c
     return fragments, pair_ids, gts
+
+
+# --------------------------------------------------------------------------------------------
+# dataset-shaped scene sets (BASELINE.json configs 3-4), generated fragment by fragment on the device
+# --------------------------------------------------------------------------------------------
+THREEDMATCH_SCENE_SIZES = [60, 60, 60, 55, 57, 37, 66, 38]      # fragments per 3DMatch test scene (utils/dataset.py:167): 433
+
+
+class SceneSet:
+    """Host-side description of a multi-scene set: which scene a fragment belongs to, its planted motion and visible fraction,
+    the pair list (pairs never cross scenes) and the ground truth of every pair.  The tensors themselves are produced per
+    fragment by `fragment_torch` — on whichever rank needs them, bit-identically (seeded device generators) — so a 433-fragment
+    set (16.6 GB of group features) never exists on the host."""
+
+    def __init__(self, sizes, n_pairs, K, seed=0, overlap_lo=0.55, overlap_hi=0.95, sigma=0.05, max_residual_deg=15.0,
+                 kp_noise=0.01, so3_dir=None):
+        gt = _group.load(so3_dir)
+        rs = np.random.RandomState(seed)
+        self.K, self.seed, self.sigma, self.kp_noise = int(K), int(seed), float(sigma), float(kp_noise)
+        self.P = gt.P
+        self.frag_ids, self.scene_of, self.motion, self.rho, self.r = [], {}, {}, {}, {}
+        pairs = []
+        base = 0
+        for s, n in enumerate(sizes):
+            ids = list(range(base, base + n))
+            for f in ids:
+                r = int(rs.randint(0, 60))
+                self.r[f] = r
+                self.motion[f] = (_small_rotation(rs, max_residual_deg) @ gt.R[r], rs.uniform(-1.0, 1.0, 3))
+                self.rho[f] = float(rs.uniform(overlap_lo, overlap_hi))
+                self.scene_of[f] = s
+            self.frag_ids += ids
+            # a fragment overlaps its temporal neighbours ...
+            for i in range(n):
+                for d in (1, 2, 3):
+                    if i + d < n:
+                        pairs.append((ids[i], ids[i + d]))
+            base += n
+        # ... plus loop closures, until the set has the requested number of pairs (3DMatch: 1623, 3DLoMatch: 1781)
+        have = set(pairs)
+        guard = 0
+        while len(pairs) < n_pairs and guard < 100 * n_pairs:
+            guard += 1
+            s = int(rs.randint(len(sizes)))
+            off = int(sum(sizes[:s]))
+            i, j = sorted(int(v) for v in rs.randint(0, sizes[s], 2))
+            if j - i > 3 and (off + i, off + j) not in have:
+                have.add((off + i, off + j))
+                pairs.append((off + i, off + j))
+        self.pair_ids = sorted(pairs[:n_pairs])
+        self.gt = {}
+        for (i, j) in self.pair_ids:
+            Ri, ti = self.motion[i]
+            Rj, tj = self.motion[j]
+            Rij = Ri @ Rj.T                      # pts_i = Ri p + ti, pts_j = Rj p + tj  ->  pts_i = Rij pts_j + (ti - Rij tj)
+            self.gt[(i, j)] = (Rij, ti - Rij @ tj)
+        self._base = {}
+
+    def _scene_base(self, s, device):
+        import torch
+        key = (s, str(device))
+        if key not in self._base:
+            if len(self._base) >= 2:
+                self._base.pop(next(iter(self._base)))
+            g = torch.Generator(device=device)
+            g.manual_seed(self.seed * 1000003 + 7919 * s + 1)
+            f = torch.randn((self.K, 32, 60), generator=g, device=device)
+            f = f / f.norm(dim=1, keepdim=True).clamp_min(1e-12)
+            k = torch.rand((self.K, 3), generator=g, device=device, dtype=torch.float64) * 3.0
+            self._base[key] = (f, k)
+        return self._base[key]
+
+    def fragment_torch(self, fid, device):
+        """-> (feat [K,32,60] f32, kps [K,3] f64) on `device`; the same values on every rank."""
+        import torch
+        K = self.K
+        base_f, base_k = self._scene_base(self.scene_of[fid], device)
+        g = torch.Generator(device=device)
+        g.manual_seed(self.seed * 1000003 + 104729 * (fid + 1))
+        n_ov = int(round(self.rho[fid] * K))
+        src = torch.randperm(K, generator=g, device=device)[:n_ov]
+        dst = torch.randperm(K, generator=g, device=device)[:n_ov]
+        feat = torch.randn((K, 32, 60), generator=g, device=device)
+        feat = feat / feat.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        kps = torch.rand((K, 3), generator=g, device=device, dtype=torch.float64) * 7.0 - 2.0
+        perm = torch.as_tensor(np.asarray(self.P[self.r[fid]], np.int64), device=device)
+        # F(R_r pc)[:, :, g] = F(pc)[:, :, P[r][g]]  (SURVEY.md section 0)
+        v = base_f[src][:, :, perm] + self.sigma * torch.randn((n_ov, 32, 60), generator=g, device=device)
+        feat[dst] = v / v.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        R, t = self.motion[fid]
+        Rt = torch.as_tensor(R, device=device, dtype=torch.float64)
+        tt = torch.as_tensor(t, device=device, dtype=torch.float64)
+        kps[dst] = base_k[src] @ Rt.T + tt + self.kp_noise * torch.randn((n_ov, 3), generator=g, device=device, dtype=torch.float64)
+        return feat.contiguous(), kps.contiguous()
+
+    def success(self, pair, T, max_rot_deg=5.0, max_trans=0.3):
+        R, t = self.gt[pair]
+        cosang = np.clip((np.trace(T[:, :3].T @ R) - 1) / 2, -1, 1)
+        return bool(np.degrees(np.arccos(cosang)) < max_rot_deg and np.linalg.norm(T[:, 3] - t) < max_trans)
