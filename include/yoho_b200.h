@@ -177,7 +177,9 @@ int yoho_gather_kps(yoho_ctx* ctx, const double* kps0, const double* kps1, const
  * (:119-126: categorical bin, then three members WITH replacement) generated on the device from a
  * counter-based Philox4x32-10 stream.  Same distribution as the reference, not the same MT19937 stream;
  * bit-parity runs pass a host-drawn list to yoho_c_ransac instead.
- * status (device int32[1]): 0 ok, 1 = degenerate statistics (reference returns None -> identity, recalltime 50001). */
+ * status (device int32[1]): 0 ok, 1 = degenerate statistics (reference returns None -> identity, recalltime 50001),
+ * 2 = dr_index holds a value outside [0,60) (the reference would raise IndexError, tests/estimator.py:39): no draws are made,
+ * hyp is zero-filled and yoho_register_pair returns the identity like for status 1. */
 int yoho_c_draw(yoho_ctx* ctx, const int64_t* dr_index, int M, int iters, uint64_t seed, int32_t* hyp,
                 int32_t* status, void* stream);
 
@@ -266,6 +268,23 @@ int yoho_fmr_batch(yoho_ctx* ctx, const double* keys0, const double* keys1, cons
  * (RR_cal.py:13-33); rte[n] = translation_error (RR_cal.py:35-46).  A singular gt gives p = NaN. */
 int yoho_registration_errors(yoho_ctx* ctx, const double* est, const double* gt, const double* info, int n, double* p,
                              double* rre_deg, double* rte, void* stream);
+
+/* "Next" row — training-time twins of the hot kernels, FP32, reference layouts ([B,C,60], group axis innermost;
+ * weight [O,C,1,13] and bias [O] as DEVICE pointers in the reference's own layout: they change every optimiser step).
+ * yoho_gconv_train_forward: y[b,o,g] = bias[o] + sum_{c,k} weight[o,c,0,k] x[b,c,N[g][k]] — Comb_Conv's gather + Conv2d(C,O,(1,13))
+ * (utils/network.py:12-21,46-52,80-84) without the 13x gathered tensor; bias may be NULL.
+ * yoho_gconv_train_backward: dx[b,c,j] = sum_{o,k} weight[o,c,0,k] dy[b,o,Ninv_k(j)] (every tap column of N is a permutation of
+ * the group), dweight[o,c,0,k] = sum_{b,g} dy[b,o,g] x[b,c,N[g][k]], dbias[o] = sum_{b,g} dy[b,o,g]; each output may be NULL
+ * (dbias is only written together with dweight).  Deterministic (fixed summation order, no atomics). */
+int yoho_gconv_train_forward(yoho_ctx* ctx, const float* x, const float* weight, const float* bias, int B, int C, int O,
+                             float* y, void* stream);
+int yoho_gconv_train_backward(yoho_ctx* ctx, const float* x, const float* weight, const float* dy, int B, int C, int O,
+                              float* dx, float* dweight, float* dbias, void* stream);
+/* Gradient of the rotation correlation cor[m,a] = sum_{f,g} des1[m,f,P[a][g]] des2[m,f,g] — PartI_train.Des2DR
+ * (utils/network.py:115-118) and Batch_hard_Rindex_loss.eqvloss (train/loss_val.py:27-31); the forward is yoho_rot_argmax's cor_out.
+ * des1, des2, grad_des1, grad_des2 [M,32,60]; grad_cor [M,60]; either gradient may be NULL. */
+int yoho_rot_correlation_backward(yoho_ctx* ctx, const float* des1, const float* des2, const float* grad_cor, int M,
+                                  float* grad_des1, float* grad_des2, void* stream);
 
 /* Launch accounting for bench.py's "gpu_launches": kernels launched by this context since creation. */
 int64_t yoho_launch_count(const yoho_ctx* ctx);

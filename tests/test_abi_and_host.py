@@ -115,7 +115,11 @@ def test_registries_and_checkpoint_keys():
     with pytest.raises(RuntimeError):
         n2.load_state_dict(sd2, strict=True)
     with pytest.raises(NotImplementedError):
-        name2network["PartI_train"](C())
+        name2network["PartII_train"](C())
+    from yoho_b200.train import PartI_train                              # SURVEY.md §8f-4 twin: the reference's keys, strict
+    t1 = name2network["PartI_train"](C())
+    assert isinstance(t1, PartI_train)
+    t1.load_state_dict(synth.to_torch_state_dict(synth.synth_state_dict("PartI", 0)), strict=True)
 
 
 def test_synth_is_reproducible():

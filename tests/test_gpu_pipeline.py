@@ -335,3 +335,56 @@ def test_part2_empty(engine):
     z = np.zeros((0, 32, 60), np.float32)
     q, tr = engine.part2(z, z, z, z, np.zeros((0,), np.int64), kps0=np.zeros((0, 3)), kps1=np.zeros((0, 3)))
     assert tuple(q.shape) == (0, 4) and tuple(tr.shape) == (0, 3, 4)
+
+
+def test_two_modules_with_different_checkpoints_share_one_engine(_engine_session):
+    """weights live in the per-device engine; a module must never silently run with another module's
+    weights.  Two PartI_test instances with different checkpoints, used alternately, and an external Engine.load_part1 in
+    between: every forward returns the result of ITS OWN checkpoint."""
+    from yoho_b200.network import PartI_test
+    a, b = PartI_test(Cfg()).cuda(), PartI_test(Cfg()).cuda()
+    a.load_state_dict(synth.to_torch_state_dict(synth.synth_state_dict('PartI', 0)))
+    b.load_state_dict(synth.to_torch_state_dict(synth.synth_state_dict('PartI', 1)))
+    x = torch.from_numpy(synth.make_fragment(9, 1)[0]).cuda()
+    with torch.no_grad():
+        ea = a(x)['eqv'].clone()
+        eb = b(x)['eqv'].clone()
+        assert (ea - eb).abs().max().item() > 1e-3
+        assert torch.equal(a(x)['eqv'], ea) and torch.equal(b(x)['eqv'], eb) and torch.equal(a(x)['eqv'], ea)
+        _engine_session.load_part1(synth.synth_state_dict('PartI', 2))          # somebody else takes the slot
+        assert torch.equal(b(x)['eqv'], eb) and torch.equal(a(x)['eqv'], ea)
+
+
+def test_host_row_ids_are_range_checked(_engine_session):
+    """match lists / rotation indices that arrive from the host are range-checked like the reference's fancy
+    indexing (IndexError); the device draw kernel reports an out-of-range rotation index instead of corrupting shared memory."""
+    e = _engine_session
+    f = synth.make_fragment(6, 1)[0]
+    with pytest.raises(IndexError):
+        e.rot_argmax(f, f, pairs=np.array([[0, 6]], np.int64))
+    with pytest.raises(IndexError):
+        e.gather_kps(np.zeros((6, 3)), np.zeros((6, 3)), np.array([[-1, 0]], np.int64))
+    with pytest.raises(IndexError):
+        e.c_draw(np.array([1, 2, 60], np.int64), 10, 1)
+    dr = torch.tensor([3, 3, 3, 3, 77, 3], dtype=torch.int64, device=e.device)     # device-resident: reported through status
+    hyp, status = e.c_draw(dr, 16, seed=1)
+    assert int(status.item()) == 2 and int(hyp.abs().sum().item()) == 0
+
+
+def test_knn_module_reference_call_forms(_engine_session):
+    """`find_nn_gpu`'s default distance is the squared one (utils/knn_search.py:26-31) and float64 inputs (the
+    3-D keypoint search of YOHO_testset.py:153-158) keep float64 arithmetic by type promotion."""
+    from yoho_b200.knn_search import knn_module
+    import yoho_oracle as O
+    rs = np.random.RandomState(0)
+    s, t = rs.rand(700, 32).astype(np.float32), rs.rand(333, 32).astype(np.float32)
+    knn = knn_module.KNN(1)
+    d, i = knn.find_nn_gpu(torch.from_numpy(s).cuda(), torch.from_numpy(t).cuda())
+    wd, wi = O.nn1(s, t)
+    assert torch.equal(i, wi) and d.dtype == torch.float32
+    assert np.allclose(d.numpy(), ((s - t[wi.numpy()]) ** 2).sum(1), rtol=1e-5)
+    k64, p32 = rs.rand(500, 3), rs.rand(2000, 3).astype(np.float32)
+    d, i = knn(torch.from_numpy(p32.T.copy())[None].cuda(), torch.from_numpy(k64.T.copy())[None].cuda())
+    assert d.dtype == torch.float64 and tuple(i.shape) == (1, 1, 500)
+    want = np.argmin(((k64[:, None, :] - p32[None].astype(np.float64)) ** 2).sum(-1), 1)
+    assert np.array_equal(i[0, 0].numpy(), want)

@@ -82,6 +82,9 @@ SYMBOLS = {
     "yoho_lift_group_features": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yoho_fmr_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_double, _vp, _vp]),
     "yoho_registration_errors": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "yoho_gconv_train_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "yoho_gconv_train_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "yoho_rot_correlation_backward": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "yoho_launch_count": (ctypes.c_int64, [_vp]),
     "yoho_debug_layer": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "yoho_profile_enable": (_i, [_vp, _i]),

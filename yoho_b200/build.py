@@ -30,6 +30,7 @@ SOURCES = {
     "fourier_mma.cu": [],
     "fourier_tc.cu": [],
     "pair.cu": [],
+    "train.cu": [],
     "estimator.cu": ["-fmad=false"],
     "metrics.cu": ["-fmad=false"],
 }

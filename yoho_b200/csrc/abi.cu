@@ -138,6 +138,7 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
         for (int i = 0; i < yoho_ctx::kPairRing; ++i) cudaEventDestroy(c->pair_ev[i]);
     }
     cudaFree(c->d_rot); cudaFree(c->d_rot32); cudaFree(c->d_perm); cudaFree(c->d_perm_t);
+    cudaFree(c->d_idx_full_inv);
     cudaFree(c->d_idx_full); cudaFree(c->d_idx_p2_init); cudaFree(c->d_idx_p2_a); cudaFree(c->d_idx_p2_b); cudaFree(c->d_idx_one); cudaFree(c->d_idx_ident);
     for (int r = 0; r < 8; ++r) {
         free_layer(c->p1f_a[r]); free_layer(c->p1f_b[r]); free_layer(c->p1f_in[r]); free_layer(c->p1f_out[r]);

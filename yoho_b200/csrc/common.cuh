@@ -61,6 +61,7 @@ struct yoho_ctx {
     uint8_t* d_perm_t = nullptr;    // [60 g][60 a] = P[a][g]
     uint8_t* d_perm = nullptr;      // [60 a][60 g] = P[a][g]
     int* d_idx_full = nullptr;      // [60][13]
+    int* d_idx_full_inv = nullptr;  // [60 j][13 k] = the g with N[g][k] == j (train.cu: backward-data; built on first use)
     int* d_idx_p2_init = nullptr;   // [45][13] -> 60
     int* d_idx_p2_a = nullptr;      // [13][13] -> 45
     int* d_idx_p2_b = nullptr;      // [1][13]  -> 13

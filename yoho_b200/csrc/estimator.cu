@@ -232,19 +232,24 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // E1 + draws.  Single CTA.  members are kept in ascending match order per bin, as the reference's lists.
-__global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict__ dr_index, int M, int iters,
+constexpr int DRAW_T = 512;       // 512 threads: 128 registers per thread, no spills (1024 threads spilled 1 KB per thread, 41 -> ? us)
+__global__ void __launch_bounds__(DRAW_T, 1) c_draw_kernel(const int64_t* __restrict__ dr_index, int M, int iters,
                                                      unsigned long long seed, int32_t* __restrict__ members_ws,
                                                      int32_t* __restrict__ hyp, int32_t* __restrict__ status) {
     __shared__ int cnt[YG];
     __shared__ int off[YG + 1];
     __shared__ double cdf[YG];
-    __shared__ int ok_s;
+    __shared__ int ok_s, bad_s;
     __shared__ uint8_t bins[16384];            // rotation bin of every match (M <= 16384 staged; larger M reads global)
     const int t = threadIdx.x;
     if (t < YG) cnt[t] = 0;
+    if (t == 0) bad_s = 0;
     __syncthreads();
-    for (int m = t; m < M; m += 1024) {
-        const int b = (int)dr_index[m];
+    for (int m = t; m < M; m += DRAW_T) {
+        // a rotation index outside [0,60) (a stale DR_index file) must not corrupt shared memory: clamp, and report status 2
+        const long long raw = dr_index[m];
+        const int b = raw < 0 ? 0 : (raw >= YG ? YG - 1 : (int)raw);
+        if (raw != (long long)b) bad_s = 1;
         if (m < 16384) bins[m] = (uint8_t)b;
         atomicAdd(&cnt[b], 1);
     }
@@ -268,8 +273,8 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
         for (int i = 0; i < YG; ++i) { off[i] = o; o += cnt[i]; tot += w_s[i]; }
         off[YG] = o;
         tot_s = tot;
-        ok_s = !(tot < 1e-4);
-        *status = ok_s ? 0 : 1;
+        ok_s = !(tot < 1e-4) && !bad_s;
+        *status = bad_s ? 2 : (ok_s ? 0 : 1);
     }
     __syncthreads();
     if (ok_s) {
@@ -284,15 +289,15 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
         __syncthreads();
         if (t < YG) cdf[t] = cdf[t] / last_s;
     }
-    // stable bucket fill: warp w owns bins w and w + 32 and walks the matches 32 at a time (ballot + prefix popcount keeps the
+    // stable bucket fill: warp w owns bins w, w + 16, w + 32, w + 48 and walks the matches 32 at a time (ballot + prefix popcount keeps the
     // members of a bin in ascending match order, like the reference's append loop)
     {
         const int warp = t >> 5, lane = t & 31;
-        for (int bin = warp; bin < YG; bin += 32) {
+        for (int bin = warp; bin < YG; bin += DRAW_T / 32) {
             int o = off[bin];
             for (int m0 = 0; m0 < M; m0 += 32) {
                 const int m = m0 + lane;
-                const bool hit = m < M && (m < 16384 ? (int)bins[m] : (int)dr_index[m]) == bin;
+                const bool hit = m < M && (m < 16384 ? (int)bins[m] : (int)dr_index[m]) == bin;   // (status 2 never reaches the draws)
                 const unsigned bal = __ballot_sync(0xffffffffu, hit);
                 if (hit) members_ws[o + __popc(bal & ((1u << lane) - 1u))] = m;
                 o += __popc(bal);
@@ -301,10 +306,10 @@ __global__ void __launch_bounds__(1024) c_draw_kernel(const int64_t* __restrict_
     }
     __syncthreads();
     if (!ok_s) {
-        for (int i = t; i < 3 * iters; i += 1024) hyp[i] = 0;
+        for (int i = t; i < 3 * iters; i += DRAW_T) hyp[i] = 0;
         return;
     }
-    for (int it = t; it < iters; it += 1024) {
+    for (int it = t; it < iters; it += DRAW_T) {
         const uint4 r = philox4x32(make_uint4((unsigned)it, 0u, 0x59484f43u, 0u),
                                    make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
         // 53-bit uniform in [0,1) like random_sample(): (a >> 5, b >> 6)
@@ -366,7 +371,7 @@ extern "C" int yoho_c_draw(yoho_ctx* ctx, const int64_t* dr_index, int M, int it
     YARG(ctx && dr_index && hyp && status && M >= 0 && iters >= 0);
     YCHECK(cudaSetDevice(ctx->device));
     if (int rc = yoho_ws_reserve(ctx, (size_t)(M + 1) * 4)) return rc;
-    c_draw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dr_index, M, iters, seed, (int32_t*)ctx->ws, hyp, status);
+    c_draw_kernel<<<1, DRAW_T, 0, (cudaStream_t)stream>>>(dr_index, M, iters, seed, (int32_t*)ctx->ws, hyp, status);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;

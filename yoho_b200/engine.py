@@ -40,6 +40,12 @@ class PairBuffers:
 
 
 class Engine:
+    """One C-ABI context on one GPU.  Contract (include/yoho_b200.h): a context owns ONE packed weight set per network and ONE
+    grow-only workspace, and its calls are not re-entrant — use it from one thread and one CUDA stream at a time (every method
+    enqueues on the current torch stream).  `get_engine` hands every caller on a device the same Engine, so two torch modules
+    holding different checkpoints share the weight slot: `network.PartI_test / PartII_test` re-upload their own weights
+    whenever `weights_owner` says another caller loaded the slot in between."""
+
     def __init__(self, device=None, so3_dir=None):
         if not torch.cuda.is_available():
             raise _lib.YohoError("yoho_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
@@ -55,6 +61,8 @@ class Engine:
         self.h = h
         self.has_part1 = False
         self.has_part2 = False
+        # who uploaded the weights currently inside the context (several nn.Modules share one engine per device)
+        self.weights_owner = {1: None, 2: None}
         self.impl_name = None
         # group-convolution implementation: tensor cores, PartI layers 2+3 in the group-Fourier domain by default;
         # YOHO_B200_GCONV=simt|tcgen05|tcgen05_split|tcgen05_fourier selects another one
@@ -72,10 +80,11 @@ class Engine:
             pass
 
     # ---- weights -----------------------------------------------------------------------------------
-    def load_part1(self, state_dict, fourier=True):
+    def load_part1(self, state_dict, fourier=True, owner=None):
         w, keep = _lib.part1_struct(state_dict)
         _lib.check(self.lib.yoho_part1_load(self.h, ctypes.byref(w)))
         self.has_part1 = True
+        self.weights_owner[1] = owner
         if fourier:
             self._load_part1_fourier(_lib._to_numpy_sd(state_dict))
 
@@ -106,10 +115,11 @@ class Engine:
         F = np.ascontiguousarray(T["F"], np.float32)
         _lib.check(self.lib.yoho_part1_load_fourier(self.h, F.ctypes.data, n, ctypes.cast(arr, ctypes.c_void_p)))
 
-    def load_part2(self, state_dict):
+    def load_part2(self, state_dict, owner=None):
         w, keep = _lib.part2_struct(state_dict)
         _lib.check(self.lib.yoho_part2_load(self.h, ctypes.byref(w)))
         self.has_part2 = True
+        self.weights_owner[2] = owner
 
     def set_gconv_impl(self, impl):
         self.impl_name = impl
@@ -159,6 +169,20 @@ class Engine:
 
     def _empty(self, shape, dtype):
         return torch.empty(shape, device=self.device, dtype=dtype)
+
+    @staticmethod
+    def _check_rows(pairs, K0, K1, what):
+        """Row ids that arrive from the HOST (the reference's on-disk match lists) are range-checked like the reference's own
+        fancy indexing would (IndexError); device-resident lists produced by this library are trusted."""
+        if isinstance(pairs, np.ndarray) and pairs.size:
+            p = pairs.reshape(-1, 2)
+            if p.min() < 0 or p[:, 0].max() >= K0 or p[:, 1].max() >= K1:
+                raise IndexError(f"{what}: match row out of range for fragments of {K0} / {K1} keypoints")
+
+    @staticmethod
+    def _check_bins(idx, what):
+        if isinstance(idx, np.ndarray) and idx.size and (idx.min() < 0 or idx.max() >= 60):
+            raise IndexError(f"{what}: rotation index outside [0, 60)")
 
     # ---- A: PartI ----------------------------------------------------------------------------------
     def part1(self, x, want_inv=True, want_desc=True):
@@ -214,6 +238,7 @@ class Engine:
         (tests/extractor.py:97-99).  Without pairs the rows are matched one to one."""
         des1, des2 = self._f32(des1), self._f32(des2)
         if pairs is not None:
+            self._check_rows(pairs, des2.shape[0], des1.shape[0], "rot_argmax")
             pairs = self._i64(pairs)
             M = pairs.shape[0]
             r1 = ctypes.c_void_p(pairs.data_ptr() + 8) if M else None
@@ -236,6 +261,9 @@ class Engine:
         """Fragment tensors [K,32,60] + pairs [M,2] (or per-match rows when pairs is None), pre_idx [M]
         -> quat [M,4] f32 and, when keypoints are given, trans [M,3,4] f64."""
         f0, f1, y0, y1 = self._f32(fcgf0), self._f32(fcgf1), self._f32(yoho0), self._f32(yoho1)
+        self._check_bins(pre_idx, "part2")
+        if pairs is not None:
+            self._check_rows(pairs, min(f0.shape[0], y0.shape[0]), min(f1.shape[0], y1.shape[0]), "part2")
         pre = self._i64(pre_idx)
         M = pre.shape[0]
         pr = self._i64(pairs) if pairs is not None else None
@@ -386,6 +414,7 @@ class Engine:
 
     # ---- E: estimators -----------------------------------------------------------------------------
     def gather_kps(self, kps0, kps1, pairs):
+        self._check_rows(pairs, len(kps0), len(kps1), "gather_kps")
         k0, k1, pr = self._f64(kps0), self._f64(kps1), self._i64(pairs)
         M = pr.shape[0]
         o0 = self._empty((M, 3), torch.float64)
@@ -394,6 +423,8 @@ class Engine:
         return o0, o1
 
     def c_draw(self, dr_index, iters, seed):
+        """-> (hyp [iters,3] i32, status i32[1]: 0 ok, 1 degenerate statistics, 2 a rotation index outside [0,60) was seen)."""
+        self._check_bins(dr_index, "c_draw")
         dr = self._i64(dr_index)
         hyp = self._empty((iters, 3), torch.int32)
         status = self._empty((1,), torch.int32)

@@ -8,26 +8,52 @@ import torch
 from .engine import get_engine
 
 
+def _exact_torch_nn(source, target, dist_type, nn_max_n):
+    """The reference's own arithmetic (utils/knn_search.py:17-24,26-66) on the GPU with torch ops, in the dtype the inputs
+    promote to.  Used for what the CUDA kernel does not cover — float64 inputs (the 3-D keypoint search of YOHO_testset.py:153-158
+    keeps float64 keypoints against a float32 cloud: type promotion gives float64 distances) and F > 32 — none of which is on the
+    §8 hot path."""
+    dev = get_engine().device
+    s, t = source.to(dev), target.to(dev)
+    ds, ids = [], []
+    step = nn_max_n if nn_max_n > 1 else max(len(s), 1)
+    for i in range(0, len(s), step):
+        d2 = torch.sum((s[i:i + step].unsqueeze(1) - t.unsqueeze(0)).pow(2), 2)
+        d = torch.sqrt(d2 + 1e-7) if dist_type == 'L2' else d2
+        m, ind = d.min(dim=1)
+        ds.append(m.cpu())
+        ids.append(ind.cpu())
+    return torch.cat(ds), torch.cat(ids)
+
+
 class modified_knn_matcher:
     def __init__(self, k=1):
         self.k = k
 
+    def _nn(self, source, target, dist_type, nn_max_n):
+        if dist_type not in ('L2', 'SquareL2'):
+            raise NotImplementedError('Not implemented')
+        source, target = source.contiguous(), target.contiguous()
+        if source.dtype != torch.float32 or target.dtype != torch.float32 or source.shape[1] > 32:
+            return _exact_torch_nn(source, target, dist_type, nn_max_n)
+        d, idx = get_engine().nn1(source, target)           # sqrt(sum (s-t)^2 + 1e-7), ties -> lowest index
+        if dist_type == 'SquareL2':                          # same argmin; the squared distance itself, as the reference returns it
+            tg = target.to(idx.device)[idx]
+            d = torch.sum((source.to(idx.device) - tg).pow(2), 1)
+        return d.cpu(), idx.cpu()
+
     def __call__(self, target_F, source_F, nn_max_n=500, dist_type='L2'):
         if self.k != 1:
             raise NotImplementedError("yoho_b200 implements the 1-NN search used by the hot path (k=1)")
-        if dist_type != 'L2':
-            raise NotImplementedError('Not implemented')
         # reference: squeeze().T -> [n,f] / [m,f] (utils/knn_search.py:145-146)
         target = target_F.squeeze().T if target_F.dim() == 3 else target_F.T
         source = source_F.squeeze().T if source_F.dim() == 3 else source_F.T
-        d, idx = get_engine().nn1(source.contiguous(), target.contiguous())
-        return d.cpu()[None, None], idx.cpu()[None, None]
+        d, idx = self._nn(source, target, dist_type, nn_max_n)
+        return d[None, None], idx[None, None]
 
-    def find_nn_gpu(self, source_F, target_F, nn_max_n=1000, return_distance=True, dist_type='L2'):
-        if dist_type != 'L2':
-            raise NotImplementedError('yoho_b200 implements the L2 distance the hot path uses')
-        d, idx = get_engine().nn1(source_F.squeeze().contiguous(), target_F.squeeze().contiguous())
-        d, idx = d.cpu(), idx.cpu()
+    def find_nn_gpu(self, source_F, target_F, nn_max_n=1000, return_distance=True, dist_type='SquareL2'):
+        # utils/knn_search.py:26-66 (its default distance is the squared one)
+        d, idx = self._nn(source_F.squeeze(), target_F.squeeze(), dist_type, nn_max_n)
         return (d, idx) if return_distance else idx
 
 

@@ -48,7 +48,7 @@ class _EngineModule(nn.Module):
         self.cfg = cfg
         self._so3 = getattr(cfg, "SO3_related_files", None)
         self._engine = None
-        self._uploaded = False
+        self._token = object()          # identifies THIS module's current weights inside the shared engine
 
     @property
     def engine(self):
@@ -61,17 +61,19 @@ class _EngineModule(nn.Module):
 
     def load_state_dict(self, state_dict, strict=True):
         res = super().load_state_dict(state_dict, strict=strict)
-        self._uploaded = False
+        self._token = object()
         return res
 
     def _ensure_uploaded(self):
-        if not self._uploaded:
+        """The engine (one per device) holds one weight set per network: upload ours unless they are the ones in there.  Another
+        module with a different checkpoint, or a direct Engine.load_part* call, changes the owner and triggers a re-upload here,
+        so two PartI_test instances never silently run with each other's weights (the reference keeps weights per module)."""
+        if self.engine.weights_owner[self._part] is not self._token:
             sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
             if self._part == 1:
-                self.engine.load_part1(sd)
+                self.engine.load_part1(sd, owner=self._token)
             else:
-                self.engine.load_part2(sd)
-            self._uploaded = True
+                self.engine.load_part2(sd, owner=self._token)
 
 
 class PartI_test(_EngineModule):
@@ -120,14 +122,19 @@ def _train_only(name):
     class _Unavailable(nn.Module):
         def __init__(self, cfg):
             super().__init__()
-            raise NotImplementedError(f"{name}: training networks are outside the B200 inference hot path "
+            raise NotImplementedError(f"{name}: the PartII training network is outside the B200 hot path "
                                       "(SURVEY.md §2.1, 'Training' row)")
     _Unavailable.__name__ = name
     return _Unavailable
 
 
+def _part1_train(cfg):
+    from .train import PartI_train          # training-time twin (csrc/train.cu)
+    return PartI_train(cfg)
+
+
 name2network = {
-    "PartI_train": _train_only("PartI_train"),
+    "PartI_train": _part1_train,
     "PartI_test": PartI_test,
     "PartII_train": _train_only("PartII_train"),
     "PartII_test": PartII_test,
