@@ -116,16 +116,17 @@ int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n_irreps, co
 
 /* Implementation of the group-convolution layers: 0 = FP32 SIMT (default), 1 = tcgen05 split-BF16,
  * 2 = tcgen05 split-BF16 with the small (lo) products in a separate TMEM accumulator (shorter rounding chain),
- * 3 = as 2, with PartI layers 2 and 3 — and, when their weights were loaded, layers 1 and 4 — evaluated in the
- * group-Fourier domain (needs yoho_part1_load_fourier). */
+ * 3 = as 2, with all four PartI layers evaluated in the group-Fourier domain (needs yoho_part1_load_fourier with the layer-1/4
+ * weights; otherwise, and for fewer than 128 keypoints, the direct layers of implementation 2 run). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
-/* Tuning knobs (experiments; defaults are the measured best).  key 0 = flag word: 1 = non-blocking producer protocol of the (2: ignored)
- * tensor-core GEMM; 4, 8, 32, 64, 128 = older transform kernels (FP32 SIMT, block-tiled / single-buffered warp-MMA); 16 = one
- * launch per irrep; 256 = tcgen05 transform kernel (default on); 512 = keep PartI layers 1 and 4 as direct convolutions;
- * 1024 = PartII last group convolution as one GEMM instead of five tap-split partial GEMMs; 2048 = PartI output side (inverse
- * transform of the layer-4 coefficients, residual, norms, pools) on the tcgen05 transform machinery, 4096 = the same with
- * shared-memory staged row accesses (both experimental, parity-green, not faster yet: default off). */
+/* Tuning knobs (defaults are the measured best).  key 0 = flag word: 1 = non-blocking producer protocol of the tensor-core GEMM
+ * (2: ignored); 256 = PartI entirely in the group-Fourier domain with the tcgen05 transform kernel (default on; cleared, or with
+ * 512 set, implementation 3 runs the direct 13-tap tensor-core layers of implementation 2); 1024 = PartII last group convolution
+ * as one GEMM instead of five tap-split partial GEMMs; 2048 = PartI output side (inverse transform of the layer-4 coefficients,
+ * residual, norms, pools) on the tcgen05 transform machinery, 4096 = the same with shared-memory staged row accesses (both
+ * parity-green, not faster: default off); 8192 = FP32 SIMT input / output side of the all-Fourier PartI instead of the register-resident
+ * warp-MMA kernels (test twin).  The warp-MMA / SIMT transform kernels of round 1 (flags 4-128) were removed. */
 int yoho_set_tuning(yoho_ctx* ctx, int key, int value);
 
 /* A1-A6 — PartI_test.forward (utils/network.py:86-105,140-147) on B keypoints.

@@ -75,7 +75,8 @@ def test_part1_tc_vs_oracle(engine, tables, K, impl):
         engine.set_gconv_impl("simt")
     s = engine.part1(x)
     ref = O.part1_forward(x[:400], sd, N)
-    _report(f"part1 K={K} {impl} vs simt", _np(o["eqv"]), _np(s["eqv"]))
+    e_all, _ = _report(f"part1 K={K} {impl} vs simt", _np(o["eqv"]), _np(s["eqv"]))
+    assert e_all <= 1e-4 - 2e-5                       # ALL rows: SIMT is within 2e-5 of the oracle (test_gpu_parity), so this bounds every row
     err, _ = _report(f"part1 K={K} {impl} vs oracle", _np(o["eqv"])[:400], ref["eqv"].numpy())
     assert err <= DESC_TOL
     assert np.abs(_np(o["inv"])[:400] - ref["inv"].numpy()).max() <= DESC_TOL
@@ -150,32 +151,19 @@ def test_part2_tc_realckpt(engine, tables, impl):
     assert err <= DESC_TOL
 
 
-def test_fourier_transform_kernels_agree(engine, tables):
-    """The tcgen05 transform kernel (default, flag 256) against the warp-autonomous MMA transform kernel (flags 3), its FP32
-    SIMT twin (flag 4) and the block-tiled MMA variants (flags 8, 32, 64, 128), through the whole PartI."""
+def test_fourier_path_variants_agree(engine, tables):
+    """The default PartI (all four layers in the group-Fourier domain, tcgen05 transform kernel) against the direct tensor-core
+    layers (flag 512: implementation 3 falls back to the 13-tap gather-GEMMs), the FP32 SIMT path and the tensor-core output side
+    (flag 2048), all against the oracle."""
     _, _, N = tables
     sd = synth.synth_state_dict("PartI", 2)
     engine.load_part1(sd)
     x, _ = synth.make_fragment(300, 41)
     engine.set_gconv_impl("tcgen05_fourier")
     try:
-        engine.set_tuning(0, 3)
-        a = engine.part1(x)
-        engine.set_tuning(0, 3 | 4)
-        b = engine.part1(x)
-        engine.set_tuning(0, 3 | 8)          # 128-channel block-tiled transform: same arithmetic, different tiling
-        c = engine.part1(x)
-        engine.set_tuning(0, 3 | 32)         # 64-channel block-tiled transform
-        c2 = engine.part1(x)
-        engine.set_tuning(0, 3 | 16)         # one launch per irrep instead of the grouped launch
-        d = engine.part1(x)
-        engine.set_tuning(0, 3 | 64)         # 16 single-buffered warps per CTA
-        e = engine.part1(x)
-        engine.set_tuning(0, 3 | 128)        # 12 single-buffered warps per CTA
-        f = engine.part1(x)
-        engine.set_tuning(0, 3 | 256)        # the default: tcgen05 transform kernel, all four layers in the Fourier domain
+        engine.set_tuning(0, 3 | 256)        # the default
         g = engine.part1(x)
-        engine.set_tuning(0, 3 | 256 | 512)  # tcgen05 transform kernel, layers 1 and 4 as direct convolutions
+        engine.set_tuning(0, 3 | 256 | 512)  # direct 13-tap tensor-core layers
         h = engine.part1(x)
         engine.set_tuning(0, 3 | 256 | 2048)  # all-Fourier with the output side (inverse transform, norms, pools) on tensor cores
         k2 = engine.part1(x)
@@ -183,21 +171,16 @@ def test_fourier_transform_kernels_agree(engine, tables):
     finally:
         engine.set_tuning(0, engine.DEFAULT_TUNING)
         engine.set_gconv_impl("simt")
+    s_ = engine.part1(x)
     ref = O.part1_forward(x, sd, N)
-    _report("fourier mma-xf vs simt-xf", _np(a["eqv"]), _np(b["eqv"]))
-    e1, _ = _report("fourier mma-xf vs oracle", _np(a["eqv"]), ref["eqv"].numpy())
-    e2, _ = _report("fourier simt-xf vs oracle", _np(b["eqv"]), ref["eqv"].numpy())
-    e3, _ = _report("fourier tcgen05-xf vs oracle", _np(g["eqv"]), ref["eqv"].numpy())
-    e4, _ = _report("fourier tcgen05-xf (layers 2+3) vs mma-xf", _np(h["eqv"]), _np(a["eqv"]))
-    e5, _ = _report("all-Fourier vs oracle", _np(g["eqv"]), ref["eqv"].numpy())
-    _report("all-Fourier inv vs oracle", _np(g["inv"]), ref["inv"].numpy())
-    e6, _ = _report("tcgen05-xf (layers 2+3) vs oracle", _np(h["eqv"]), ref["eqv"].numpy())
-    assert e1 <= DESC_TOL and e2 <= DESC_TOL and e3 <= DESC_TOL and e4 <= 2e-5 and e5 <= DESC_TOL and e6 <= DESC_TOL
+    e3, _ = _report("all-Fourier vs oracle", _np(g["eqv"]), ref["eqv"].numpy())
+    e4, _ = _report("all-Fourier vs direct tensor-core layers", _np(g["eqv"]), _np(h["eqv"]))
+    e5, _ = _report("all-Fourier vs FP32 SIMT", _np(g["eqv"]), _np(s_["eqv"]))
+    e6, _ = _report("direct tensor-core layers vs oracle", _np(h["eqv"]), ref["eqv"].numpy())
+    assert e3 <= DESC_TOL and e4 <= 5e-5 and e5 <= 5e-5 and e6 <= DESC_TOL
     assert float(np.abs(_np(g["inv"]) - ref["inv"].numpy()).max()) <= DESC_TOL
     e7, _ = _report("all-Fourier, tensor-core output side vs oracle", _np(k2["eqv"]), ref["eqv"].numpy())
     e8, _ = _report("all-Fourier, tensor-core output side vs SIMT output side", _np(k2["eqv"]), _np(g["eqv"]))
     assert e7 <= DESC_TOL and e8 <= 2e-5
     assert float(np.abs(_np(k2["inv"]) - ref["inv"].numpy()).max()) <= DESC_TOL
     assert float(np.abs(_np(k2["desc"]) - _np(g["desc"])).max()) <= 2e-5
-    assert torch.equal(a["eqv"], c["eqv"]) and torch.equal(a["eqv"], c2["eqv"]) and torch.equal(a["eqv"], d["eqv"])
-    assert torch.equal(a["eqv"], e["eqv"]) and torch.equal(a["eqv"], f["eqv"])

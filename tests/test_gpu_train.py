@@ -87,10 +87,59 @@ def test_rot_correlation_and_des2dr(_engine_session, tables):
     assert torch.equal(Des2DR(torch.from_numpy(a).to(dev), torch.from_numpy(y).to(dev)).cpu(), torch.arange(37) % 60)
 
 
+def _train_inputs():
+    pr = synth.make_fragment_pair(24, seed=9, overlap=1.0, sigma=0.1)
+    f0, f1 = pr["feat_B"][pr["ids_B"]], pr["feat_A"][pr["ids_A"]]
+    return f0, f1, np.full((24,), pr["r"], np.int64)
+
+
+def test_every_backward_call_of_a_real_training_step(_engine_session, tables):
+    """One training-mode step of PartI_train + Batch_hard_Rindex_loss on the CUDA kernels; every group-convolution backward call
+    inside it (8 calls: 4 layers x 2 branches, real activations and real upstream gradients) is re-derived with float64 torch
+    autograd from the SAME inputs: dx and dweight within 2e-5 of their own scale.  (This is the discontinuity-free statement; the
+    end-to-end comparison below has to tolerate ReLU-mask flips.)"""
+    from yoho_b200 import train as T
+    _, _, N = tables
+    dev = _engine_session.device
+    calls = []
+    orig = T._GroupConv.backward
+
+    def spy(ctx, dy):
+        out = orig(ctx, dy)
+        x, w = ctx.saved_tensors
+        calls.append((x.detach().clone(), w.detach().clone(), dy.detach().clone(), [None if o is None else o.detach().clone() for o in out]))
+        return out
+    T._GroupConv.backward = staticmethod(spy)
+    try:
+        m = T.PartI_train(None).to(dev)
+        m.load_state_dict(synth.to_torch_state_dict(synth.synth_state_dict("PartI", 4)), strict=True)
+        m.train()
+        f0, f1, ti = _train_inputs()
+        out = m({"feats0": torch.from_numpy(f0).to(dev), "feats1": torch.from_numpy(f1).to(dev), "true_idx": torch.from_numpy(ti).to(dev)})
+        T.Batch_hard_Rindex_loss()(out).backward()
+        torch.cuda.synchronize()
+    finally:
+        T._GroupConv.backward = staticmethod(orig)
+    assert len(calls) == 8
+    for x, w, dy, (dx, dw, db) in calls:
+        xr, wr = x.double().cpu().requires_grad_(True), w.double().cpu().requires_grad_(True)
+        torch.nn.functional.conv2d(O.gather13(xr, N), wr)[:, :, :, 0].backward(dy.double().cpu())
+        if dx is not None:
+            assert _rel(dx.double().cpu(), xr.grad) <= 2e-5
+        assert _rel(dw.double().cpu(), wr.grad) <= 2e-5
+        # a conv bias in front of a training-mode BatchNorm has zero gradient: compare on the scale of the terms that cancel
+        want_b = dy.double().cpu().sum((0, 2))
+        assert float((db.double().cpu() - want_b).abs().max()) <= 2e-5 * float(dy.double().abs().sum((0, 2)).max())
+
+
 def test_part1_train_step_matches_reference_modules(_engine_session, tables):
     """PartI_train + Batch_hard_Rindex_loss, one forward / backward in TRAINING mode (BatchNorm batch statistics), against the
-    unmodified reference modules (utils/network.py:106-138, train/loss_val.py:20-56) on the CPU in float64: same loss, same
-    gradient for every parameter.  The reference's checkpoint keys load with strict=True."""
+    unmodified reference modules (utils/network.py:106-138, train/loss_val.py:20-56) in float64: same loss, same rotation
+    indices, same gradients.  The reference's checkpoint keys load with strict=True.
+    ReLU makes the gradient a discontinuous function of the forward values: a pre-activation within FP32 rounding of zero takes
+    the other sub-gradient and changes one row of the preceding layer's weight gradient by a visible amount (measured here: the
+    same happens between torch's own FP32 and FP64 runs when a flip occurs).  So the end-to-end bar is: median error 1e-5 of the
+    tensor's scale, 97 % of the entries within 2e-4, relative L2 error 3e-2; the per-call test above is the tight one."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_shim
     if not ref_shim.available():
@@ -104,14 +153,11 @@ def test_part1_train_step_matches_reference_modules(_engine_session, tables):
     ours = T.PartI_train(None).to(dev)
     ours.load_state_dict(sd, strict=True)
     ours.train()
-    # the reference's modules call .cuda() on their tables; run them on the GPU too, in float64 for the arbiter
     theirs = ref.network.PartI_train(ref.cfgI)
     theirs.load_state_dict(sd, strict=True)
     theirs = theirs.double().cuda()
     theirs.train()
-    pr = synth.make_fragment_pair(24, seed=9, overlap=1.0, sigma=0.1)
-    f0, f1 = pr["feat_B"][pr["ids_B"]], pr["feat_A"][pr["ids_A"]]
-    true_idx = np.full((24,), pr["r"], np.int64)
+    f0, f1, true_idx = _train_inputs()
     d32 = {"feats0": torch.from_numpy(f0).to(dev), "feats1": torch.from_numpy(f1).to(dev), "true_idx": torch.from_numpy(true_idx).to(dev)}
     d64 = {"feats0": torch.from_numpy(f0).double().cuda(), "feats1": torch.from_numpy(f1).double().cuda(), "true_idx": torch.from_numpy(true_idx).cuda()}
     out = ours(d32)
@@ -120,9 +166,19 @@ def test_part1_train_step_matches_reference_modules(_engine_session, tables):
     rout = theirs(d64)
     rloss = loss_mod.Batch_hard_Rindex_loss(ref.cfgI)(rout)
     rloss.backward()
-    assert abs(float(loss) - float(rloss)) <= 1e-4 * max(1.0, abs(float(rloss)))
+    assert abs(float(loss.detach()) - float(rloss.detach())) <= 2e-6 * max(1.0, abs(float(rloss.detach())))
     assert torch.equal(out["DR_pre_index"].cpu(), rout["DR_pre_index"].cpu())
+    for k in ("feats0_eqv_af_conv", "feats1_eqv_af_conv", "feats0_inv", "feats1_inv"):
+        assert float((out[k].detach().double() - rout[k].detach()).abs().max()) <= 1e-5
     rp = dict(theirs.named_parameters())
     for name, p in ours.named_parameters():
         assert p.grad is not None, name
-        assert _rel(p.grad.double().cpu(), rp[name].grad.cpu()) <= 2e-3, name
+        a, b = p.grad.double().cpu(), rp[name].grad.cpu()
+        scale = float(b.abs().max())
+        if scale < 1e-12:                           # conv bias in front of a training-mode BatchNorm: exactly zero in exact arithmetic
+            assert float(a.abs().max()) <= 1e-6, name
+            continue
+        d = (a - b).abs()
+        assert float(d.median()) <= 1e-5 * scale, name
+        assert float((d > 2e-4 * scale).double().mean()) <= 0.03, name
+        assert float((a - b).norm() / b.norm()) <= 3e-2, name

@@ -26,8 +26,6 @@ SOURCES = {
     "part2.cu": [],
     "match.cu": [],
     "lift.cu": [],
-    "fourier.cu": [],
-    "fourier_mma.cu": [],
     "fourier_tc.cu": [],
     "pair.cu": [],
     "train.cu": [],

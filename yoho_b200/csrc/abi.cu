@@ -144,7 +144,7 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
         free_layer(c->p1f_a[r]); free_layer(c->p1f_b[r]); free_layer(c->p1f_in[r]); free_layer(c->p1f_out[r]);
         cudaFree(c->d_fidx[r]); cudaFree(c->d_fomap[r]); cudaFree(c->d_fomap_out[r]);
     }
-    cudaFree(c->d_Fg2m); cudaFree(c->d_Fm2g); cudaFree(c->d_F); cudaFree(c->d_p1_bias31);
+    cudaFree(c->d_F); cudaFree(c->d_p1_bias31);
     cudaFree(c->d_fwd_hi); cudaFree(c->d_fwd_lo); cudaFree(c->d_inv_hi); cudaFree(c->d_inv_lo);
     cudaFree(c->ws);
     delete c;
@@ -229,18 +229,13 @@ extern "C" int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n
         cudaFree(ctx->d_fidx[r]); cudaFree(ctx->d_fomap[r]); cudaFree(ctx->d_fomap_out[r]);
         ctx->d_fidx[r] = ctx->d_fomap[r] = ctx->d_fomap_out[r] = nullptr;
     }
-    cudaFree(ctx->d_Fg2m); cudaFree(ctx->d_Fm2g); cudaFree(ctx->d_F);
-    ctx->d_Fg2m = ctx->d_Fm2g = ctx->d_F = nullptr;
+    cudaFree(ctx->d_F);
+    ctx->d_F = nullptr;
     {
         std::vector<float> Fv(F_host, F_host + YG * YG);
         if (int rc0 = upload(&ctx->d_F, Fv)) return rc0;
     }
-    std::vector<float> g2m(YG * 64, 0.f), m2g(YG * 64, 0.f);
-    for (int m = 0; m < YG; ++m)
-        for (int g = 0; g < YG; ++g) { g2m[g * 64 + m] = F_host[m * YG + g]; m2g[m * 64 + g] = F_host[m * YG + g]; }
     int rc = 0;
-    if ((rc = upload(&ctx->d_Fg2m, g2m))) return rc;
-    if ((rc = upload(&ctx->d_Fm2g, m2g))) return rc;
     {   // bf16 hi/lo copies with the OUTPUT index as the row: forward[m][g] = F[m][g], inverse[g][m] = F[m][g]
         auto f2bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7FFFu + ((u >> 16) & 1u); return (unsigned short)(u >> 16); };
         auto bf2f = [](unsigned short h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; };

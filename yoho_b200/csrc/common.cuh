@@ -53,7 +53,7 @@ struct yoho_ctx {
     int device = 0;
     int num_sms = 148;
     int gconv_impl = 0;
-    int tc_flags = 3 | 256;         // tuning flags: bit0 noinc producers (gconv_tc.cu; bit1 is ignored); 256 = tcgen05 transform kernel (fourier_tc.cu)
+    int tc_flags = 3 | 256;         // tuning flags (include/yoho_b200.h yoho_set_tuning): bit0 noinc producers (gconv_tc.cu; bit1 ignored); 256 = all-Fourier PartI with the tcgen05 transform kernel (fourier_tc.cu)
     int64_t launches = 0;
     // group tables on the device
     double* d_rot = nullptr;        // [60][9] f64
@@ -87,9 +87,7 @@ struct yoho_ctx {
     int* d_fomap_out[8] = {nullptr};
     float* d_p1_bias31 = nullptr;   // [256] bias of layer 3 + bias of layer 1 (the shortcut's bias, added in the group domain)
     float* d_F = nullptr;           // [60 m][60 g] FP32 (input transform and the finalize kernel's inverse transform)
-    float* d_Fg2m = nullptr;        // [60][64]: Fg2m[g][m] = F[m][g]   (forward transform as M1[k=g][m])
-    float* d_Fm2g = nullptr;        // [60][64]: Fm2g[m][g] = F[m][g]   (inverse transform as M1[k=m][g])
-    // the same two matrices for the mma.sync transform kernel: [64 out][64 in] bf16 hi/lo (row = OUTPUT index)
+    // forward / inverse transform matrices for the tcgen05 transform kernel: [64 out][64 in] bf16 hi/lo (row = OUTPUT index)
     void* d_fwd_hi = nullptr; void* d_fwd_lo = nullptr;     // forward: rows m (coefficient), cols g
     void* d_inv_hi = nullptr; void* d_inv_lo = nullptr;     // inverse: rows g, cols m
     // PartII

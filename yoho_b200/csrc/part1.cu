@@ -9,13 +9,7 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
-// fourier.cu / abi.cu
-int group_transform(yoho_ctx* ctx, const float* in, int B, int C, const float* m1, const float* m2, const float* bias,
-                    const float* resid, const float* scale, const float* shift, void* out_hi, void* out_lo, float* out_f32,
-                    cudaStream_t st);
-int group_transform_mma(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
-                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
-                        void* out_hi, void* out_lo, cudaStream_t st);
+// fourier_tc.cu / gconv_tc.cu / abi.cu
 int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
                        const void* m2_lo, const float* bias, const float* resid, const float* scale, const float* shift,
                        void* out_hi, void* out_lo, cudaStream_t st, const void* in2_hi, const void* in2_lo);
@@ -260,6 +254,188 @@ __global__ void __launch_bounds__(128) part1_finalize_fourier_kernel(const float
     }
 }
 
+// ---- warp-MMA input / output side (default) -------------------------------------------------------------------------------------
+// Both sides are 64 x 64 x 32 products per keypoint against the CONSTANT transform matrix, far too small for a tcgen05 tile but
+// shared-memory-wavefront bound as SIMT code (61 / 84 us per 5000 keypoints against a 12 us HBM floor).  Here the matrix lives in
+// registers as mma.sync A fragments (bf16 hi and lo, one 16-row tile per warp) for the whole kernel, the per-keypoint operand is
+// read from global memory straight into B fragments (FP32 -> bf16 hi/lo split in registers: no shared-memory staging at all),
+// and D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulates in FP32 (the same three-product scheme as the tensor-core GEMMs).
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {           // low half = a
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragments (hi, lo) of the 16-row tile `rt` of the 64 x 64 (zero-padded) matrix M[r][k] = transposed ? F[k][r] : F[r][k].
+__device__ __forceinline__ void load_matrix_frags(const float* __restrict__ F, bool transposed, int rt, int lane,
+                                                  uint32_t (&ah)[4][4], uint32_t (&al)[4][4]) {
+    const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = 16 * rt + gid + ((i & 1) ? 8 : 0);
+            const int k = 16 * t + 2 * tig + ((i & 2) ? 8 : 0);
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int kk = k + e;
+                v[e] = (r < YG && kk < YG) ? __ldg(F + (transposed ? kk * YG + r : r * YG + kk)) : 0.f;
+            }
+            split2(v[0], v[1], ah[t][i], al[t][i]);
+        }
+}
+
+// X0[b][m][c] (bf16 hi / lo) = sum_g F[m][g] x[b][c][g].  CTA = 4 warps = the four 16-row tiles of m; CTAs stride over keypoints.
+// Column n of n-tile j carries channel 8*(n/2) + 2*j + (n%2), so that a thread's eight results of a row are eight CONSECUTIVE
+// channels: one 16-byte store per row for hi and one for lo.
+__global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ F,
+                                                            unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    uint32_t ah[4][4], al[4][4];
+    load_matrix_frags(F, false, w, lane, ah, al);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* xb = x + (size_t)b * YF * YG;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* xc = xb + (8 * (gid >> 1) + 2 * j + (gid & 1)) * YG;      // channel of column n = gid of n-tile j
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int g0 = 16 * t + 2 * tig;
+                const float2 v0 = *reinterpret_cast<const float2*>(xc + g0);               // g0 <= 54: always valid
+                float2 v1 = make_float2(0.f, 0.f);
+                if (g0 + 8 < YG) v1 = *reinterpret_cast<const float2*>(xc + g0 + 8);        // 60 is even: the pair is valid together
+                uint32_t bh0, bl0, bh1, bl1;
+                split2(v0.x, v0.y, bh0, bl0);
+                split2(v1.x, v1.y, bh1, bl1);
+                mma_bf16(acc[j], ah[t], bh0, bh1);
+                mma_bf16(acc[j], al[t], bh0, bh1);
+                mma_bf16(acc[j], ah[t], bl0, bl1);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = 16 * w + gid + 8 * h;
+            if (m < YG) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split2(acc[j][2 * h], acc[j][2 * h + 1], ph[j], pl[j]);
+                const size_t o = ((size_t)b * YG + m) * YF + 8 * tig;
+                *reinterpret_cast<uint4*>(hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+        }
+    }
+}
+
+// Output side: e[c][g] = bias4[c] + sum_m F[m][g] Y4[b][m][c] + x[b][c][g], then the tail of PartI_network.forward
+// (utils/network.py:98-103) and the matcher's numpy mean (tests/matcher.py:35).  Warp w owns the group elements 16w .. 16w+15.
+__global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
+                                                                const float* __restrict__ bias4, const float* __restrict__ x,
+                                                                float* __restrict__ eqv, float* __restrict__ inv,
+                                                                float* __restrict__ desc, int B) {
+    __shared__ float es[YF][YG + 1];
+    __shared__ float part[4][YF];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    uint32_t ah[4][4], al[4][4];
+    load_matrix_frags(F, true, w, lane, ah, al);                  // A[g][m] = F[m][g]
+    float bias[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bias[j][0] = __ldg(bias4 + 8 * j + 2 * tig); bias[j][1] = __ldg(bias4 + 8 * j + 2 * tig + 1); }
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* yb = y4f + (size_t)b * YG * YF;
+        const float* xb = x + (size_t)b * YF * YG;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int m0 = 16 * t + 2 * tig;                       // coefficient rows m0, m0+1 and m0+8, m0+9
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* p = yb + 8 * j + gid;                 // column n = gid of n-tile j is channel 8j + gid (8 lanes = one 32-byte sector)
+                const float v00 = p[m0 * YF], v01 = p[(m0 + 1) * YF];
+                float v10 = 0.f, v11 = 0.f;
+                if (m0 + 8 < YG) { v10 = p[(m0 + 8) * YF]; v11 = p[(m0 + 9) * YF]; }
+                uint32_t bh0, bl0, bh1, bl1;
+                split2(v00, v01, bh0, bl0);
+                split2(v10, v11, bh1, bl1);
+                mma_bf16(acc[j], ah[t], bh0, bh1);
+                mma_bf16(acc[j], al[t], bh0, bh1);
+                mma_bf16(acc[j], ah[t], bl0, bl1);
+            }
+        }
+        // thread: group elements g = 16w + gid (+8), channels c = 8j + 2 tig + {0,1}
+        float e[2][8], ss[2] = {0.f, 0.f}, cs[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int g = 16 * w + gid + 8 * h;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int c = 8 * j + 2 * tig + i;
+                    const float v = g < YG ? (acc[j][2 * h + i] + bias[j][i]) + xb[c * YG + g] : 0.f;
+                    e[h][2 * j + i] = v;
+                    ss[h] = fmaf(v, v, ss[h]);
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cs[k] = e[0][k] + e[1][k];    // invariant pooling uses the UN-normalised e (utils/network.py:99 precedes :102)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], 1);
+            ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+        }
+        __syncthreads();                                           // previous keypoint done with es / part
+        if (gid == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) part[w][8 * (k >> 1) + 2 * tig + (k & 1)] = cs[k];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int g = 16 * w + gid + 8 * h;
+            if (g < YG) {
+                const float nrm = fmaxf(sqrtf(ss[h]), 1e-4f);      // torch.clamp_min(torch.norm(eqv, dim=1), 1e-4)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) es[8 * (k >> 1) + 2 * tig + (k & 1)][g] = e[h][k] / nrm;
+            }
+        }
+        __syncthreads();
+        float* out = eqv + (size_t)b * YF * YG;
+        for (int i = threadIdx.x; i < YF * YG; i += 128) out[i] = es[i / YG][i % YG];
+        if (w == 0) {
+            if (desc) desc[(size_t)b * YF + lane] = numpy_mean60(&es[lane][0], 1);
+        } else if (w == 1 && inv) {
+            const float m = (((part[0][lane] + part[1][lane]) + part[2][lane]) + part[3][lane]) / 60.0f;
+            float q = m * m;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            inv[(size_t)b * YF + lane] = m / fmaxf(sqrtf(q), 1e-4f);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(64) group_mean_kernel(const float* __restrict__ eqv, float* __restrict__ desc, int K) {
     __shared__ float e[YF][YG + 1];
     const int b = blockIdx.x;
@@ -286,8 +462,9 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
     const bool tc_on = ctx->gconv_impl >= 1 && ctx->p1_in.w_hi && ctx->p1_a.w_hi && ctx->p1_b.w_hi && ctx->p1_out.w_hi;
     // per keypoint: xt 32, y1 256, a1 256 (fp32, or bf16 hi+lo = same bytes), a2 512 (same), a3 256, y4 32 floats x 60
     const bool fourier_on = tc_on && ctx->gconv_impl == 3 && ctx->has_p1f;
-    // group-Fourier path adds: a1 fp32 (256), X1 hi|lo (256), Y2 fp32 (512), X2 hi|lo (512), Y3 fp32 (256)
-    const size_t per_kp = (size_t)YG * ((32 + 256 + 256 + 512 + 256 + 512) + (fourier_on ? (256 + 256 + 512 + 512 + 256) : 0)) * sizeof(float);
+    // group-Fourier path: X0 32, Y1 256, X1 256, Y2 512, X2 512, Y3 256, X3 256 (bf16 hi|lo pairs = fp32 bytes), Y4 32
+    const size_t direct_f = 32 + 256 + 256 + 512 + 256 + 512, fourier_f = 32 + 256 + 256 + 512 + 512 + 256 + 256 + 32;
+    const size_t per_kp = (size_t)YG * (fourier_on && fourier_f > direct_f ? fourier_f : direct_f) * sizeof(float);
     const int n_chunks = (B + P1_CHUNK - 1) / P1_CHUNK;
     const int chunk = n_chunks > 0 ? (B + n_chunks - 1) / n_chunks : 0;      // balanced passes
     if (int rc = yoho_ws_reserve(ctx, per_kp * (size_t)chunk)) return rc;
@@ -312,7 +489,7 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         const float* xs = x + (size_t)s * YF * YG;
         // ---- the whole stack in the group-Fourier domain: per-irrep GEMMs for all four layers, transforms only
         // at the three BatchNorm/ReLU points, shortcut added as Fourier coefficients.  Needs the tcgen05 transform kernel.
-        if (fourier_on && ctx->has_p1f_io && n >= 128 && (ctx->tc_flags & 256) && !(ctx->tc_flags & (4 | 16 | 512))) {
+        if (fourier_on && ctx->has_p1f_io && n >= 128 && (ctx->tc_flags & 256) && !(ctx->tc_flags & 512)) {
             const size_t R = (size_t)n * YG;
             unsigned short* w16 = (unsigned short*)ctx->ws;
             unsigned short* X0h = w16;            unsigned short* X0l = X0h + R * 32;
@@ -323,8 +500,10 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             unsigned short* Y3h = X2l + R * 512;  unsigned short* Y3l = Y3h + R * 256;
             unsigned short* X3h = Y3l + R * 256;  unsigned short* X3l = X3h + R * 256;
             float* Y4 = (float*)(X3l + R * 256);
-            const int sgrid = n < 8 * ctx->num_sms ? n : 8 * ctx->num_sms;      // keypoint-striding CTAs, F resident in shared memory
-            fourier_in_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
+            const bool simt_io = (ctx->tc_flags & 8192) != 0;                    // test twin: FP32 SIMT input / output side
+            const int sgrid = n < 8 * ctx->num_sms ? n : 8 * ctx->num_sms;      // keypoint-striding CTAs, transform matrix resident on chip
+            if (simt_io) fourier_in_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
+            else fourier_in_mma_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
             ctx->launches++;
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
@@ -371,9 +550,14 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             } else {
             if (int rc = layer(ctx->p1f_out, X3h, X3l, nullptr, nullptr, Y4, 32, true)) return rc;
             const int fgrid = n < 6 * ctx->num_sms ? n : 6 * ctx->num_sms;
-            part1_finalize_fourier_kernel<<<fgrid, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
-                                                                  inv ? inv + (size_t)s * YF : nullptr,
-                                                                  desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
+            if (simt_io)
+                part1_finalize_fourier_kernel<<<fgrid, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+                                                                      inv ? inv + (size_t)s * YF : nullptr,
+                                                                      desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
+            else
+                part1_finalize_mma_kernel<<<sgrid, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+                                                                 inv ? inv + (size_t)s * YF : nullptr,
+                                                                 desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
             ctx->launches++;
             }
             continue;
@@ -386,67 +570,8 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         a.resid = nullptr; a.out_raw = y1;
         a.scale = ctx->p1_bn_a.scale; a.shift = ctx->p1_bn_a.shift;
         if (tc) { a.act_hi = xt_hi; a.act_lo = xt_lo; a.out_hi = a1_hi; a.out_lo = a1_lo; } else { a.act = xt; a.out_act = a1; }
-        if (fourier_on && n >= 128 && (ctx->tc_flags & 4)) { a.out_hi = a.out_lo = nullptr; a.out_act = y4 + (size_t)n * YG * 512; }   // FP32 a1 for the SIMT transform
         if (int rc = gconv_forward(ctx, ctx->p1_in, a, st)) return rc;
         a.out_act = nullptr;
-        const bool fourier = fourier_on && n >= 128;
-        if (fourier) {
-            // ---- layers 2 and 3 in the group-Fourier domain (yoho_b200/fourier.py) ----
-            // Every tensor between the kernels is a bf16 hi/lo pair (same bytes as FP32): the GEMMs consume it directly
-            // and the warp-MMA transform kernel streams it into its operand tiles with cp.async.  The FP32 SIMT transform
-            // kernel (tuning flag 4, kept as the reference twin) takes FP32 instead.
-            const bool xmma = (ctx->tc_flags & 4) == 0;
-            float* fa1 = y4 + (size_t)n * YG * 512;                 // FP32 a1 (SIMT transform path only)
-            unsigned short* X1h = (unsigned short*)(fa1 + (size_t)n * YG * 256);
-            unsigned short* X1l = X1h + (size_t)n * YG * 256;
-            float* Y2 = (float*)(X1l + (size_t)n * YG * 256);
-            unsigned short* Y2h = (unsigned short*)Y2;
-            unsigned short* Y2l = Y2h + (size_t)n * YG * 512;
-            unsigned short* X2h = (unsigned short*)(Y2 + (size_t)n * YG * 512);
-            unsigned short* X2l = X2h + (size_t)n * YG * 512;
-            float* Y3 = (float*)(X2l + (size_t)n * YG * 512);
-            unsigned short* Y3h = (unsigned short*)Y3;
-            unsigned short* Y3l = Y3h + (size_t)n * YG * 256;
-            yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
-            if (int rc = xmma ? group_transform_mma(ctx, a1_hi, a1_lo, n, 256, ctx->d_fwd_hi, ctx->d_fwd_lo, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, st)
-                              : group_transform(ctx, fa1, n, 256, ctx->d_Fg2m, nullptr, nullptr, nullptr, nullptr, nullptr, X1h, X1l, nullptr, st)) return rc;
-            yoho_prof_end(ctx, st);
-            GConvArgs f{};
-            f.B = n; f.Jin = YG; f.out_J = YG;
-            const bool grouped = (ctx->tc_flags & 16) == 0 && ctx->nf <= 5;   // all irreps of a layer in one persistent launch
-            GConvArgs fs[8];
-            const GLayer* Ls[8];
-            for (int q = 0; q < ctx->nf; ++q) {
-                const int r = ctx->nf - 1 - q;                               // largest irrep first: short tiles make up the tail
-                f.act_hi = X1h; f.act_lo = X1l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
-                f.omap = ctx->d_fomap[r]; f.ogroup = 512;
-                if (xmma) { f.out_raw = nullptr; f.out_hi = Y2h; f.out_lo = Y2l; } else { f.out_raw = Y2; f.out_hi = f.out_lo = nullptr; }
-                fs[q] = f; Ls[q] = &ctx->p1f_a[r];
-                if (!grouped) { if (int rc = gconv_forward(ctx, ctx->p1f_a[r], f, st)) return rc; }
-            }
-            if (grouped) { if (int rc = gconv_forward_grouped(ctx, Ls, fs, ctx->nf, st)) return rc; }
-            yoho_prof_begin(ctx, 8, 2.0 * n * 512 * 7200.0, st);
-            if (int rc = xmma ? group_transform_mma(ctx, Y2h, Y2l, n, 512, ctx->d_inv_hi, ctx->d_inv_lo, ctx->d_fwd_hi, ctx->d_fwd_lo, ctx->p1_a.bias, nullptr,
-                                                    ctx->p1_bn_b.scale, ctx->p1_bn_b.shift, X2h, X2l, st)
-                              : group_transform(ctx, Y2, n, 512, ctx->d_Fm2g, ctx->d_Fg2m, ctx->p1_a.bias, nullptr, ctx->p1_bn_b.scale,
-                                                ctx->p1_bn_b.shift, X2h, X2l, nullptr, st)) return rc;
-            yoho_prof_end(ctx, st);
-            for (int q = 0; q < ctx->nf; ++q) {
-                const int r = ctx->nf - 1 - q;
-                f.act_hi = X2h; f.act_lo = X2l; f.idx = ctx->d_fidx[r]; f.Jout = ctx->fd[r];
-                f.omap = ctx->d_fomap[r]; f.ogroup = 256;
-                if (xmma) { f.out_raw = nullptr; f.out_hi = Y3h; f.out_lo = Y3l; } else { f.out_raw = Y3; f.out_hi = f.out_lo = nullptr; }
-                fs[q] = f; Ls[q] = &ctx->p1f_b[r];
-                if (!grouped) { if (int rc = gconv_forward(ctx, ctx->p1f_b[r], f, st)) return rc; }
-            }
-            if (grouped) { if (int rc = gconv_forward_grouped(ctx, Ls, fs, ctx->nf, st)) return rc; }
-            yoho_prof_begin(ctx, 8, 2.0 * n * 256 * 3600.0, st);
-            if (int rc = xmma ? group_transform_mma(ctx, Y3h, Y3l, n, 256, ctx->d_inv_hi, ctx->d_inv_lo, nullptr, nullptr, ctx->p1_b.bias, y1,
-                                                    ctx->p1_bn_out.scale, ctx->p1_bn_out.shift, a3_hi, a3_lo, st)
-                              : group_transform(ctx, Y3, n, 256, ctx->d_Fm2g, nullptr, ctx->p1_b.bias, y1, ctx->p1_bn_out.scale,
-                                                ctx->p1_bn_out.shift, a3_hi, a3_lo, nullptr, st)) return rc;
-            yoho_prof_end(ctx, st);
-        } else {
         // layer 2: a2 = relu(BN_b(GC_a(a1)))
         a.out_raw = nullptr;
         a.scale = ctx->p1_bn_b.scale; a.shift = ctx->p1_bn_b.shift;
@@ -457,7 +582,6 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
         a.scale = ctx->p1_bn_out.scale; a.shift = ctx->p1_bn_out.shift;
         if (tc) { a.act_hi = a2_hi; a.act_lo = a2_lo; a.out_hi = a3_hi; a.out_lo = a3_lo; } else { a.act = a2; a.out_act = a3; }
         if (int rc = gconv_forward(ctx, ctx->p1_b, a, st)) return rc;
-        }
         // layer 4: y4 = GC_out(a3).  Tensor-core path: one dense GEMM Z = a3 . W_cat [256 x 13*32] (a3 is read once, not
         // 13 times); the 13-tap gather-add happens on the 100 KB Z tile of each keypoint inside the finalize kernel.
         a.resid = nullptr; a.out_raw = y4; a.out_act = nullptr; a.out_hi = a.out_lo = nullptr; a.scale = a.shift = nullptr;
