@@ -26,4 +26,13 @@ for _ in range(passes):
     eng.part1(xd, want_inv=False, want_desc=True)
 torch.cuda.synchronize()
 pr = eng.profile_read()
-print(f"part1 {K} kpts x{passes}: " + ", ".join(f"{q['name']}={q['ms'] / passes:.3f}" for q in pr if q["launches"]))
+eng.profile(False)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+reps = 10
+e0.record()
+for _ in range(reps):
+    eng.part1(xd, want_inv=False, want_desc=True)
+e1.record()
+torch.cuda.synchronize()
+print(f"part1 {K} kpts x{passes}: " + ", ".join(f"{q['name']}={q['ms'] / passes:.3f}" for q in pr if q["launches"])
+      + f" | whole PartI {e0.elapsed_time(e1) / reps:.3f} ms (mean of {reps}, back to back)")

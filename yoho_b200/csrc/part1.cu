@@ -8,6 +8,7 @@
 //   e = y4 + x0 ; inv = normalise(mean_g e) ; eqv = e / max(||e||_c, 1e-4) ; desc = mean_g eqv (:98-103, tests/matcher.py:35)
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "tcgen05.cuh"      // mbarrier / 1-D TMA bulk-copy helpers
 
 // fourier_tc.cu / gconv_tc.cu / abi.cu
 int group_transform_tc(yoho_ctx* ctx, const void* in_hi, const void* in_lo, int B, int C, const void* m1_hi, const void* m1_lo, const void* m2_hi,
@@ -294,15 +295,31 @@ __device__ __forceinline__ void load_matrix_frags(const float* __restrict__ F, b
 }
 
 // X0[b][m][c] (bf16 hi / lo) = sum_g F[m][g] x[b][c][g].  CTA = 4 warps = the four 16-row tiles of m; CTAs stride over keypoints.
-// Column n of n-tile j carries channel 8*(n/2) + 2*j + (n%2), so that a thread's eight results of a row are eight CONSECUTIVE
-// channels: one 16-byte store per row for hi and one for lo.
+// The 7 680-byte [32][60] tile of a keypoint arrives by ONE 1-D TMA bulk copy into a ring of IN_ST shared-memory stages, issued
+// IN_ST keypoints ahead by one thread (mbarrier complete_tx), so the loads of the next keypoints are in flight while this one is
+// multiplied: the register-fed first version (B fragments straight from global memory) was latency bound at 52 us.
+constexpr int IN_ST = 4;
 __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ F,
                                                             unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
+    __shared__ __align__(128) float xs[IN_ST][YF * YG];
+    __shared__ __align__(8) unsigned long long full[IN_ST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const int n_mine = blockIdx.x < B ? (B - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < IN_ST; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+        for (int s = 0; s < IN_ST && s < n_mine; ++s) {
+            mbar_expect_tx(&full[s], YF * YG * 4);
+            bulk_g2s(&xs[s][0], x + (size_t)(blockIdx.x + (size_t)s * gridDim.x) * YF * YG, YF * YG * 4, &full[s]);
+        }
+    }
     uint32_t ah[4][4], al[4][4];
     load_matrix_frags(F, false, w, lane, ah, al);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const float* xb = x + (size_t)b * YF * YG;
+    __syncthreads();                                               // barrier initialisation visible to the waiters
+    for (int it = 0; it < n_mine; ++it) {
+        const int b = blockIdx.x + it * gridDim.x, s = it % IN_ST;
+        mbar_wait(&full[s], (it / IN_ST) & 1);
+        const float* xb = &xs[s][0];
         float acc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -310,7 +327,7 @@ __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __rest
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float* xc = xb + (8 * (gid >> 1) + 2 * j + (gid & 1)) * YG;      // channel of column n = gid of n-tile j
+            const float* xc = xb + (8 * j + gid) * YG;             // column n = gid of n-tile j is channel 8j + gid
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int g0 = 16 * t + 2 * tig;
@@ -325,16 +342,24 @@ __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __rest
                 mma_bf16(acc[j], ah[t], bl0, bl1);
             }
         }
+        __syncthreads();                                           // every warp has read stage s: refill it IN_ST keypoints ahead
+        if (threadIdx.x == 0 && it + IN_ST < n_mine) {
+            mbar_expect_tx(&full[s], YF * YG * 4);
+            bulk_g2s(&xs[s][0], x + (size_t)(b + (size_t)IN_ST * gridDim.x) * YF * YG, YF * YG * 4, &full[s]);
+        }
+        // thread: rows m = 16w + gid (+8), channels 8j + 2 tig + {0,1}: one bf16 pair (4 bytes) per n-tile, hi and lo
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int m = 16 * w + gid + 8 * h;
             if (m < YG) {
-                uint32_t ph[4], pl[4];
+                const size_t o = ((size_t)b * YG + m) * YF + 2 * tig;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) split2(acc[j][2 * h], acc[j][2 * h + 1], ph[j], pl[j]);
-                const size_t o = ((size_t)b * YG + m) * YF + 8 * tig;
-                *reinterpret_cast<uint4*>(hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t ph, pl;
+                    split2(acc[j][2 * h], acc[j][2 * h + 1], ph, pl);
+                    *reinterpret_cast<uint32_t*>(hi + o + 8 * j) = ph;
+                    *reinterpret_cast<uint32_t*>(lo + o + 8 * j) = pl;
+                }
             }
         }
     }
@@ -342,21 +367,49 @@ __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __rest
 
 // Output side: e[c][g] = bias4[c] + sum_m F[m][g] Y4[b][m][c] + x[b][c][g], then the tail of PartI_network.forward
 // (utils/network.py:98-103) and the matcher's numpy mean (tests/matcher.py:35).  Warp w owns the group elements 16w .. 16w+15.
+// Both tiles of a keypoint (Y4 coefficients and x) are prefetched by TMA bulk copies into a two-stage ring: Y4 row by row
+// (60 x 128 B, by the lanes of warp 0) into rows padded to 36 floats so that the B-fragment reads are bank-conflict free.
+constexpr int FIN_ST = 2;
+constexpr int FIN_PITCH = 36;
 __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
                                                                 const float* __restrict__ bias4, const float* __restrict__ x,
                                                                 float* __restrict__ eqv, float* __restrict__ inv,
                                                                 float* __restrict__ desc, int B) {
+    __shared__ __align__(128) float ys[FIN_ST][YG * FIN_PITCH];
+    __shared__ __align__(128) float xs[FIN_ST][YF * YG];
     __shared__ float es[YF][YG + 1];
     __shared__ float part[4][YF];
+    __shared__ __align__(8) unsigned long long full[FIN_ST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const int n_mine = blockIdx.x < B ? (B - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    auto prefetch = [&](int it) {                                  // called by all lanes of warp 0
+        const int s = it % FIN_ST;
+        const size_t b = blockIdx.x + (size_t)it * gridDim.x;
+        if (lane == 0) {
+            mbar_expect_tx(&full[s], 2 * YF * YG * 4);
+            bulk_g2s(&xs[s][0], x + b * YF * YG, YF * YG * 4, &full[s]);
+        }
+        __syncwarp();                                              // expect_tx is posted before any row copy can complete
+        for (int m = lane; m < YG; m += 32) bulk_g2s(&ys[s][m * FIN_PITCH], y4f + (b * YG + m) * YF, YF * 4, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FIN_ST; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
     uint32_t ah[4][4], al[4][4];
     load_matrix_frags(F, true, w, lane, ah, al);                  // A[g][m] = F[m][g]
     float bias[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { bias[j][0] = __ldg(bias4 + 8 * j + 2 * tig); bias[j][1] = __ldg(bias4 + 8 * j + 2 * tig + 1); }
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const float* yb = y4f + (size_t)b * YG * YF;
-        const float* xb = x + (size_t)b * YF * YG;
+    __syncthreads();
+    if (w == 0)
+        for (int it = 0; it < FIN_ST && it < n_mine; ++it) prefetch(it);
+    for (int it = 0; it < n_mine; ++it) {
+        const size_t b = blockIdx.x + (size_t)it * gridDim.x;
+        const int s = it % FIN_ST;
+        mbar_wait(&full[s], (it / FIN_ST) & 1);
+        const float* yb = &ys[s][0];
+        const float* xb = &xs[s][0];
         float acc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -367,10 +420,10 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
             const int m0 = 16 * t + 2 * tig;                       // coefficient rows m0, m0+1 and m0+8, m0+9
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float* p = yb + 8 * j + gid;                 // column n = gid of n-tile j is channel 8j + gid (8 lanes = one 32-byte sector)
-                const float v00 = p[m0 * YF], v01 = p[(m0 + 1) * YF];
+                const float* p = yb + 8 * j + gid;                 // column n = gid of n-tile j is channel 8j + gid
+                const float v00 = p[m0 * FIN_PITCH], v01 = p[(m0 + 1) * FIN_PITCH];
                 float v10 = 0.f, v11 = 0.f;
-                if (m0 + 8 < YG) { v10 = p[(m0 + 8) * YF]; v11 = p[(m0 + 9) * YF]; }
+                if (m0 + 8 < YG) { v10 = p[(m0 + 8) * FIN_PITCH]; v11 = p[(m0 + 9) * FIN_PITCH]; }
                 uint32_t bh0, bl0, bh1, bl1;
                 split2(v00, v01, bh0, bl0);
                 split2(v10, v11, bh1, bl1);
@@ -407,7 +460,8 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
             cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
             cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
         }
-        __syncthreads();                                           // previous keypoint done with es / part
+        __syncthreads();                                           // previous keypoint done with es / part; everyone done with stage s
+        if (w == 0 && it + FIN_ST < n_mine) prefetch(it + FIN_ST);
         if (gid == 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) part[w][8 * (k >> 1) + 2 * tig + (k & 1)] = cs[k];
@@ -422,16 +476,16 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
             }
         }
         __syncthreads();
-        float* out = eqv + (size_t)b * YF * YG;
+        float* out = eqv + b * YF * YG;
         for (int i = threadIdx.x; i < YF * YG; i += 128) out[i] = es[i / YG][i % YG];
-        if (w == 0) {
-            if (desc) desc[(size_t)b * YF + lane] = numpy_mean60(&es[lane][0], 1);
+        if (w == 2) {
+            if (desc) desc[b * YF + lane] = numpy_mean60(&es[lane][0], 1);
         } else if (w == 1 && inv) {
             const float m = (((part[0][lane] + part[1][lane]) + part[2][lane]) + part[3][lane]) / 60.0f;
             float q = m * m;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            inv[(size_t)b * YF + lane] = m / fmaxf(sqrtf(q), 1e-4f);
+            inv[b * YF + lane] = m / fmaxf(sqrtf(q), 1e-4f);
         }
     }
 }
@@ -502,8 +556,18 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
             float* Y4 = (float*)(X3l + R * 256);
             const bool simt_io = (ctx->tc_flags & 8192) != 0;                    // test twin: FP32 SIMT input / output side
             const int sgrid = n < 8 * ctx->num_sms ? n : 8 * ctx->num_sms;      // keypoint-striding CTAs, transform matrix resident on chip
+            // the warp-MMA kernels are persistent: exactly one wave of resident CTAs (the TMA ring of a CTA prefetches ITS next keypoints)
+            static int occ_in = 0, occ_fin = 0;
+            if (!occ_in) {
+                YCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_in, fourier_in_mma_kernel, 128, 0));
+                YCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fin, part1_finalize_mma_kernel, 128, 0));
+                if (occ_in < 1) occ_in = 1;
+                if (occ_fin < 1) occ_fin = 1;
+            }
+            const int grid_in = n < occ_in * ctx->num_sms ? n : occ_in * ctx->num_sms;
+            const int grid_fin = n < occ_fin * ctx->num_sms ? n : occ_fin * ctx->num_sms;
             if (simt_io) fourier_in_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
-            else fourier_in_mma_kernel<<<sgrid, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
+            else fourier_in_mma_kernel<<<grid_in, 128, 0, st>>>(xs, ctx->d_F, X0h, X0l, n);
             ctx->launches++;
             GConvArgs f{};
             f.B = n; f.Jin = YG; f.out_J = YG;
@@ -555,7 +619,7 @@ extern "C" int yoho_part1_forward(yoho_ctx* ctx, const float* x, int B, float* e
                                                                       inv ? inv + (size_t)s * YF : nullptr,
                                                                       desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
             else
-                part1_finalize_mma_kernel<<<sgrid, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
+                part1_finalize_mma_kernel<<<grid_fin, 128, 0, st>>>(Y4, ctx->d_F, ctx->p1_out.bias, xs, eqv + (size_t)s * YF * YG,
                                                                  inv ? inv + (size_t)s * YF : nullptr,
                                                                  desc_mean ? desc_mean + (size_t)s * YF : nullptr, n);
             ctx->launches++;
