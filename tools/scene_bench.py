@@ -80,7 +80,9 @@ def run_scene(eng, key, K=5000, scale=1.0, seed=7):
            "plan_balance": plan.balance, "transfers": len(plan.transfers),
            "exchange": {"collective": "batched NCCL send/recv of (eqv [K,32,60], desc [K,32]) for fragments straddling a cut",
                         "bytes_total": _sum_over_ranks(float(tim["exchange_bytes_received"]), dev),
-                        "ms_max_rank": _max_over_ranks(tim["exchange_ms"], dev)},
+                        "stall_ms_max_rank": _max_over_ranks(tim["exchange_stall_ms"], dev),
+                        "note": "posted right after the owner computed the straddling fragments; stall = time the compute stream of "
+                                "a rank waited for receives after finishing its all-local pairs"},
            "phase_ms_max_rank": {"part1": _max_over_ranks(tim["part1_ms"], dev), "pairs": _max_over_ranks(tim["pairs_ms"], dev)},
            "scaling": "strong", "data": "synthetic (yoho_b200.synth.SceneSet, generated on the device per fragment)"}
     return out

@@ -10,7 +10,9 @@ The reference runs PartI once per FRAGMENT (tests/extractor.py:46-47) and everyt
   phase 1  PartI once per fragment on its owner.
   exchange the PartI outputs (eqv [K,32,60] + matcher descriptor [K,32]) of exactly those straddling fragments travel
            owner -> user with one batched NCCL send/recv group.  No all-gather: a scene-aware cut moves a few fragments per
-           cut instead of landing every fragment on every rank (433 x 38.4 MB = 16.6 GB per rank for config 3).
+           cut instead of landing every fragment on every rank (433 x 38.4 MB = 16.6 GB per rank for config 3).  The owner
+           computes those fragments FIRST and posts the group at once; it progresses on NCCL's stream behind the rest of
+           phase 1 and the all-local pairs of phase 2, and only the straddling pairs wait for it.
   phase 2  every rank registers its pairs from the cached PartI outputs with the split-phase pair call (pair i+1's matching is
            queued before the host waits for pair i's match count).
   gather   one tiny all-gather of the [n_pairs, 2, 3, 4] float64 transforms.
@@ -100,12 +102,13 @@ def plan_scene(frag_ids, pair_ids, world, scene_of=None, frag_cost=FRAG_COST_MS,
     return ScenePlan(owner_f, owner_p, order, transfers, cost, comp)
 
 
-def exchange_part1(plan, local, template, device, rank=None):
-    """Send / receive the PartI outputs of the fragments of `plan.transfers` that involve this rank.
-    local: {fid: (eqv, desc)} of the owned fragments; template(fid) -> K (rows of that fragment, known from its inputs).
-    Returns ({fid: (eqv, desc)} received, bytes received).  One batched isend/irecv group (NCCL over NVLink on the box)."""
+def exchange_part1_start(plan, local, template, device, rank=None):
+    """Post the sends / receives of the PartI outputs of the fragments of `plan.transfers` that involve this rank.
+    local: {fid: (eqv, desc)} holding at least the fragments this rank SENDS; template(fid) -> K (rows of that fragment).
+    Returns ({fid: (eqv, desc)} receive buffers, requests, bytes to receive).  One batched isend/irecv group (NCCL over NVLink on
+    the box): it progresses on NCCL's own stream while the caller keeps computing; `req.wait()` before touching the buffers."""
     rank = ydist.rank() if rank is None else rank
-    ops, got, keep = [], {}, []
+    ops, got = [], {}
     nbytes = 0
     for s, d, f in plan.transfers:
         if s == rank:
@@ -120,9 +123,15 @@ def exchange_part1(plan, local, template, device, rank=None):
             ops.append(tdist.P2POp(tdist.irecv, ds, s))
             got[f] = (e, ds)
             nbytes += e.numel() * 4 + ds.numel() * 4
-    if ops:
-        for req in tdist.batch_isend_irecv(ops):
-            req.wait()
+    reqs = tdist.batch_isend_irecv(ops) if ops else []
+    return got, reqs, nbytes
+
+
+def exchange_part1(plan, local, template, device, rank=None):
+    """Blocking form of `exchange_part1_start`: returns ({fid: (eqv, desc)} received, bytes received)."""
+    got, reqs, nbytes = exchange_part1_start(plan, local, template, device, rank)
+    for req in reqs:
+        req.wait()
     return got, nbytes
 
 
@@ -146,60 +155,76 @@ def register_scene(pipe: PairPipeline, fragments, pair_ids, timing=None, frag_id
     for f in touched:                                   # inputs resident before the clock starts (like bench.py's `value`)
         feat, kps = load(f)
         inputs[f] = (eng._f32(feat), eng._f64(kps))
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing is not None else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timing is not None else None
     if ev:
         torch.cuda.synchronize()
         if w > 1:
             tdist.barrier()
         ev[0].record()
-    # phase 1: PartI once per fragment, on its owner (tests/extractor.py:46-47)
+    # phase 1: PartI once per fragment, on its owner (tests/extractor.py:46-47) — the fragments other ranks are waiting for first,
+    # so that their transfer is posted early and travels (NCCL's own stream) behind the rest of this rank's work
     cache = {}
-    for f in my_frags:
+    outgoing = list(dict.fromkeys(f for s_, d_, f in plan.transfers if s_ == rk))
+    incoming = {f for s_, d_, f in plan.transfers if d_ == rk}
+
+    def part1(f):
         o = eng.part1(inputs[f][0], want_inv=False, want_desc=True)
         cache[f] = (o["eqv"], o["desc"])
+    for f in outgoing:
+        part1(f)
+    reqs, nbytes, got = [], 0, {}
+    if w > 1 and plan.transfers:
+        got, reqs, nbytes = exchange_part1_start(plan, cache, lambda f: inputs[f][0].shape[0], dev, rk)
+    for f in my_frags:
+        if f not in cache:
+            part1(f)
     if ev:
         ev[1].record()
-    # exchange: only the fragments that pairs straddling a cut need
-    nbytes = 0
-    if w > 1 and plan.transfers:
-        got, nbytes = exchange_part1(plan, cache, lambda f: inputs[f][0].shape[0], dev, rk)
-        cache.update(got)
+    # phase 2: everything else once per pair; the hypothesis draws are seeded by the pair's position in `pair_ids`, so the
+    # result does not depend on the sharding.  Pairs whose fragments are all local run first; the others after the receives.
+    out = torch.zeros((len(my_pairs), 2, 3, 4), dtype=torch.float64, device=dev)
+    order = [n for n, pi in enumerate(my_pairs) if not (set(pair_ids[pi]) & incoming)]
+    late = [n for n, pi in enumerate(my_pairs) if set(pair_ids[pi]) & incoming]
+    pend = []
+
+    def finish(tok_n):
+        tok, n = tok_n
+        t = eng.register_pair_end(tok)
+        out[n] = t["T_co"]
+
+    def run(ns):
+        for n in ns:
+            pi = my_pairs[n]
+            a, b = pair_ids[pi]
+            if pipe.fused:
+                tok = eng.register_pair_begin(inputs[a][0], inputs[b][0], inputs[a][1], inputs[b][1], pipe.c_iters, pipe.o_iters,
+                                              pipe.c_dist, pipe.o_dist, pipe.seed + 1 + pi, eqvA=cache[a][0], eqvB=cache[b][0],
+                                              descA=cache[a][1], descB=cache[b][1])
+                pend.append((tok, n))
+                if len(pend) > 1:                       # pair i+1's matching is queued before the host waits for pair i's count
+                    finish(pend.pop(0))
+            else:
+                r = pipe.register(inputs[a][0], inputs[b][0], inputs[a][1], inputs[b][1], eqvA=cache[a][0], eqvB=cache[b][0],
+                                  descA=cache[a][1], descB=cache[b][1], seed=pipe.seed + 1 + pi)
+                out[n, 0], out[n, 1] = r["T_c"], r["T_o"]
+    run(order)
     if ev:
         ev[2].record()
-    # phase 2: everything else once per pair; the hypothesis draws are seeded by the pair's position in `pair_ids`, so the
-    # result does not depend on the sharding
-    out = torch.zeros((len(my_pairs), 2, 3, 4), dtype=torch.float64, device=dev)
-    if pipe.fused:
-        LOOK = 1
-        pend = []
-
-        def finish(tok_n):
-            tok, n = tok_n
-            t = eng.register_pair_end(tok)
-            out[n] = t["T_co"]
-        for n, pi in enumerate(my_pairs):
-            a, b = pair_ids[pi]
-            tok = eng.register_pair_begin(inputs[a][0], inputs[b][0], inputs[a][1], inputs[b][1], pipe.c_iters, pipe.o_iters,
-                                          pipe.c_dist, pipe.o_dist, pipe.seed + 1 + pi, eqvA=cache[a][0], eqvB=cache[b][0],
-                                          descA=cache[a][1], descB=cache[b][1])
-            pend.append((tok, n))
-            if len(pend) > LOOK:
-                finish(pend.pop(0))
-        while pend:
-            finish(pend.pop(0))
-    else:
-        for n, pi in enumerate(my_pairs):
-            a, b = pair_ids[pi]
-            r = pipe.register(inputs[a][0], inputs[b][0], inputs[a][1], inputs[b][1], eqvA=cache[a][0], eqvB=cache[b][0],
-                              descA=cache[a][1], descB=cache[b][1], seed=pipe.seed + 1 + pi)
-            out[n, 0], out[n, 1] = r["T_c"], r["T_o"]
+    for req in reqs:                                    # the compute stream now waits for whatever has not landed yet
+        req.wait()
+    cache.update(got)
     if ev:
         ev[3].record()
+    run(late)
+    while pend:
+        finish(pend.pop(0))
+    if ev:
+        ev[4].record()
         torch.cuda.synchronize()
-        timing.update(part1_ms=ev[0].elapsed_time(ev[1]), exchange_ms=ev[1].elapsed_time(ev[2]), pairs_ms=ev[2].elapsed_time(ev[3]),
-                      total_ms=ev[0].elapsed_time(ev[3]), fragments_owned=len(my_frags), fragments_touched=len(touched),
-                      pairs=len(my_pairs), exchange_bytes_received=int(nbytes), transfers_total=len(plan.transfers),
-                      plan_balance=plan.balance)
+        timing.update(part1_ms=ev[0].elapsed_time(ev[1]), pairs_ms=ev[1].elapsed_time(ev[2]) + ev[3].elapsed_time(ev[4]),
+                      exchange_stall_ms=ev[2].elapsed_time(ev[3]), total_ms=ev[0].elapsed_time(ev[4]), fragments_owned=len(my_frags),
+                      fragments_touched=len(touched), pairs=len(my_pairs), pairs_after_exchange=len(late),
+                      exchange_bytes_received=int(nbytes), transfers_total=len(plan.transfers), plan_balance=plan.balance)
     if w == 1:
         full = torch.zeros((len(pair_ids), 2, 3, 4), dtype=torch.float64, device=dev)
         if my_pairs:

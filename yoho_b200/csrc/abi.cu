@@ -128,10 +128,10 @@ extern "C" int yoho_ctx_destroy(yoho_ctx* c) {
     if (!c) return YOHO_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p1_out_cat, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3,
+    GLayer* layers[] = {&c->p1_in, &c->p1_a, &c->p1_b, &c->p1_out, &c->p1_out_cat, &c->p2_init, &c->p2_a, &c->p2_b, &c->p2_fc1, &c->p2_fc2, &c->p2_fc3, &c->p2_fc2_pad,
                         &c->p2_b_split[0], &c->p2_b_split[1], &c->p2_b_split[2], &c->p2_b_split[3], &c->p2_b_split[4]};
     for (GLayer* l : layers) free_layer(*l);
-    GBn* bns[] = {&c->p1_bn_a, &c->p1_bn_b, &c->p1_bn_out, &c->p2_bn_init, &c->p2_bn_a, &c->p2_bn_b, &c->p2_bn1, &c->p2_bn2};
+    GBn* bns[] = {&c->p1_bn_a, &c->p1_bn_b, &c->p1_bn_out, &c->p2_bn_init, &c->p2_bn_a, &c->p2_bn_b, &c->p2_bn1, &c->p2_bn2, &c->p2_bn2_pad};
     for (GBn* b : bns) free_bn(*b);
     if (c->pair_M_pinned) {
         cudaFreeHost(c->pair_M_pinned);
@@ -337,6 +337,31 @@ extern "C" int yoho_part2_load(yoho_ctx* ctx, const yoho_part2_weights* w) {
     if ((rc = pack_bn(ctx->p2_bn1, w->bn1, 512))) return rc;
     if ((rc = pack_conv(ctx, ctx->p2_fc2, w->fc2, 512, 128, 1))) return rc;
     if ((rc = pack_bn(ctx->p2_bn2, w->bn2, 128))) return rc;
+    {   // the two hidden 1x1 layers of PartII_To_R_FC as dense tensor-core GEMMs (one tap): 256 -> 512, and 512 -> 128 zero-padded
+        // to one 256-column tile (n_valid = 128 at the call)
+        std::vector<float> w1((size_t)256 * 512);
+        for (int o = 0; o < 512; ++o)
+            for (int c = 0; c < 256; ++c) w1[(size_t)c * 512 + o] = w->fc1.weight_host[(size_t)o * 256 + c];
+        ctx->p2_fc1.tc_dense = 1;
+        if ((rc = gconv_tc_pack(ctx, ctx->p2_fc1, w1))) return rc;
+        GLayer& L = ctx->p2_fc2_pad;
+        free_layer(L);
+        L.cin = 512; L.cout = 256; L.taps = 1; L.tc_dense = 1; L.prof_class = 7;
+        std::vector<float> w2((size_t)512 * 256, 0.f), b2(256, 0.f), sc(256, 0.f), sh(256, 0.f);
+        for (int o = 0; o < 128; ++o) {
+            for (int c = 0; c < 512; ++c) w2[(size_t)c * 256 + o] = w->fc2.weight_host[(size_t)o * 512 + c];
+            b2[o] = w->fc2.bias_host[o];
+            const double sdv = (double)w->bn2.weight_host[o] / sqrt((double)w->bn2.running_var_host[o] + 1e-5);
+            sc[o] = (float)sdv;
+            sh[o] = (float)((double)w->bn2.bias_host[o] - (double)w->bn2.running_mean_host[o] * sdv);
+        }
+        if ((rc = upload(&L.bias, b2))) return rc;
+        if ((rc = gconv_tc_pack(ctx, L, w2))) return rc;
+        free_bn(ctx->p2_bn2_pad);
+        ctx->p2_bn2_pad.c = 256;
+        if ((rc = upload(&ctx->p2_bn2_pad.scale, sc))) return rc;
+        if ((rc = upload(&ctx->p2_bn2_pad.shift, sh))) return rc;
+    }
     if ((rc = pack_conv(ctx, ctx->p2_fc3, w->fc3, 128, 4, 1))) return rc;   // packed [128][4]
     ctx->p2_init.prof_class = 4; ctx->p2_a.prof_class = 5; ctx->p2_b.prof_class = 6;
     ctx->p2_fc1.prof_class = 7; ctx->p2_fc2.prof_class = 7; ctx->p2_fc3.prof_class = 7;

@@ -93,6 +93,8 @@ struct yoho_ctx {
     // PartII
     bool has_p2 = false;
     GLayer p2_init, p2_a, p2_b, p2_fc1, p2_fc2, p2_fc3;
+    GLayer p2_fc2_pad;              // head layer 512 -> 128 zero-padded to 256 columns (one tensor-core N tile); p2_bn2_pad likewise
+    GBn p2_bn2_pad;
     GLayer p2_b_split[5];           // p2_b cut along its 13 taps (3,3,3,2,2): five partial GEMMs in one launch (only 22 row tiles at M = 2800)
     GBn p2_bn_init, p2_bn_a, p2_bn_b, p2_bn1, p2_bn2;
     // split-phase pair calls (pair.cu): FIFO of match counts in flight — pinned host slot + event per begun pair

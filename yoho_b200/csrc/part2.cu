@@ -10,6 +10,8 @@
 
 int gconv_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConvArgs* as, int n, cudaStream_t st);
 
+int gconv_split_bf16(yoho_ctx* ctx, const float* x, void* hi, void* lo, size_t n, cudaStream_t st);   // gconv_tc.cu
+
 namespace {
 
 // z0a[m][g][0:128] = relu(BN_init(concat_c(P_r FCGF_B, FCGF_A, P_r YOHO_B, YOHO_A)))   one CTA per match.
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) part2_assemble_kernel(const float* __rest
 
 // Last 1x1 conv (128 -> 4), quaternion normalisation, R(q) in float32 as the reference evaluates it on numpy
 // float32 scalars, R = R(q) @ Rgroup_f32[idx] and t = k0 - R k1 in float64.  One warp per match.
-__global__ void __launch_bounds__(128) part2_head_kernel(const float* __restrict__ h2, const float* __restrict__ w3,
+__global__ void __launch_bounds__(128) part2_head_kernel(const float* __restrict__ h2, int pitch, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, const int64_t* __restrict__ pairs,
                                                         const int64_t* __restrict__ pre_idx, const float* __restrict__ rot32,
                                                         const double* __restrict__ kps0, const double* __restrict__ kps1,
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128) part2_head_kernel(const float* __restrict
     if (m >= M) return;
     float h[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = lane; c < 128; c += 32) {
-        const float v = h2[(size_t)m * 128 + c];
+        const float v = h2[(size_t)m * pitch + c];
 #pragma unroll
         for (int o = 0; o < 4; ++o) h[o] = fmaf(v, w3[c * 4 + o], h[o]);   // w3 packed [128][4]
     }
@@ -123,7 +125,8 @@ __global__ void gather_kps_kernel(const double* __restrict__ kps0, const double*
 
 // z3[m][c] = bias[c] + z1[m][g = 0][c] + the five tap-split partial sums of the last group convolution, added in split order.
 __global__ void part2_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, const float* __restrict__ z1,
-                                    int zero_pos, float* __restrict__ z3, int n) {
+                                    int zero_pos, float* __restrict__ z3, unsigned short* __restrict__ z3_hi,
+                                    unsigned short* __restrict__ z3_lo, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index over [n][64]
     if (i >= n * 64) return;
     const int m = i >> 6, c4 = i & 63;
@@ -138,6 +141,18 @@ __global__ void part2_reduce_kernel(const float* __restrict__ part, const float*
     const float4 r = reinterpret_cast<const float4*>(z1 + ((size_t)m * 45 + zero_pos) * 256)[c4];
     acc.x = (acc.x + b.x) + r.x; acc.y = (acc.y + b.y) + r.y; acc.z = (acc.z + b.z) + r.z; acc.w = (acc.w + b.w) + r.w;
     reinterpret_cast<float4*>(z3)[i] = acc;
+    if (z3_hi) {                                                  // bf16 hi/lo image for the tensor-core head
+        const float f[4] = {acc.x, acc.y, acc.z, acc.w};
+        unsigned short h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat16 hh = __float2bfloat16_rn(f[k]);
+            h[k] = __bfloat16_as_ushort(hh);
+            l[k] = __bfloat16_as_ushort(__float2bfloat16_rn(f[k] - __bfloat162float(hh)));
+        }
+        reinterpret_cast<uint2*>(z3_hi)[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        reinterpret_cast<uint2*>(z3_lo)[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
 }
 
 constexpr int P2_CHUNK = 4096;
@@ -156,7 +171,7 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
     if (M == 0) return YOHO_OK;
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
-    const size_t per = sizeof(float) * ((size_t)YG * 128 + 45 * 256 * 2 + 13 * 512 + 256 + 512 + 128 + 5 * 256);
+    const size_t per = sizeof(float) * ((size_t)YG * 128 + 45 * 256 * 2 + 13 * 512 + 256 + 512 + 256 + 5 * 256 + 256);
     const int chunk = M < P2_CHUNK ? M : P2_CHUNK;
     if (int rc = yoho_ws_reserve(ctx, per * (size_t)chunk)) return rc;
     for (int s = 0; s < M; s += chunk) {
@@ -168,7 +183,11 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
         float* z3 = a2 + (size_t)n * 13 * 512;
         float* h1 = z3 + (size_t)n * 256;
         float* h2 = h1 + (size_t)n * 512;
-        float* zpart = h2 + (size_t)n * 128;         // [n][5][256] tap-split partial sums of the last group convolution
+        float* zpart = h2 + (size_t)n * 256;         // [n][5][256] tap-split partial sums of the last group convolution
+        unsigned short* z3_hi = (unsigned short*)(zpart + (size_t)n * 5 * 256);      // bf16 hi|lo image of z3 (tensor-core head)
+        unsigned short* z3_lo = z3_hi + (size_t)n * 256;
+        unsigned short* h1_hi = (unsigned short*)h1;
+        unsigned short* h1_lo = h1_hi + (size_t)n * 512;
         const int64_t* pr = pairs ? pairs + 2 * (size_t)s : nullptr;
         // without a match list the inputs are already per-match rows: advance them with the chunk
         const size_t adv = pairs ? 0 : (size_t)s * YF * YG;
@@ -214,20 +233,35 @@ extern "C" int yoho_part2_forward(yoho_ctx* ctx, const float* fcgf0, const float
                 t0 += ctx->p2_b_split[q].taps;
             }
             if (int rc = gconv_forward_grouped(ctx, Ls, fs, 5, st)) return rc;
-            part2_reduce_kernel<<<(n * 64 + 255) / 256, 256, 0, st>>>(zpart, ctx->p2_b.bias, z1, ctx->hop2_zero_pos, z3, n);
+            part2_reduce_kernel<<<(n * 64 + 255) / 256, 256, 0, st>>>(zpart, ctx->p2_b.bias, z1, ctx->hop2_zero_pos, z3, z3_hi, z3_lo, n);
             ctx->launches++;
-        } else if (int rc = gconv_forward(ctx, ctx->p2_b, a, st)) return rc;
+        } else {
+            if (int rc = gconv_forward(ctx, ctx->p2_b, a, st)) return rc;
+            if (tc) { if (int rc = gconv_split_bf16(ctx, z3, z3_hi, z3_lo, (size_t)n * 256, st)) return rc; }
+        }
         a.act_hi = a.act_lo = nullptr;
-        // head: 256 -> 512 -> 128 with BN+ReLU, as 1-tap layers
+        // head: 256 -> 512 -> 128 with BN+ReLU, as 1-tap layers.  Tensor-core path: two dense GEMMs (the second zero-padded to one
+        // 256-column tile, 128 valid), h2 rows 256 floats apart
         a.resid = nullptr; a.idx = ctx->d_idx_one; a.Jin = 1; a.Jout = 1;
+        const bool tc_head = tc && ctx->p2_fc1.w_hi && ctx->p2_fc2_pad.w_hi;
+        if (tc_head) {
+            a.act = nullptr; a.act_hi = z3_hi; a.act_lo = z3_lo; a.out_raw = nullptr; a.out_act = nullptr; a.out_hi = h1_hi; a.out_lo = h1_lo;
+            a.scale = ctx->p2_bn1.scale; a.shift = ctx->p2_bn1.shift;
+            if (int rc = gconv_forward(ctx, ctx->p2_fc1, a, st)) return rc;
+            a.act_hi = h1_hi; a.act_lo = h1_lo; a.out_hi = a.out_lo = nullptr; a.out_act = h2; a.n_valid = 128;
+            a.scale = ctx->p2_bn2_pad.scale; a.shift = ctx->p2_bn2_pad.shift;
+            if (int rc = gconv_forward(ctx, ctx->p2_fc2_pad, a, st)) return rc;
+            a.n_valid = 0; a.act_hi = a.act_lo = nullptr;
+        } else {
         a.act = z3; a.out_raw = nullptr; a.out_act = h1; a.scale = ctx->p2_bn1.scale; a.shift = ctx->p2_bn1.shift;
         if (int rc = gconv_forward(ctx, ctx->p2_fc1, a, st)) return rc;
         a.act = h1; a.out_act = h2; a.scale = ctx->p2_bn2.scale; a.shift = ctx->p2_bn2.shift;
         if (int rc = gconv_forward(ctx, ctx->p2_fc2, a, st)) return rc;
+        }
         const double* k0 = kps0;
         const double* k1 = kps1;
         if (!pairs && trans) { k0 = kps0 + 3 * (size_t)s; k1 = kps1 + 3 * (size_t)s; }
-        part2_head_kernel<<<(n + 3) / 4, 128, 0, st>>>(h2, ctx->p2_fc3.w, ctx->p2_fc3.bias, pr, pre_idx + s, ctx->d_rot32,
+        part2_head_kernel<<<(n + 3) / 4, 128, 0, st>>>(h2, tc_head ? 256 : 128, ctx->p2_fc3.w, ctx->p2_fc3.bias, pr, pre_idx + s, ctx->d_rot32,
                                                        k0, k1, quat + 4 * (size_t)s, trans ? trans + 12 * (size_t)s : nullptr, n);
         ctx->launches++;
     }
