@@ -294,14 +294,26 @@ __device__ __forceinline__ void load_matrix_frags(const float* __restrict__ F, b
         }
 }
 
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {     // packed conversions (cvt.rn.bf16x2.f32)
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // X0[b][m][c] (bf16 hi / lo) = sum_g F[m][g] x[b][c][g].  CTA = 4 warps = the four 16-row tiles of m; CTAs stride over keypoints.
-// The 7 680-byte [32][60] tile of a keypoint arrives by ONE 1-D TMA bulk copy into a ring of IN_ST shared-memory stages, issued
-// IN_ST keypoints ahead by one thread (mbarrier complete_tx), so the loads of the next keypoints are in flight while this one is
-// multiplied: the register-fed first version (B fragments straight from global memory) was latency bound at 52 us.
+//  * the 7 680-byte [32][60] tile of a keypoint arrives by ONE 1-D TMA bulk copy into a ring of IN_ST shared-memory stages, issued
+//    IN_ST keypoints ahead by one thread (mbarrier complete_tx): the register-fed first version (B fragments straight from global
+//    memory) was latency bound at 52 us;
+//  * the CTA converts the tile ONCE to packed bf16 hi / lo pairs (g even | g odd = exactly a B-fragment register) in a padded
+//    shared-memory image, and the four warps read their fragments from it with conflict-free 32-bit loads: with every warp
+//    splitting the whole tile itself (second version, 36 us) the kernel was bound by the FP32 -> bf16 conversion pipe, 4x redundantly.
 constexpr int IN_ST = 4;
+constexpr int CV_PITCH = 36;                  // 32 (g-pair) columns + 4: bank = 4 c + pair -> the 8 x 4 lanes of a fragment load hit 32 banks
 __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ F,
                                                             unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B) {
     __shared__ __align__(128) float xs[IN_ST][YF * YG];
+    __shared__ uint32_t cvh[YF * CV_PITCH], cvl[YF * CV_PITCH];
     __shared__ __align__(8) unsigned long long full[IN_ST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
     const int n_mine = blockIdx.x < B ? (B - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -313,40 +325,46 @@ __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __rest
             bulk_g2s(&xs[s][0], x + (size_t)(blockIdx.x + (size_t)s * gridDim.x) * YF * YG, YF * YG * 4, &full[s]);
         }
     }
+    for (int i = threadIdx.x; i < YF * CV_PITCH; i += 128) { cvh[i] = 0u; cvl[i] = 0u; }     // pair columns 30, 31 (g = 60..63) stay zero
     uint32_t ah[4][4], al[4][4];
     load_matrix_frags(F, false, w, lane, ah, al);
-    __syncthreads();                                               // barrier initialisation visible to the waiters
+    __syncthreads();                                               // barrier initialisation + zeroed padding visible
     for (int it = 0; it < n_mine; ++it) {
         const int b = blockIdx.x + it * gridDim.x, s = it % IN_ST;
         mbar_wait(&full[s], (it / IN_ST) & 1);
-        const float* xb = &xs[s][0];
+        // cooperative split of the tile: 960 (channel, g-pair) items, 7.5 per thread
+        for (int i = threadIdx.x; i < YF * (YG / 2); i += 128) {
+            const int c = i / (YG / 2), pr = i - c * (YG / 2);
+            const float2 v = *reinterpret_cast<const float2*>(&xs[s][c * YG + 2 * pr]);
+            split_pack(v.x, v.y, cvh[c * CV_PITCH + pr], cvl[c * CV_PITCH + pr]);
+        }
+        __syncthreads();                                           // image complete; stage s is free again
+        if (threadIdx.x == 0 && it + IN_ST < n_mine) {
+            mbar_expect_tx(&full[s], YF * YG * 4);
+            bulk_g2s(&xs[s][0], x + (size_t)(b + (size_t)IN_ST * gridDim.x) * YF * YG, YF * YG * 4, &full[s]);
+        }
         float acc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float* xc = xb + (8 * j + gid) * YG;             // column n = gid of n-tile j is channel 8j + gid
+        for (int t = 0; t < 4; ++t) {
+            uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int g0 = 16 * t + 2 * tig;
-                const float2 v0 = *reinterpret_cast<const float2*>(xc + g0);               // g0 <= 54: always valid
-                float2 v1 = make_float2(0.f, 0.f);
-                if (g0 + 8 < YG) v1 = *reinterpret_cast<const float2*>(xc + g0 + 8);        // 60 is even: the pair is valid together
-                uint32_t bh0, bl0, bh1, bl1;
-                split2(v0.x, v0.y, bh0, bl0);
-                split2(v1.x, v1.y, bh1, bl1);
-                mma_bf16(acc[j], ah[t], bh0, bh1);
-                mma_bf16(acc[j], al[t], bh0, bh1);
-                mma_bf16(acc[j], ah[t], bl0, bl1);
+            for (int j = 0; j < 4; ++j) {                          // column n = gid of n-tile j is channel 8j + gid
+                const int o = (8 * j + gid) * CV_PITCH + 8 * t + tig;
+                bh0[j] = cvh[o]; bl0[j] = cvl[o]; bh1[j] = cvh[o + 4]; bl1[j] = cvl[o + 4];
             }
+            // the n-tile is the INNER loop: consecutive mma.sync instructions belong to four independent accumulator chains
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16(acc[j], ah[t], bh0[j], bh1[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16(acc[j], al[t], bh0[j], bh1[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16(acc[j], ah[t], bl0[j], bl1[j]);
         }
-        __syncthreads();                                           // every warp has read stage s: refill it IN_ST keypoints ahead
-        if (threadIdx.x == 0 && it + IN_ST < n_mine) {
-            mbar_expect_tx(&full[s], YF * YG * 4);
-            bulk_g2s(&xs[s][0], x + (size_t)(b + (size_t)IN_ST * gridDim.x) * YF * YG, YF * YG * 4, &full[s]);
-        }
+        __syncthreads();                                           // every warp has read the image: the next keypoint may overwrite it
         // thread: rows m = 16w + gid (+8), channels 8j + 2 tig + {0,1}: one bf16 pair (4 bytes) per n-tile, hi and lo
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __rest
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint32_t ph, pl;
-                    split2(acc[j][2 * h], acc[j][2 * h + 1], ph, pl);
+                    split_pack(acc[j][2 * h], acc[j][2 * h + 1], ph, pl);
                     *reinterpret_cast<uint32_t*>(hi + o + 8 * j) = ph;
                     *reinterpret_cast<uint32_t*>(lo + o + 8 * j) = pl;
                 }
@@ -367,34 +385,33 @@ __global__ void __launch_bounds__(128) fourier_in_mma_kernel(const float* __rest
 
 // Output side: e[c][g] = bias4[c] + sum_m F[m][g] Y4[b][m][c] + x[b][c][g], then the tail of PartI_network.forward
 // (utils/network.py:98-103) and the matcher's numpy mean (tests/matcher.py:35).  Warp w owns the group elements 16w .. 16w+15.
-// Both tiles of a keypoint (Y4 coefficients and x) are prefetched by TMA bulk copies into a two-stage ring: Y4 row by row
-// (60 x 128 B, by the lanes of warp 0) into rows padded to 36 floats so that the B-fragment reads are bank-conflict free.
+// Both tiles of a keypoint (Y4 coefficients and x) are prefetched by two TMA bulk copies into a two-stage ring; the Y4 tile is
+// converted once per CTA to packed bf16 hi / lo pairs along m (= B-fragment registers) in a 40-column image (conflict-free reads).
 constexpr int FIN_ST = 2;
-constexpr int FIN_PITCH = 36;
+constexpr int FV_PITCH = 40;
 __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __restrict__ y4f, const float* __restrict__ F,
                                                                 const float* __restrict__ bias4, const float* __restrict__ x,
                                                                 float* __restrict__ eqv, float* __restrict__ inv,
                                                                 float* __restrict__ desc, int B) {
-    __shared__ __align__(128) float ys[FIN_ST][YG * FIN_PITCH];
+    __shared__ __align__(128) float ys[FIN_ST][YG * YF];
     __shared__ __align__(128) float xs[FIN_ST][YF * YG];
+    __shared__ uint32_t cvh[(YG / 2) * FV_PITCH], cvl[(YG / 2) * FV_PITCH];   // [m-pair][channel]; pairs 30, 31 (m = 60..63) read as zero
     __shared__ float es[YF][YG + 1];
     __shared__ float part[4][YF];
     __shared__ __align__(8) unsigned long long full[FIN_ST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
     const int n_mine = blockIdx.x < B ? (B - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    auto prefetch = [&](int it) {                                  // called by all lanes of warp 0
+    auto prefetch = [&](int it) {                                  // one thread
         const int s = it % FIN_ST;
         const size_t b = blockIdx.x + (size_t)it * gridDim.x;
-        if (lane == 0) {
-            mbar_expect_tx(&full[s], 2 * YF * YG * 4);
-            bulk_g2s(&xs[s][0], x + b * YF * YG, YF * YG * 4, &full[s]);
-        }
-        __syncwarp();                                              // expect_tx is posted before any row copy can complete
-        for (int m = lane; m < YG; m += 32) bulk_g2s(&ys[s][m * FIN_PITCH], y4f + (b * YG + m) * YF, YF * 4, &full[s]);
+        mbar_expect_tx(&full[s], 2 * YF * YG * 4);
+        bulk_g2s(&xs[s][0], x + b * YF * YG, YF * YG * 4, &full[s]);
+        bulk_g2s(&ys[s][0], y4f + b * YG * YF, YG * YF * 4, &full[s]);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < FIN_ST; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+        for (int it = 0; it < FIN_ST && it < n_mine; ++it) prefetch(it);
     }
     uint32_t ah[4][4], al[4][4];
     load_matrix_frags(F, true, w, lane, ah, al);                  // A[g][m] = F[m][g]
@@ -402,14 +419,15 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
 #pragma unroll
     for (int j = 0; j < 4; ++j) { bias[j][0] = __ldg(bias4 + 8 * j + 2 * tig); bias[j][1] = __ldg(bias4 + 8 * j + 2 * tig + 1); }
     __syncthreads();
-    if (w == 0)
-        for (int it = 0; it < FIN_ST && it < n_mine; ++it) prefetch(it);
     for (int it = 0; it < n_mine; ++it) {
         const size_t b = blockIdx.x + (size_t)it * gridDim.x;
         const int s = it % FIN_ST;
         mbar_wait(&full[s], (it / FIN_ST) & 1);
-        const float* yb = &ys[s][0];
-        const float* xb = &xs[s][0];
+        for (int i = threadIdx.x; i < (YG / 2) * YF; i += 128) {   // 960 (m-pair, channel) items
+            const int pr = i / YF, c = i - pr * YF;
+            split_pack(ys[s][(2 * pr) * YF + c], ys[s][(2 * pr + 1) * YF + c], cvh[pr * FV_PITCH + c], cvl[pr * FV_PITCH + c]);
+        }
+        __syncthreads();                                           // image complete (and the previous keypoint's es / part consumed)
         float acc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -417,22 +435,23 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const int m0 = 16 * t + 2 * tig;                       // coefficient rows m0, m0+1 and m0+8, m0+9
+            uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float* p = yb + 8 * j + gid;                 // column n = gid of n-tile j is channel 8j + gid
-                const float v00 = p[m0 * FIN_PITCH], v01 = p[(m0 + 1) * FIN_PITCH];
-                float v10 = 0.f, v11 = 0.f;
-                if (m0 + 8 < YG) { v10 = p[(m0 + 8) * FIN_PITCH]; v11 = p[(m0 + 9) * FIN_PITCH]; }
-                uint32_t bh0, bl0, bh1, bl1;
-                split2(v00, v01, bh0, bl0);
-                split2(v10, v11, bh1, bl1);
-                mma_bf16(acc[j], ah[t], bh0, bh1);
-                mma_bf16(acc[j], al[t], bh0, bh1);
-                mma_bf16(acc[j], ah[t], bl0, bl1);
+            for (int j = 0; j < 4; ++j) {                          // column n = gid of n-tile j is channel 8j + gid; rows m = 16t + 2 tig (+8)
+                const int o = (8 * t + tig) * FV_PITCH + 8 * j + gid;
+                const bool ok1 = 8 * t + tig + 4 < YG / 2;
+                bh0[j] = cvh[o]; bl0[j] = cvl[o];
+                bh1[j] = ok1 ? cvh[o + 4 * FV_PITCH] : 0u; bl1[j] = ok1 ? cvl[o + 4 * FV_PITCH] : 0u;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16(acc[j], ah[t], bh0[j], bh1[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16(acc[j], al[t], bh0[j], bh1[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16(acc[j], ah[t], bl0[j], bl1[j]);
         }
         // thread: group elements g = 16w + gid (+8), channels c = 8j + 2 tig + {0,1}
+        const float* xb = &xs[s][0];
         float e[2][8], ss[2] = {0.f, 0.f}, cs[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -460,8 +479,6 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
             cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
             cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
         }
-        __syncthreads();                                           // previous keypoint done with es / part; everyone done with stage s
-        if (w == 0 && it + FIN_ST < n_mine) prefetch(it + FIN_ST);
         if (gid == 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) part[w][8 * (k >> 1) + 2 * tig + (k & 1)] = cs[k];
@@ -475,7 +492,8 @@ __global__ void __launch_bounds__(128) part1_finalize_mma_kernel(const float* __
                 for (int k = 0; k < 8; ++k) es[8 * (k >> 1) + 2 * tig + (k & 1)][g] = e[h][k] / nrm;
             }
         }
-        __syncthreads();
+        __syncthreads();                                           // es / part complete; everyone is done with stage s and the image
+        if (threadIdx.x == 0 && it + FIN_ST < n_mine) prefetch(it + FIN_ST);
         float* out = eqv + b * YF * YG;
         for (int i = threadIdx.x; i < YF * YG; i += 128) out[i] = es[i / YG][i % YG];
         if (w == 2) {
