@@ -120,7 +120,8 @@ int yoho_part1_load_fourier(yoho_ctx* ctx, const float* F_host, int n_irreps, co
  * weights; otherwise, and for fewer than 128 keypoints, the direct layers of implementation 2 run). */
 int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
 
-/* Tuning knobs (defaults are the measured best).  key 0 = flag word: 1 = non-blocking producer protocol of the tensor-core GEMM
+/* Tuning knobs (defaults are the measured best).  key 1 = smallest accumulation length K (taps x Cin) for which the tensor-core GEMM
+ * keeps the hi*hi products and the cross products in two TMEM accumulators (shorter rounding chain, no epilogue overlap).  key 0 = flag word: 1 = non-blocking producer protocol of the tensor-core GEMM
  * (2: ignored); 256 = PartI entirely in the group-Fourier domain with the tcgen05 transform kernel (default on; cleared, or with
  * 512 set, implementation 3 runs the direct 13-tap tensor-core layers of implementation 2); 1024 = PartII last group convolution
  * as one GEMM instead of five tap-split partial GEMMs; 2048 = PartI output side (inverse transform of the layer-4 coefficients,

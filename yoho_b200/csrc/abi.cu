@@ -376,8 +376,9 @@ extern "C" int yoho_set_gconv_impl(yoho_ctx* ctx, int impl) {
 }
 
 extern "C" int yoho_set_tuning(yoho_ctx* ctx, int key, int value) {
-    YARG(ctx && key == 0);
-    ctx->tc_flags = value;
+    YARG(ctx && (key == 0 || key == 1));
+    if (key == 0) ctx->tc_flags = value;
+    else { YARG(value >= 0); ctx->split_min_k = value; }
     return YOHO_OK;
 }
 

@@ -54,6 +54,7 @@ struct yoho_ctx {
     int num_sms = 148;
     int gconv_impl = 0;
     int tc_flags = 3 | 256;         // tuning flags (include/yoho_b200.h yoho_set_tuning): bit0 noinc producers (gconv_tc.cu; bit1 ignored); 256 = all-Fourier PartI with the tcgen05 transform kernel (fourier_tc.cu)
+    int split_min_k = 1024;         // tensor-core GEMM: accumulation chains of at least this many K elements use the split accumulators (tuning key 1)
     int64_t launches = 0;
     // group tables on the device
     double* d_rot = nullptr;        // [60][9] f64

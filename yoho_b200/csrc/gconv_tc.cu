@@ -590,7 +590,7 @@ int gconv_tc_forward(yoho_ctx* ctx, const GLayer& L, const GConvArgs& a, cudaStr
     p.total_tiles = ((p.grp[0].m_total + BM - 1) / BM) * p.grp[0].n_tiles;
     // split accumulators only where the accumulation chain is long; short-K layers (PartI layers 1 and 4, the group-Fourier
     // GEMMs) keep two accumulator buffers in flight so that their (relatively heavy) epilogue overlaps the next tile's MMAs
-    const bool split = ctx->gconv_impl >= 2 && p.grp[0].nkb * BK >= 1024 && !a.omap;
+    const bool split = ctx->gconv_impl >= 2 && p.grp[0].nkb * BK >= ctx->split_min_k && !a.omap;
     if (bn == 256) return split ? tc_launch<256, true>(ctx, p, st) : tc_launch<256, false>(ctx, p, st);
     return split ? tc_launch<32, true>(ctx, p, st) : tc_launch<32, false>(ctx, p, st);
 }
