@@ -127,6 +127,23 @@ def exchange_part1_start(plan, local, template, device, rank=None):
     return got, reqs, nbytes
 
 
+def warmup_exchange(plan, device, rank=None):
+    """One 4-byte send/recv per (source, destination) pair of the plan: NCCL sets up its point-to-point channels lazily at the
+    first transfer between two ranks (~1 s measured), which a benchmark keeps out of its timed region with this call."""
+    rank = ydist.rank() if rank is None else rank
+    ops, keep = [], []
+    for s, d in sorted({(s, d) for s, d, _ in plan.transfers}):
+        if s == rank or d == rank:
+            t = torch.zeros((1,), dtype=torch.float32, device=device)
+            keep.append(t)
+            ops.append(tdist.P2POp(tdist.isend if s == rank else tdist.irecv, t, d if s == rank else s))
+    if ops:
+        for req in tdist.batch_isend_irecv(ops):
+            req.wait()
+    if torch.cuda.is_available() and device.type == "cuda":
+        torch.cuda.synchronize()
+
+
 def exchange_part1(plan, local, template, device, rank=None):
     """Blocking form of `exchange_part1_start`: returns ({fid: (eqv, desc)} received, bytes received)."""
     got, reqs, nbytes = exchange_part1_start(plan, local, template, device, rank)
