@@ -162,3 +162,35 @@ def test_rot_argmax_fullsize_vs_oracle(eng, tables):
         top2 = np.sort(c64.numpy(), axis=1)[:, -2:]
         assert np.all((top2[:, 1] - top2[:, 0]) <= 1e-5), "non-tie rotation index mismatch"
     assert (idx == pr["r"]).mean() > 0.9
+
+
+@pytest.mark.parametrize("Ka,Kb", [(256, 256), (600, 515), (1300, 2049), (5000, 5000)])
+def test_tensor_core_search_equals_simt_search(eng, Ka, Kb):
+    """The tcgen05 search with exact verification (csrc/match_tc.cu) against the FP32 SIMT search (tuning flag 16384): identical
+    argmins, identical distance BITS, identical mutual set — including exact duplicates (2 and 6 copies: lowest index wins, the
+    6-copy groups overflow the four-candidate window and go through the exhaustive re-scan), near-duplicates inside the
+    approximation window and a zero row."""
+    rs = np.random.RandomState(Ka + 3 * Kb)
+    dA = (rs.standard_normal((Ka, 32)) * 0.1).astype(np.float32)
+    dB = (rs.standard_normal((Kb, 32)) * 0.1).astype(np.float32)
+    n = min(Ka, Kb) // 3
+    dB[:n] = dA[rs.permutation(Ka)[:n]] + (rs.standard_normal((n, 32)) * 0.01).astype(np.float32)
+    dB[n:n + 20] = dB[:20]                                     # duplicates of B rows
+    for c in range(6):
+        dB[n + 20 + c * 5: n + 25 + c * 5] = dA[50:55]          # six copies of five A rows
+    dA[60:70] = dA[50:60]                                      # duplicate A rows
+    dB[n + 60: n + 70] = dB[n + 50: n + 60] + np.float32(1e-6)  # near-duplicates (inside the verification window)
+    dA[100] = 0.0
+    try:
+        pairs, cnt, nnA, nnB = eng.mutual_nn(dA, dB, want_nn=True)
+        d_tc, i_tc = eng.nn1(dA, dB)
+        eng.set_tuning(0, eng.DEFAULT_TUNING | 16384)
+        pairs2, cnt2, nnA2, nnB2 = eng.mutual_nn(dA, dB, want_nn=True)
+        d_simt, i_simt = eng.nn1(dA, dB)
+    finally:
+        eng.set_tuning(0, eng.DEFAULT_TUNING)
+    assert torch.equal(nnA, nnA2) and torch.equal(nnB, nnB2)
+    M = int(cnt.item())
+    assert M == int(cnt2.item()) and torch.equal(pairs[:M], pairs2[:M])
+    assert torch.equal(i_tc, i_simt) and torch.equal(d_tc.view(torch.int32), d_simt.view(torch.int32))
+    assert np.array_equal(_np(i_tc), O.nn1(dA, dB)[1].numpy()) or _check_nn(dA, dB, _np(i_tc)) >= 0

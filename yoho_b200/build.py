@@ -25,6 +25,7 @@ SOURCES = {
     "part1.cu": [],
     "part2.cu": [],
     "match.cu": [],
+    "match_tc.cu": [],
     "lift.cu": [],
     "fourier_tc.cu": [],
     "pair.cu": [],

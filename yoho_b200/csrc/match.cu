@@ -2,6 +2,10 @@
 // rotation-correlation argmax (tests/extractor.py:74-78).
 #include "common.cuh"
 
+size_t nn_tc_ws_bytes(int Ka, int Kb);                                                        // match_tc.cu
+int nn_pass_tc(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, unsigned long long* rowbest,
+               unsigned long long* colbest, void* ws, cudaStream_t st);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------------
@@ -274,16 +278,26 @@ __global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict
     }
 }
 
+// Tensor-core search with exact verification (match_tc.cu) when both sides have at least one 256-row tile; the FP32 SIMT kernel
+// otherwise (and as the test twin: tuning flag 16384).  Both produce the same keys.
+bool nn_use_tc(const yoho_ctx* ctx, int Ka, int Kb) {
+    return ctx->gconv_impl >= 1 && !(ctx->tc_flags & 16384) && Ka >= 256 && Kb >= 256;
+}
+
 int nn_pass(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, unsigned long long* rowbest,
-            unsigned long long* colbest, cudaStream_t st) {
+            unsigned long long* colbest, void* tc_ws, cudaStream_t st) {
     const size_t n = (size_t)Ka + Kb;   // rowbest and colbest are contiguous
     fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowbest, n, ~0ull);
+    ctx->launches++;
+    if (tc_ws && nn_use_tc(ctx, Ka, Kb)) return nn_pass_tc(ctx, dA, Ka, dB, Kb, rowbest, colbest, tc_ws, st);
     dim3 grid((Kb + MT - 1) / MT, (Ka + MT - 1) / MT);
     nn_tile_kernel<<<grid, 256, 0, st>>>(dA, Ka, dB, Kb, rowbest, colbest);
-    ctx->launches += 2;
+    ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
 }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
@@ -292,10 +306,11 @@ extern "C" int yoho_mutual_nn(yoho_ctx* ctx, const float* dA, int Ka, const floa
     YARG(ctx && dA && dB && pairs && n_pairs && Ka > 0 && Kb > 0);
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
-    if (int rc = yoho_ws_reserve(ctx, ((size_t)Ka + Kb) * 8)) return rc;
+    const size_t keys = align_up(((size_t)Ka + Kb) * 8, 1024);
+    if (int rc = yoho_ws_reserve(ctx, keys + nn_tc_ws_bytes(Ka, Kb))) return rc;
     unsigned long long* rowbest = (unsigned long long*)ctx->ws;
     unsigned long long* colbest = rowbest + Ka;
-    if (int rc = nn_pass(ctx, dA, Ka, dB, Kb, rowbest, colbest, st)) return rc;
+    if (int rc = nn_pass(ctx, dA, Ka, dB, Kb, rowbest, colbest, (char*)ctx->ws + keys, st)) return rc;
     mutual_compact_kernel<<<1, 1024, 0, st>>>(rowbest, Ka, colbest, Kb, pairs, n_pairs, nnA, nnB);
     ctx->launches++;
     YCHECK(cudaGetLastError());
@@ -307,9 +322,9 @@ extern "C" int yoho_nn1(yoho_ctx* ctx, const float* source, int m, const float* 
     YARG(ctx && source && target && m > 0 && n > 0 && F >= 1 && F <= YF);
     cudaStream_t st = (cudaStream_t)stream;
     YCHECK(cudaSetDevice(ctx->device));
-    const size_t keys = ((size_t)m + n) * 8;
-    const size_t padb = F == YF ? 0 : ((size_t)m + n) * YF * 4;
-    if (int rc = yoho_ws_reserve(ctx, keys + padb)) return rc;
+    const size_t keys = align_up(((size_t)m + n) * 8, 1024);
+    const size_t padb = F == YF ? 0 : align_up(((size_t)m + n) * YF * 4, 1024);
+    if (int rc = yoho_ws_reserve(ctx, keys + padb + nn_tc_ws_bytes(m, n))) return rc;
     unsigned long long* rowbest = (unsigned long long*)ctx->ws;
     unsigned long long* colbest = rowbest + m;
     const float* s = source;
@@ -322,7 +337,7 @@ extern "C" int yoho_nn1(yoho_ctx* ctx, const float* source, int m, const float* 
         ctx->launches += 2;
         s = ps; tg = pt;
     }
-    if (int rc = nn_pass(ctx, s, m, tg, n, rowbest, colbest, st)) return rc;
+    if (int rc = nn_pass(ctx, s, m, tg, n, rowbest, colbest, (char*)ctx->ws + keys + padb, st)) return rc;
     nn1_out_kernel<<<(m + 255) / 256, 256, 0, st>>>(rowbest, m, dist, idx);
     ctx->launches++;
     YCHECK(cudaGetLastError());
