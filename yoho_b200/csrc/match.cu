@@ -286,10 +286,10 @@ bool nn_use_tc(const yoho_ctx* ctx, int Ka, int Kb) {
 
 int nn_pass(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, unsigned long long* rowbest,
             unsigned long long* colbest, void* tc_ws, cudaStream_t st) {
+    if (tc_ws && nn_use_tc(ctx, Ka, Kb)) return nn_pass_tc(ctx, dA, Ka, dB, Kb, rowbest, colbest, tc_ws, st);
     const size_t n = (size_t)Ka + Kb;   // rowbest and colbest are contiguous
     fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowbest, n, ~0ull);
     ctx->launches++;
-    if (tc_ws && nn_use_tc(ctx, Ka, Kb)) return nn_pass_tc(ctx, dA, Ka, dB, Kb, rowbest, colbest, tc_ws, st);
     dim3 grid((Kb + MT - 1) / MT, (Ka + MT - 1) / MT);
     nn_tile_kernel<<<grid, 256, 0, st>>>(dA, Ka, dB, Kb, rowbest, colbest);
     ctx->launches++;
