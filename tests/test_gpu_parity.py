@@ -371,6 +371,56 @@ def test_device_draws(engine):
     assert int(status.item()) == 1
 
 
+def _philox4x32(ctr, key):
+    """Philox4x32-10 (csrc/estimator.cu) on python ints."""
+    c = list(ctr); k = list(key)
+    for _ in range(10):
+        p0 = 0xD2511F53 * c[0]
+        p1 = 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xffffffff, p0 & 0xffffffff]
+        k = [(k[0] + 0x9E3779B9) & 0xffffffff, (k[1] + 0xBB67AE85) & 0xffffffff]
+    return c
+
+
+def test_device_draws_equal_host_restatement(engine):
+    """yoho_c_draw against a line-by-line host restatement of its arithmetic (DR_statictic weights in float64 in the reference's
+    order, np.random.choice's cdf construction, searchsorted(side='right'), members in ascending match order, Philox4x32-10
+    counters): every triplet identical.  Pins the kernel across restructurings (histogram / bucket fill / search)."""
+    rs = np.random.RandomState(4)
+    for M, seed in ((2800, 11), (517, 12345678901), (40, 3)):
+        dr = np.where(rs.rand(M) < 0.5, 17, rs.randint(0, 60, M)).astype(np.int64)
+        iters = 1000
+        hyp, status = engine.c_draw(dr, iters, seed)
+        cnt = np.bincount(dr, minlength=60)
+        w = [0.0 if c < 2 else (c / 100.0) * (c / 100.0 - 0.01) * (c / 100.0 - 0.02) for c in cnt]
+        tot = 0.0
+        for x in w:
+            tot += x
+        if tot < 1e-4:
+            assert int(status.item()) == 1
+            continue
+        assert int(status.item()) == 0
+        pn = [x / tot for x in w]
+        cdf, c = [], 0.0
+        for x in pn:
+            c += x
+            cdf.append(c)
+        cdf = [x / cdf[-1] for x in cdf]
+        members = [np.nonzero(dr == b)[0] for b in range(60)]
+        key = (seed & 0xffffffff, (seed >> 32) & 0xffffffff)
+        want = np.zeros((iters, 3), np.int32)
+        for it in range(iters):
+            r = _philox4x32((it, 0, 0x59484f43, 0), key)
+            u = ((r[0] >> 5) * 67108864.0 + (r[1] >> 6)) / 9007199254740992.0
+            b = 0
+            while b < 59 and not (u < cdf[b]):
+                b += 1
+            r2 = _philox4x32((it, 1, 0x59484f43, 0), key)
+            n = int(cnt[b])
+            want[it] = [members[b][(r2[j] * n) >> 32] for j in range(3)]
+        assert np.array_equal(_np(hyp), want)
+
+
 def test_device_order_is_permutation(engine):
     for M in (1, 87, 2500):
         o = _np(engine.o_order(M, seed=3))

@@ -232,7 +232,7 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // E1 + draws.  Single CTA.  members are kept in ascending match order per bin, as the reference's lists.
-constexpr int DRAW_T = 512;       // 512 threads: 128 registers per thread, no spills (1024 threads spilled 1 KB per thread, 41 -> ? us)
+constexpr int DRAW_T = 512;       // 512 threads: 128 registers per thread (1024 threads spilled 1 KB per thread at the 64-register cap)
 __global__ void __launch_bounds__(DRAW_T, 1) c_draw_kernel(const int64_t* __restrict__ dr_index, int M, int iters,
                                                      unsigned long long seed, int32_t* __restrict__ members_ws,
                                                      int32_t* __restrict__ hyp, int32_t* __restrict__ status) {
@@ -242,16 +242,24 @@ __global__ void __launch_bounds__(DRAW_T, 1) c_draw_kernel(const int64_t* __rest
     __shared__ int ok_s, bad_s;
     __shared__ uint8_t bins[16384];            // rotation bin of every match (M <= 16384 staged; larger M reads global)
     const int t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
     if (t < YG) cnt[t] = 0;
     if (t == 0) bad_s = 0;
     __syncthreads();
-    for (int m = t; m < M; m += DRAW_T) {
-        // a rotation index outside [0,60) (a stale DR_index file) must not corrupt shared memory: clamp, and report status 2
-        const long long raw = dr_index[m];
-        const int b = raw < 0 ? 0 : (raw >= YG ? YG - 1 : (int)raw);
-        if (raw != (long long)b) bad_s = 1;
-        if (m < 16384) bins[m] = (uint8_t)b;
-        atomicAdd(&cnt[b], 1);
+    // histogram: lanes of a warp that hold the same bin elect one leader (match_any), so a dominant bin (half of the matches of a
+    // registered pair share the planted rotation) costs one shared-memory atomic per warp instead of 32 serialised ones
+    for (int m0 = 0; m0 < M; m0 += DRAW_T) {
+        const int m = m0 + t;
+        int b = 64;                                                      // lanes past the end form their own group
+        if (m < M) {
+            // a rotation index outside [0,60) (a stale DR_index file) must not corrupt shared memory: clamp, and report status 2
+            const long long raw = dr_index[m];
+            b = raw < 0 ? 0 : (raw >= YG ? YG - 1 : (int)raw);
+            if (raw != (long long)b) bad_s = 1;
+            if (m < 16384) bins[m] = (uint8_t)b;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (b < YG && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&cnt[b], __popc(peers));
     }
     __syncthreads();
     // DR_statictic weights (tests/estimator.py:41-51): the per-bin products in parallel, the two running sums serially in bin
@@ -289,19 +297,35 @@ __global__ void __launch_bounds__(DRAW_T, 1) c_draw_kernel(const int64_t* __rest
         __syncthreads();
         if (t < YG) cdf[t] = cdf[t] / last_s;
     }
-    // stable bucket fill: warp w owns bins w, w + 16, w + 32, w + 48 and walks the matches 32 at a time (ballot + prefix popcount keeps the
-    // members of a bin in ascending match order, like the reference's append loop)
+    // stable bucket fill (members of a bin in ascending match order, like the reference's append loop): per chunk of DRAW_T matches
+    // a match's position = bin start + matches of the bin in earlier chunks + in earlier warps of this chunk + in earlier lanes of
+    // its warp (match_any).  Replaces a per-bin scan of all matches (60 x M/32 dependent ballot steps).
     {
-        const int warp = t >> 5, lane = t & 31;
-        for (int bin = warp; bin < YG; bin += DRAW_T / 32) {
-            int o = off[bin];
-            for (int m0 = 0; m0 < M; m0 += 32) {
-                const int m = m0 + lane;
-                const bool hit = m < M && (m < 16384 ? (int)bins[m] : (int)dr_index[m]) == bin;   // (status 2 never reaches the draws)
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) members_ws[o + __popc(bal & ((1u << lane) - 1u))] = m;
-                o += __popc(bal);
+        __shared__ int wcnt[DRAW_T / 32][64];
+        __shared__ int run[64];
+        if (t < 64) run[t] = t < YG ? off[t] : 0;
+        for (int m0 = 0; m0 < M; m0 += DRAW_T) {
+            for (int i = t; i < (DRAW_T / 32) * 64; i += DRAW_T) (&wcnt[0][0])[i] = 0;
+            __syncthreads();
+            const int m = m0 + t;
+            const int b = m < M ? (m < 16384 ? (int)bins[m] : (int)min(max(dr_index[m], (int64_t)0), (int64_t)(YG - 1))) : 64;
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            const int before = __popc(peers & ((1u << lane) - 1u));
+            if (b < YG && before == 0) wcnt[warp][b] = __popc(peers);
+            __syncthreads();
+            if (b < YG) {
+                int pre = run[b];
+                for (int w = 0; w < warp; ++w) pre += wcnt[w][b];
+                members_ws[pre + before] = m;
             }
+            __syncthreads();
+            if (t < YG) {
+                int tot = 0;
+#pragma unroll
+                for (int w = 0; w < DRAW_T / 32; ++w) tot += wcnt[w][t];
+                run[t] += tot;
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -314,8 +338,14 @@ __global__ void __launch_bounds__(DRAW_T, 1) c_draw_kernel(const int64_t* __rest
                                    make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
         // 53-bit uniform in [0,1) like random_sample(): (a >> 5, b >> 6)
         const double u = ((double)(r.x >> 5) * 67108864.0 + (double)(r.y >> 6)) / 9007199254740992.0;
-        int bin = 0;
-        while (bin < YG - 1 && !(u < cdf[bin])) ++bin;     // searchsorted(cdf, u, side='right')
+        // searchsorted(cdf, u, side='right') over the non-decreasing cdf, clamped to the last bin: number of entries of
+        // cdf[0..58] that are <= u (binary search; the linear scan it replaces cost up to 59 FP64 compares per draw)
+        int lo_b = 0, hi_b = YG - 1;
+        while (lo_b < hi_b) {
+            const int mid = (lo_b + hi_b) >> 1;
+            if (u < cdf[mid]) hi_b = mid; else lo_b = mid + 1;
+        }
+        int bin = lo_b;
         while (cnt[bin] == 0 && bin > 0) --bin;            // unreachable guard
         const uint4 r2 = philox4x32(make_uint4((unsigned)it, 1u, 0x59484f43u, 0u),
                                     make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
