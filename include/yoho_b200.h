@@ -127,7 +127,10 @@ int yoho_set_gconv_impl(yoho_ctx* ctx, int impl);
  * as one GEMM instead of five tap-split partial GEMMs; 2048 = PartI output side (inverse transform of the layer-4 coefficients,
  * residual, norms, pools) on the tcgen05 transform machinery, 4096 = the same with shared-memory staged row accesses (both
  * parity-green, not faster: default off); 8192 = FP32 SIMT input / output side of the all-Fourier PartI instead of the register-resident
- * warp-MMA kernels (test twin); 16384 = FP32 SIMT 1-NN search instead of the tensor-core search with exact verification (test twin).
+ * warp-MMA kernels (test twin); 16384 = FP32 SIMT 1-NN search instead of the tensor-core search with exact verification (test twin);
+ * 32768 = the grouped tensor-core launches of PartI run as 2-CTA clusters whose CTAs take adjacent row tiles of one column
+ * tile and share every weight tile (each fetches half of it, TMA multicast to both; bit-identical results, measured neutral:
+ * 2.22 ms against 2.23 ms per 5000-keypoint PartI, so it stays off).
  * The warp-MMA / SIMT transform kernels of round 1 (flags 4-128) were removed. */
 int yoho_set_tuning(yoho_ctx* ctx, int key, int value);
 

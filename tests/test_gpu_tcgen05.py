@@ -167,6 +167,8 @@ def test_fourier_path_variants_agree(engine, tables):
         h = engine.part1(x)
         engine.set_tuning(0, 3 | 256 | 2048)  # all-Fourier with the output side (inverse transform, norms, pools) on tensor cores
         k2 = engine.part1(x)
+        engine.set_tuning(0, 3 | 256 | 32768)  # grouped GEMM launches as 2-CTA clusters sharing every weight tile by multicast
+        k3 = engine.part1(x)
         torch.cuda.synchronize()
     finally:
         engine.set_tuning(0, engine.DEFAULT_TUNING)
@@ -184,3 +186,5 @@ def test_fourier_path_variants_agree(engine, tables):
     assert e7 <= DESC_TOL and e8 <= 2e-5
     assert float(np.abs(_np(k2["inv"]) - ref["inv"].numpy()).max()) <= DESC_TOL
     assert float(np.abs(_np(k2["desc"]) - _np(g["desc"])).max()) <= 2e-5
+    # same products in the same order: the cluster launch is bit-identical to the default one
+    assert all(torch.equal(k3[k].view(torch.int32), g[k].view(torch.int32)) for k in ("eqv", "inv", "desc"))

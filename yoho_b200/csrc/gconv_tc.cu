@@ -88,10 +88,34 @@ struct TcArgs {
     const float* scale;
     const float* shift;
     int flags;                   // bit0: non-blocking producer completion (bit1, once a lane-map choice, is ignored)
+    int cluster;                 // 1: launched as 2-CTA clusters that share every weight tile (each CTA fetches half of it and multicasts
+                                 // it to both); `tile` then counts PAIR tiles: the two CTAs take row tiles 2 m and 2 m + 1 of one column tile
     // remapped output rows (group-Fourier layers): columns are groups of `ogroup`; group i of GEMM row (b,j) is written to
     // row b*out_J + omap[j*n_groups + i] of an [.., ogroup]-wide output.
     int ogroup, out_J;
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in `mask`, signalling the mbarrier at the same offset in each
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, unsigned long long* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(unsigned long long* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 
 __device__ __forceinline__ int find_group(const TcArgs& p, int tile) {
     int g = 0;
@@ -187,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bars->full[s], 128 + 1);   // 128 A-producer threads + the W producer's expect_tx arrive
-            mbar_init(&bars->empty[s], 1);        // tcgen05.commit
+            mbar_init(&bars->empty[s], p.cluster ? 2 : 1);   // tcgen05.commit (of both CTAs of a cluster: the peer writes into this stage too)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);    // tcgen05.commit
@@ -204,8 +228,13 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster) cluster_sync_all();           // the peer's barriers are initialised before anything is multicast to them
     const uint32_t tmem_base = bars->tmem_base;
     const int total_tiles = p.total_tiles;
+    // cluster mode: CTA pair c = blockIdx.x / 2 walks the pair tiles c, c + gridDim.x / 2, ...; rank r takes row tile 2 m + r
+    const int cs = p.cluster ? 2 : 1;
+    const int crank = p.cluster ? (int)cluster_ctarank() : 0;
+    const int tile0 = blockIdx.x / cs, tstride = gridDim.x / cs;
 
     if (warp < 4) {
         // ================= A producers =================
@@ -217,9 +246,9 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         const uint32_t c = (uint32_t)(lane & 3);          // 16-byte chunk of the 64-byte row this lane copies
         const int rsub = lane >> 2;                       // row within a group of 8
         uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < total_tiles; tile += tstride) {
             const TcGroup& G = p.grp[find_group(p, tile)];
-            const int m_tile = (tile - G.tile_begin) / G.n_tiles;
+            const int m_tile = ((tile - G.tile_begin) / G.n_tiles) * cs + crank;
             const int* idx_g = idx_s + G.idx_off;
             int rowbase[4], rowj[4];
             uint32_t okmask = 0;
@@ -265,18 +294,24 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         // ================= W producer (one thread) =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tstride) {
                 const TcGroup& G = p.grp[find_group(p, tile)];
                 const int n_tile = (tile - G.tile_begin) % G.n_tiles;
                 const uint8_t* wh = G.w_hi + (size_t)n_tile * G.nkb * W_TILE;
                 const uint8_t* wl = G.w_lo + (size_t)n_tile * G.nkb * W_TILE;
                 const uint32_t wbytes = (uint32_t)G.n_mma * (BK * 2);       // rows [0, n_mma) of the tile image
+                const uint32_t hbytes = wbytes / 2, hoff = (uint32_t)crank * hbytes;   // cluster mode: this CTA's half of the rows
                 for (int kb = 0; kb < G.nkb; ++kb) {
                     uint8_t* dst = stage_base + stage * STAGE_BYTES + 2 * A_TILE;
-                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    mbar_wait(&bars->empty[stage], phase ^ 1);             // cluster mode: BOTH CTAs have released this stage
                     mbar_expect_tx(&bars->full[stage], 2 * wbytes);
-                    bulk_g2s(dst, wh + (size_t)kb * W_TILE, wbytes, &bars->full[stage]);
-                    bulk_g2s(dst + W_TILE, wl + (size_t)kb * W_TILE, wbytes, &bars->full[stage]);
+                    if (p.cluster) {
+                        bulk_g2s_mc(dst + hoff, wh + (size_t)kb * W_TILE + hoff, hbytes, &bars->full[stage], (uint16_t)3);
+                        bulk_g2s_mc(dst + W_TILE + hoff, wl + (size_t)kb * W_TILE + hoff, hbytes, &bars->full[stage], (uint16_t)3);
+                    } else {
+                        bulk_g2s(dst, wh + (size_t)kb * W_TILE, wbytes, &bars->full[stage]);
+                        bulk_g2s(dst + W_TILE, wl + (size_t)kb * W_TILE, wbytes, &bars->full[stage]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -285,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tstride) {
                 mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -309,7 +344,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
                         tc_mma(d_lo, a_lo + adv, w_hi + adv, idesc, SPLIT ? first : 1u);
                         tc_mma(d_lo, a_hi + adv, w_lo + adv, idesc, 1u);
                     }
-                    tc_commit(&bars->empty[stage]);            // stage reusable once these MMAs have read it
+                    if (p.cluster) tc_commit_mc(&bars->empty[stage], (uint16_t)3);   // both CTAs learn that this CTA is done with the stage
+                    else tc_commit(&bars->empty[stage]);       // stage reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&bars->tmem_full[acc]);              // accumulator complete
@@ -322,10 +358,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < total_tiles; tile += tstride) {
             const TcGroup& G = p.grp[find_group(p, tile)];
-            const int m_tile = (tile - G.tile_begin) / G.n_tiles;
-            const int n_tile = (tile - G.tile_begin) - m_tile * G.n_tiles;
+            const int m_pair = (tile - G.tile_begin) / G.n_tiles;
+            const int n_tile = (tile - G.tile_begin) - m_pair * G.n_tiles;
+            const int m_tile = m_pair * cs + crank;
             const int* omap_s = idx_s + G.omap_off;
             const int row = m_tile * BM + q * 32 + lane;
             const bool ok = row < G.m_total;
@@ -449,6 +486,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_tc_kernel(const TcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster) cluster_sync_all();           // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -544,6 +582,20 @@ template <int BN, bool SPLIT>
 static int tc_launch(yoho_ctx* ctx, TcArgs& p, cudaStream_t st) {
     // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
     YCHECK(cudaFuncSetAttribute(gconv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, SPLIT>::SMEM_BYTES));
+    if (p.cluster) {
+        // 2-CTA clusters: total_tiles counts pair tiles
+        int pairs = p.total_tiles < ctx->num_sms / 2 ? p.total_tiles : ctx->num_sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = Cfg<BN, SPLIT>::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        YCHECK(cudaLaunchKernelEx(&cfg, gconv_tc_kernel<BN, SPLIT>, p));
+        ctx->launches++;
+        return YOHO_OK;
+    }
     const int grid = p.total_tiles < ctx->num_sms ? p.total_tiles : ctx->num_sms;
     gconv_tc_kernel<BN, SPLIT><<<grid, THREADS, Cfg<BN, SPLIT>::SMEM_BYTES, st>>>(p);
     ctx->launches++;
@@ -560,6 +612,7 @@ static void tc_fill_common(TcArgs& p, const GLayer& L, const GConvArgs& a, yoho_
     p.out_hi = (__nv_bfloat16*)a.out_hi; p.out_lo = (__nv_bfloat16*)a.out_lo;
     p.scale = a.scale; p.shift = a.shift;
     p.flags = ctx->tc_flags;
+    p.cluster = 0;
     p.ogroup = a.omap ? a.ogroup : L.cout; p.out_J = a.out_J;
 }
 
@@ -603,6 +656,8 @@ int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConv
     TcArgs p;
     tc_fill_common(p, *Ls[0], as[0], ctx);
     p.ngroups = n;
+    // 2-CTA clusters sharing every weight tile (tuning flag 32768): the weight tile is 2/3 of the operand bytes of a K block
+    p.cluster = (ctx->tc_flags & 32768) ? 1 : 0;
     int tiles = 0;
     for (int g = 0; g < n; ++g) {
         const GLayer& L = *Ls[g];
@@ -611,8 +666,11 @@ int gconv_tc_forward_grouped(yoho_ctx* ctx, const GLayer* const* Ls, const GConv
         YARG(L.cin == Ls[0]->cin && a.ogroup == as[0].ogroup && a.act_hi == as[0].act_hi && a.out_hi == as[0].out_hi &&
              a.out_raw == as[0].out_raw && a.B == as[0].B && a.Jin == as[0].Jin && L.cout % a.ogroup == 0 && (a.ogroup & (a.ogroup - 1)) == 0);
         tc_fill_group(p.grp[g], L, a, 256, tiles, g * 32, 160 + g * 40);   // <= 25 index entries, <= 5 x 8 output-row entries
-        tiles += ((p.grp[g].m_total + BM - 1) / BM) * p.grp[g].n_tiles;
+        const int m_tiles = (p.grp[g].m_total + BM - 1) / BM;
+        tiles += (p.cluster ? (m_tiles + 1) / 2 : m_tiles) * p.grp[g].n_tiles;
+        if (p.cluster && (p.grp[g].n_mma % 32)) p.cluster = -1;           // halves must be whole 16-row groups of the tile image
     }
+    if (p.cluster < 0) { yoho_set_error("cluster mode needs UMMA N multiples of 32"); return YOHO_ERR_ARG; }
     p.total_tiles = tiles;
     return tc_launch<256, false>(ctx, p, st);
 }
