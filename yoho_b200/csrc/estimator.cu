@@ -125,14 +125,17 @@ __device__ void kabsch3(const double* __restrict__ k0, const double* __restrict_
     }
 }
 
-__device__ __forceinline__ bool is_inlier(const double* __restrict__ k0, const double* __restrict__ k1, int m,
-                                          const double T[12], double thr2) {
-    const double x = k1[3 * m], y = k1[3 * m + 1], z = k1[3 * m + 2];
+// The inlier test on loaded coordinates: p = k1 point (x, y, z), q = k0 point (a, b, c).
+__device__ __forceinline__ bool inlier_xyz(double x, double y, double z, double a, double b, double c, const double T[12], double thr2) {
     const double px = fma(T[2], z, fma(T[1], y, T[0] * x)) + T[3];
     const double py = fma(T[6], z, fma(T[5], y, T[4] * x)) + T[7];
     const double pz = fma(T[10], z, fma(T[9], y, T[8] * x)) + T[11];
-    const double dx = k0[3 * m] - px, dy = k0[3 * m + 1] - py, dz = k0[3 * m + 2] - pz;
+    const double dx = a - px, dy = b - py, dz = c - pz;
     return fma(dz, dz, fma(dy, dy, dx * dx)) < thr2;
+}
+__device__ __forceinline__ bool is_inlier(const double* __restrict__ k0, const double* __restrict__ k1, int m,
+                                          const double T[12], double thr2) {
+    return inlier_xyz(k1[3 * m], k1[3 * m + 1], k1[3 * m + 2], k0[3 * m], k0[3 * m + 1], k0[3 * m + 2], T, thr2);
 }
 
 // Transform of hypothesis h.  YOHO-O: the given transform (through `order`).  YOHO-C: Kabsch of the triplet with the
@@ -153,22 +156,64 @@ __device__ __forceinline__ void hypothesis_transform(const double* __restrict__ 
     }
 }
 
-// One warp per hypothesis.  mode 0: Kabsch from hyp triplets; mode 1: given transforms (YOHO-O).
-__global__ void __launch_bounds__(256) score_kernel(const double* __restrict__ k0, const double* __restrict__ k1, int M,
-                                                   const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
-                                                   const double* __restrict__ fixed,
-                                                   const double* __restrict__ trans, const int32_t* __restrict__ order,
-                                                   int n_hyp, double thr2, int32_t* __restrict__ counts) {
-    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (h >= n_hyp) return;
-    double T[12];
-    hypothesis_transform(k0, k1, hyp, signs, fixed, trans, order, h, T);
-    int n = 0;
-    for (int m = lane; m < M; m += 32) n += is_inlier(k0, k1, m, T, thr2) ? 1 : 0;
+// Four hypotheses per CTA of eight warps.  Warp w < 4 forms the transform of hypothesis 4*blockIdx.x + w (Kabsch from the triplet,
+// or the given transform: YOHO-O); then every thread keeps all four transforms in registers and walks the matches with a stride
+// of 256, testing each loaded match against the four: one set of (stride-24-byte) coordinate loads serves four hypotheses, and
+// the kernel — one partial wave, bound by the latency of those loads — has eleven dependent rounds of them per thread at 2800
+// matches.  The transforms go to `T_all` for select_kernel.
+constexpr int SC_H = 4;
+constexpr int SC_T = 256;
+__global__ void __launch_bounds__(SC_T, 2) score_kernel(const double* __restrict__ k0, const double* __restrict__ k1, int M,
+                                                         const int32_t* __restrict__ hyp, const int8_t* __restrict__ signs,
+                                                         const double* __restrict__ fixed,
+                                                         const double* __restrict__ trans, const int32_t* __restrict__ order,
+                                                         int n_hyp, double thr2, double* __restrict__ T_all,
+                                                         int32_t* __restrict__ counts) {
+    __shared__ double Ts[SC_H][12];
+    __shared__ int cs[SC_T / 32][SC_H];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h0 = blockIdx.x * SC_H;
+    if (w < SC_H) {
+        double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        const int h = h0 + w;
+        if (h < n_hyp) hypothesis_transform(k0, k1, hyp, signs, fixed, trans, order, h, T);
+        if (lane == 0) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if (lane == 0) counts[h] = n;
+            for (int i = 0; i < 12; ++i) {
+                Ts[w][i] = T[i];
+                if (h < n_hyp) T_all[12 * (size_t)h + i] = T[i];
+            }
+        }
+    }
+    __syncthreads();
+    double T[SC_H][12];
+#pragma unroll
+    for (int q = 0; q < SC_H; ++q)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[q][i] = Ts[q][i];
+    int n[SC_H];
+#pragma unroll
+    for (int q = 0; q < SC_H; ++q) n[q] = 0;
+#pragma unroll 2
+    for (int m = threadIdx.x; m < M; m += SC_T) {
+        const double x = k1[3 * m], y = k1[3 * m + 1], z = k1[3 * m + 2];
+        const double a = k0[3 * m], b = k0[3 * m + 1], c = k0[3 * m + 2];
+#pragma unroll
+        for (int q = 0; q < SC_H; ++q) n[q] += inlier_xyz(x, y, z, a, b, c, T[q], thr2) ? 1 : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < SC_H; ++q) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) n[q] += __shfl_xor_sync(0xffffffffu, n[q], o);
+        if (lane == 0) cs[w][q] = n[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < SC_H && h0 + (int)threadIdx.x < n_hyp) {
+        int tot = 0;
+#pragma unroll
+        for (int v = 0; v < SC_T / 32; ++v) tot += cs[v][threadIdx.x];
+        counts[h0 + threadIdx.x] = tot;
+    }
 }
 
 // First strictly-best hypothesis, its transform and inlier mask.  Single CTA.
@@ -177,7 +222,7 @@ __global__ void __launch_bounds__(1024) select_kernel(const double* __restrict__
                                                      const double* __restrict__ fixed,
                                                      const double* __restrict__ trans, const int32_t* __restrict__ order,
                                                      int n_hyp, double thr2, const int32_t* __restrict__ counts,
-                                                     double* __restrict__ T_out, int32_t* __restrict__ best_iter,
+                                                     const double* __restrict__ T_all, double* __restrict__ T_out, int32_t* __restrict__ best_iter,
                                                      int32_t* __restrict__ n_inl, uint8_t* __restrict__ mask) {
     __shared__ unsigned long long red[32];
     __shared__ double Ts[12];
@@ -205,7 +250,9 @@ __global__ void __launch_bounds__(1024) select_kernel(const double* __restrict__
         *best_iter = bi;
         *n_inl = cnt > 0 ? cnt : 0;
         double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-        if (bi >= 0) hypothesis_transform(k0, k1, hyp, signs, fixed, trans, order, bi, T);
+        if (bi >= 0) {             // the transform score_kernel formed for this hypothesis (bit for bit what it scored)
+            for (int i = 0; i < 12; ++i) T[i] = T_all[12 * (size_t)bi + i];
+        }
         for (int i = 0; i < 12; ++i) { Ts[i] = T[i]; T_out[i] = T[i]; }
     }
     __syncthreads();
@@ -411,17 +458,16 @@ static int score_and_select(yoho_ctx* ctx, const double* k0, const double* k1, i
                             const int8_t* signs, const double* fixed, const double* trans, const int32_t* order, int n_hyp,
                             double dist,
                             double* T, int32_t* best_iter, int32_t* n_inl, uint8_t* mask, int32_t* counts, cudaStream_t st) {
-    int32_t* cnt = counts;
-    if (!cnt) {
-        if (int rc = yoho_ws_reserve(ctx, (size_t)(n_hyp + 1) * 4)) return rc;
-        cnt = (int32_t*)ctx->ws;
-    }
+    // workspace: the transforms of all hypotheses (96 B each), then the counts when the caller does not want them
+    if (int rc = yoho_ws_reserve(ctx, (size_t)(n_hyp + 1) * (96 + 4))) return rc;
+    double* T_all = (double*)ctx->ws;
+    int32_t* cnt = counts ? counts : (int32_t*)(T_all + 12 * (size_t)(n_hyp + 1));
     const double thr2 = dist * dist;
     if (n_hyp > 0) {
-        score_kernel<<<(n_hyp + 7) / 8, 256, 0, st>>>(k0, k1, M, hyp, signs, fixed, trans, order, n_hyp, thr2, cnt);
+        score_kernel<<<(n_hyp + SC_H - 1) / SC_H, SC_T, 0, st>>>(k0, k1, M, hyp, signs, fixed, trans, order, n_hyp, thr2, T_all, cnt);
         ctx->launches++;
     }
-    select_kernel<<<1, 1024, 0, st>>>(k0, k1, M, hyp, signs, fixed, trans, order, n_hyp, thr2, cnt, T, best_iter, n_inl, mask);
+    select_kernel<<<1, 1024, 0, st>>>(k0, k1, M, hyp, signs, fixed, trans, order, n_hyp, thr2, cnt, T_all, T, best_iter, n_inl, mask);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;

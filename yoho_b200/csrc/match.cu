@@ -170,111 +170,131 @@ __global__ void pad32_kernel(const float* __restrict__ src, int n, int F, float*
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Rotation-correlation argmax.  One CTA per match: both [32x60] tiles (7680 B each, contiguous in HBM)
-// are staged in shared memory by two 1-D TMA bulk copies that signal one mbarrier; 225 threads form the
-// 60x60 channel-contracted product of the two tiles in 4x4 register tiles, 240 threads then sum, per rotation,
-// its 60 permuted entries (4 quarters of the group axis x 60 rotations); the quarters are added in a fixed order
-// and warp 0 takes the argmax with lowest-index tie-break (torch.argmax).
+// Rotation-correlation argmax.  Persistent CTAs (four per SM) walk the matches; both [32x60] tiles of a match (7680 B each,
+// contiguous in HBM) are staged in shared memory by two 1-D TMA bulk copies that signal one mbarrier, TWO matches ahead of the
+// one being computed (two stages).  225 threads form the 60x60 channel-contracted product of the two tiles in 4x4 register tiles,
+// 240 threads then sum, per rotation, its 60 permuted entries (4 quarters of the group axis x 60 rotations); the quarters are
+// added in a fixed order and warp 0 takes the argmax with lowest-index tie-break (torch.argmax).  Bound by shared-memory
+// bandwidth (ncu: l1tex 86 %, 2 x 4 wavefronts of 16-byte reads per 16 FMAs in step 1), not by the loads: 38 us per 2800 matches.
 // ---------------------------------------------------------------------------------------------------
 constexpr int TILE_FLOATS = YF * YG;           // 1920
 constexpr int TILE_BYTES = TILE_FLOATS * 4;    // 7680
+constexpr int ROT_ST = 2;
+
+struct __align__(128) RotSmem {
+    float s1[ROT_ST][TILE_FLOATS];
+    float s2[ROT_ST][TILE_FLOATS];
+    float S[YG][YG + 1];                       // S[g][g'] = sum_f des2[f][g] * des1[f][g']
+    float part[4][64];
+    uint8_t pt[YG * YG];                       // pt[g*60 + a] = P[a][g]
+    unsigned long long bar[ROT_ST];
+};
 
 __global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict__ des1, const int64_t* __restrict__ rows1,
                                                         const float* __restrict__ des2, const int64_t* __restrict__ rows2,
                                                         int row_stride, int M, const uint8_t* __restrict__ perm_t,
                                                         int64_t* __restrict__ idx_out, float* __restrict__ cor_out) {
-    __shared__ __align__(128) float s1[TILE_FLOATS];
-    __shared__ __align__(128) float s2[TILE_FLOATS];
-    __shared__ __align__(16) uint8_t pt[YG * YG];   // pt[g*60 + a] = P[a][g]
-    __shared__ float S[YG][YG + 1];                  // S[g][g'] = sum_f des2[f][g] * des1[f][g']
-    __shared__ float part[4][64];
-    __shared__ __align__(8) unsigned long long bar;
-    const int m = blockIdx.x;
+    extern __shared__ __align__(128) uint8_t rot_smem_raw[];
+    RotSmem& sm = *reinterpret_cast<RotSmem*>(rot_smem_raw);
     const int t = threadIdx.x;
-    const int64_t r1 = rows1 ? rows1[(size_t)m * row_stride] : m;
-    const int64_t r2 = rows2 ? rows2[(size_t)m * row_stride] : m;
-    const uint32_t bar_a = smem_u32(&bar);
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_a));
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
-    }
-    __syncthreads();
-    if (t == 0) {
+    auto fetch = [&](int m, int st) {          // thread 0: both tiles of match m -> stage st
+        const int64_t r1 = rows1 ? rows1[(size_t)m * row_stride] : m;
+        const int64_t r2 = rows2 ? rows2[(size_t)m * row_stride] : m;
+        const uint32_t bar_a = smem_u32(&sm.bar[st]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_a), "r"(2 * TILE_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                         smem_u32(s1)),
+                         smem_u32(sm.s1[st])),
                      "l"(des1 + (size_t)r1 * TILE_FLOATS), "r"(TILE_BYTES), "r"(bar_a)
                      : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                         smem_u32(s2)),
+                         smem_u32(sm.s2[st])),
                      "l"(des2 + (size_t)r2 * TILE_FLOATS), "r"(TILE_BYTES), "r"(bar_a)
                      : "memory");
-    }
-    for (int i = t; i < YG * YG / 4; i += 256) reinterpret_cast<uint32_t*>(pt)[i] = __ldg(reinterpret_cast<const uint32_t*>(perm_t) + i);
-    {   // wait for both tiles (phase 0)
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(ok)
-                : "r"(bar_a), "r"(0)
-                : "memory");
+    };
+    if (t == 0) {
+        for (int st = 0; st < ROT_ST; ++st) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.bar[st])));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+        for (int st = 0; st < ROT_ST; ++st) {
+            const int m = blockIdx.x + st * gridDim.x;
+            if (m < M) fetch(m, st);
         }
     }
+    for (int i = t; i < YG * YG / 4; i += 256) reinterpret_cast<uint32_t*>(sm.pt)[i] = __ldg(reinterpret_cast<const uint32_t*>(perm_t) + i);
     __syncthreads();
-    // Step 1: the 60x60 channel-contracted product S[g][g'] = sum_f des2[f][g] des1[f][g'], 4x4 register tiles (225 threads):
-    // two 16-byte shared reads per 16 FMAs.  Step 2: cor[a] = sum_g S[g][P[a][g]] — 60 gathered adds per rotation instead of
-    // 1920 gathered multiply-adds (the permutation acts on the group axis only, so it commutes with the channel sum).
-    if (t < 225) {
-        const int gi = (t / 15) * 4, gj = (t % 15) * 4;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-        for (int f = 0; f < YF; ++f) {
-            const float4 u = *reinterpret_cast<const float4*>(s2 + f * YG + gi);
-            const float4 v = *reinterpret_cast<const float4*>(s1 + f * YG + gj);
-            const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
+    int it = 0;
+    for (int m = blockIdx.x; m < M; m += gridDim.x, ++it) {
+        const int st = it % ROT_ST;
+        {   // wait for both tiles of this match
+            const uint32_t bar_a = smem_u32(&sm.bar[st]), par = (uint32_t)(it / ROT_ST) & 1u;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(ok)
+                    : "r"(bar_a), "r"(par)
+                    : "memory");
+            }
+        }
+        const float* s1 = sm.s1[st];
+        const float* s2 = sm.s2[st];
+        // Step 1: the 60x60 channel-contracted product S[g][g'] = sum_f des2[f][g] des1[f][g'], 4x4 register tiles (225 threads):
+        // two 16-byte shared reads per 16 FMAs.  Step 2: cor[a] = sum_g S[g][P[a][g]] — 60 gathered adds per rotation instead of
+        // 1920 gathered multiply-adds (the permutation acts on the group axis only, so it commutes with the channel sum).
+        if (t < 225) {
+            const int gi = (t / 15) * 4, gj = (t % 15) * 4;
+            float acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
-        }
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+            for (int f = 0; f < YF; ++f) {
+                const float4 u = *reinterpret_cast<const float4*>(s2 + f * YG + gi);
+                const float4 v = *reinterpret_cast<const float4*>(s1 + f * YG + gj);
+                const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) S[gi + i][gj + j] = acc[i][j];
-    }
-    __syncthreads();
-    const int a = t & 63, q = t >> 6;   // rotation a, quarter q of the group axis
-    float acc = 0.f;
-    if (a < YG) {
-#pragma unroll
-        for (int g = q * 15; g < q * 15 + 15; ++g) acc += S[g][pt[g * YG + a]];
-    }
-    part[q][a] = acc;
-    __syncthreads();
-    if (t < 32) {
-        float best = -INFINITY;
-        int bi = 0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int aa = t + 32 * h;
-            if (aa < YG) {
-                const float c = ((part[0][aa] + part[1][aa]) + part[2][aa]) + part[3][aa];
-                if (cor_out) cor_out[(size_t)m * YG + aa] = c;
-                if (c > best) { best = c; bi = aa; }
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
             }
-        }
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sm.S[gi + i][gj + j] = acc[i][j];
         }
-        if (t == 0) idx_out[m] = bi;
+        __syncthreads();                       // S complete; the tiles of this stage are consumed
+        if (t == 0) {
+            const int mn = m + ROT_ST * gridDim.x;
+            if (mn < M) fetch(mn, st);
+        }
+        const int a = t & 63, q = t >> 6;      // rotation a, quarter q of the group axis
+        float acc = 0.f;
+        if (a < YG) {
+#pragma unroll
+            for (int g = q * 15; g < q * 15 + 15; ++g) acc += sm.S[g][sm.pt[g * YG + a]];
+        }
+        sm.part[q][a] = acc;
+        __syncthreads();
+        if (t < 32) {
+            float best = -INFINITY;
+            int bi = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int aa = t + 32 * h;
+                if (aa < YG) {
+                    const float c = ((sm.part[0][aa] + sm.part[1][aa]) + sm.part[2][aa]) + sm.part[3][aa];
+                    if (cor_out) cor_out[(size_t)m * YG + aa] = c;
+                    if (c > best) { best = c; bi = aa; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (t == 0) idx_out[m] = bi;
+        }
     }
 }
 
@@ -349,7 +369,10 @@ extern "C" int yoho_rot_argmax(yoho_ctx* ctx, const float* des1, const int64_t* 
     YARG(ctx && des1 && des2 && idx && M >= 0 && row_stride >= 1);
     if (M == 0) return YOHO_OK;
     YCHECK(cudaSetDevice(ctx->device));
-    rot_argmax_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(des1, rows1, des2, rows2, row_stride, M, ctx->d_perm_t, idx, cor_out);
+    // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
+    YCHECK(cudaFuncSetAttribute(rot_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RotSmem)));
+    const int grid = M < 4 * ctx->num_sms ? M : 4 * ctx->num_sms;
+    rot_argmax_kernel<<<grid, 256, sizeof(RotSmem), (cudaStream_t)stream>>>(des1, rows1, des2, rows2, row_stride, M, ctx->d_perm_t, idx, cor_out);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;

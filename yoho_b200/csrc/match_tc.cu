@@ -396,11 +396,8 @@ int nn_pass_tc(yoho_ctx* ctx, const float* dA, int Ka, const float* dB, int Kb, 
     if (nsplit > NN_MAX_SPLIT) nsplit = NN_MAX_SPLIT;
     p.nsplit = nsplit;
     dim3 grid(mt * nsplit, 2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        YCHECK(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
-        attr_set = true;
-    }
+    // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
+    YCHECK(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     nn_tc_kernel<<<grid, NN_THREADS, NN_SMEM, st>>>(p);
     dim3 gver(((Ka > Kb ? Ka : Kb) + 7) / 8, 2);
     nn_verify_kernel<<<gver, 256, 0, st>>>(p);
