@@ -170,16 +170,16 @@ __global__ void pad32_kernel(const float* __restrict__ src, int n, int F, float*
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Rotation-correlation argmax.  Persistent CTAs (four per SM) walk the matches; both [32x60] tiles of a match (7680 B each,
-// contiguous in HBM) are staged in shared memory by two 1-D TMA bulk copies that signal one mbarrier, TWO matches ahead of the
-// one being computed (two stages).  225 threads form the 60x60 channel-contracted product of the two tiles in 4x4 register tiles,
-// 240 threads then sum, per rotation, its 60 permuted entries (4 quarters of the group axis x 60 rotations); the quarters are
-// added in a fixed order and warp 0 takes the argmax with lowest-index tie-break (torch.argmax).  Bound by shared-memory
-// bandwidth (ncu: l1tex 86 %, 2 x 4 wavefronts of 16-byte reads per 16 FMAs in step 1), not by the loads: 38 us per 2800 matches.
+// Rotation-correlation argmax.  Persistent 64-thread CTAs (four per SM) walk the matches; both [32x60] tiles of a match (7680 B
+// each, contiguous in HBM) are staged in shared memory by two 1-D TMA bulk copies that signal one mbarrier, TWO matches ahead of
+// the one being computed (two stages).  60 threads form the 60x60 channel-contracted product of the two tiles in 6x10 register
+// blocks, then each sums, for its rotation, the 60 permuted entries (four quarters of the group axis, added in a fixed order);
+// the argmax takes the lowest index among equal values (torch.argmax).
 // ---------------------------------------------------------------------------------------------------
 constexpr int TILE_FLOATS = YF * YG;           // 1920
 constexpr int TILE_BYTES = TILE_FLOATS * 4;    // 7680
 constexpr int ROT_ST = 2;
+constexpr int ROT_T = 64;
 
 struct __align__(128) RotSmem {
     float s1[ROT_ST][TILE_FLOATS];
@@ -190,10 +190,10 @@ struct __align__(128) RotSmem {
     unsigned long long bar[ROT_ST];
 };
 
-__global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict__ des1, const int64_t* __restrict__ rows1,
-                                                        const float* __restrict__ des2, const int64_t* __restrict__ rows2,
-                                                        int row_stride, int M, const uint8_t* __restrict__ perm_t,
-                                                        int64_t* __restrict__ idx_out, float* __restrict__ cor_out) {
+__global__ void __launch_bounds__(ROT_T) rot_argmax_kernel(const float* __restrict__ des1, const int64_t* __restrict__ rows1,
+                                                          const float* __restrict__ des2, const int64_t* __restrict__ rows2,
+                                                          int row_stride, int M, const uint8_t* __restrict__ perm_t,
+                                                          int64_t* __restrict__ idx_out, float* __restrict__ cor_out) {
     extern __shared__ __align__(128) uint8_t rot_smem_raw[];
     RotSmem& sm = *reinterpret_cast<RotSmem*>(rot_smem_raw);
     const int t = threadIdx.x;
@@ -219,8 +219,9 @@ __global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict
             if (m < M) fetch(m, st);
         }
     }
-    for (int i = t; i < YG * YG / 4; i += 256) reinterpret_cast<uint32_t*>(sm.pt)[i] = __ldg(reinterpret_cast<const uint32_t*>(perm_t) + i);
+    for (int i = t; i < YG * YG / 4; i += ROT_T) reinterpret_cast<uint32_t*>(sm.pt)[i] = __ldg(reinterpret_cast<const uint32_t*>(perm_t) + i);
     __syncthreads();
+    const int gi = (t / 6) * 6, gj = (t % 6) * 10;       // this thread's 6 x 10 block of S (t < 60)
     int it = 0;
     for (int m = blockIdx.x; m < M; m += gridDim.x, ++it) {
         const int st = it % ROT_ST;
@@ -237,63 +238,74 @@ __global__ void __launch_bounds__(256) rot_argmax_kernel(const float* __restrict
         }
         const float* s1 = sm.s1[st];
         const float* s2 = sm.s2[st];
-        // Step 1: the 60x60 channel-contracted product S[g][g'] = sum_f des2[f][g] des1[f][g'], 4x4 register tiles (225 threads):
-        // two 16-byte shared reads per 16 FMAs.  Step 2: cor[a] = sum_g S[g][P[a][g]] — 60 gathered adds per rotation instead of
-        // 1920 gathered multiply-adds (the permutation acts on the group axis only, so it commutes with the channel sum).
-        if (t < 225) {
-            const int gi = (t / 15) * 4, gj = (t % 15) * 4;
-            float acc[4][4];
+        // Step 1: the 60x60 channel-contracted product S[g][g'] = sum_f des2[f][g] des1[f][g'] in 6x10 register blocks (60 threads):
+        // eight 8-byte shared reads per 60 FMAs (a 4x4 blocking — two 16-byte reads per 16 FMAs — was bound by shared-memory
+        // wavefronts at 38 us per 2800 matches; the sum over f runs in the same order, so S is unchanged bit for bit).
+        if (t < YG) {
+            float acc[6][10];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
+                for (int j = 0; j < 10; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
             for (int f = 0; f < YF; ++f) {
-                const float4 u = *reinterpret_cast<const float4*>(s2 + f * YG + gi);
-                const float4 v = *reinterpret_cast<const float4*>(s1 + f * YG + gj);
-                const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
+                float uu[6], vv[10];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 3; ++i) {
+                    const float2 u = *reinterpret_cast<const float2*>(s2 + f * YG + gi + 2 * i);
+                    uu[2 * i] = u.x; uu[2 * i + 1] = u.y;
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
+                for (int j = 0; j < 5; ++j) {
+                    const float2 v = *reinterpret_cast<const float2*>(s1 + f * YG + gj + 2 * j);
+                    vv[2 * j] = v.x; vv[2 * j + 1] = v.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sm.S[gi + i][gj + j] = acc[i][j];
+                for (int j = 0; j < 10; ++j) sm.S[gi + i][gj + j] = acc[i][j];
         }
         __syncthreads();                       // S complete; the tiles of this stage are consumed
         if (t == 0) {
             const int mn = m + ROT_ST * gridDim.x;
             if (mn < M) fetch(mn, st);
         }
-        const int a = t & 63, q = t >> 6;      // rotation a, quarter q of the group axis
-        float acc = 0.f;
-        if (a < YG) {
+        // Step 2: cor[a] = sum_g S[g][P[a][g]] — 60 gathered adds per rotation instead of 1920 gathered multiply-adds (the
+        // permutation acts on the group axis only, so it commutes with the channel sum); four quarter sums added in a fixed order.
+        float c = -INFINITY;
+        if (t < YG) {
+            float q4[4];
 #pragma unroll
-            for (int g = q * 15; g < q * 15 + 15; ++g) acc += sm.S[g][sm.pt[g * YG + a]];
+            for (int q = 0; q < 4; ++q) {
+                float acc = 0.f;
+#pragma unroll
+                for (int g = q * 15; g < q * 15 + 15; ++g) acc += sm.S[g][sm.pt[g * YG + t]];
+                q4[q] = acc;
+            }
+            c = ((q4[0] + q4[1]) + q4[2]) + q4[3];
+            if (cor_out) cor_out[(size_t)m * YG + t] = c;
         }
-        sm.part[q][a] = acc;
-        __syncthreads();
-        if (t < 32) {
-            float best = -INFINITY;
-            int bi = 0;
+        // argmax with lowest-index tie-break: inside each warp, then warp 1's (rotations 32..59) against warp 0's
+        float best = c;
+        int bi = t;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int aa = t + 32 * h;
-                if (aa < YG) {
-                    const float c = ((sm.part[0][aa] + sm.part[1][aa]) + sm.part[2][aa]) + sm.part[3][aa];
-                    if (cor_out) cor_out[(size_t)m * YG + aa] = c;
-                    if (c > best) { best = c; bi = aa; }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (t == 0) idx_out[m] = bi;
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (t == 32) { sm.part[0][0] = best; sm.part[0][1] = __int_as_float(bi); }
+        __syncthreads();                       // also: every read of S is done before the next match's step 1 writes it
+        if (t == 0) {
+            const float ob = sm.part[0][0];
+            const int oi = __float_as_int(sm.part[0][1]);
+            if (ob > best) bi = oi;            // equal values keep the lower index (warp 0's)
+            idx_out[m] = bi;
         }
     }
 }
@@ -372,7 +384,7 @@ extern "C" int yoho_rot_argmax(yoho_ctx* ctx, const float* des1, const int64_t* 
     // per-device attribute; cheap enough to set on every launch (one process may drive several devices)
     YCHECK(cudaFuncSetAttribute(rot_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RotSmem)));
     const int grid = M < 4 * ctx->num_sms ? M : 4 * ctx->num_sms;
-    rot_argmax_kernel<<<grid, 256, sizeof(RotSmem), (cudaStream_t)stream>>>(des1, rows1, des2, rows2, row_stride, M, ctx->d_perm_t, idx, cor_out);
+    rot_argmax_kernel<<<grid, ROT_T, sizeof(RotSmem), (cudaStream_t)stream>>>(des1, rows1, des2, rows2, row_stride, M, ctx->d_perm_t, idx, cor_out);
     ctx->launches++;
     YCHECK(cudaGetLastError());
     return YOHO_OK;
